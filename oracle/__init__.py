@@ -1,0 +1,178 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of the CPU oracle (oracle/tinyad_oracle.hh).
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this.
+The product package tinyad_b200 never does.
+"""
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# term kinds (keep in sync with oracle_capi.cc)
+SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
+EDGE_DIRICHLET1D, QUADRATIC2D, REPEATED_HANDLE, TRIG_MIX2D = 5, 6, 7, 8
+SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
+
+
+class _Term(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("n_elements", ctypes.c_int64),
+                ("conn", ctypes.c_void_p), ("data", ctypes.c_void_p), ("n_data", ctypes.c_int)]
+
+
+def build(force=False):
+    """Compile liboracle.so (g++ -O3 -fopenmp); idempotent."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cc", "tinyad_oracle.hh", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        L.oracle_scalar_eval.restype = ctypes.c_void_p
+        L.oracle_scalar_eval.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+        L.oracle_vector_eval.restype = ctypes.c_void_p
+        L.oracle_vector_eval.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_int]
+        L.oracle_last_error.restype = ctypes.c_char_p
+        L.oracle_result_f.restype = ctypes.c_double
+        L.oracle_result_f.argtypes = [ctypes.c_void_p]
+        for n in ("nnz", "rows", "cols", "g_size", "r_size"):
+            f = getattr(L, "oracle_result_" + n)
+            f.restype = ctypes.c_int64
+            f.argtypes = [ctypes.c_void_p]
+        L.oracle_result_copy.argtypes = [ctypes.c_void_p] * 6
+        L.oracle_result_phases.argtypes = [ctypes.c_void_p] * 3
+        L.oracle_result_free.argtypes = [ctypes.c_void_p]
+        L.oracle_project.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
+        L.oracle_scalar_case.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+@dataclass
+class Term:
+    kind: int
+    conn: np.ndarray   # (n_elements, valence) int32
+    data: np.ndarray   # (n_elements, n_data) float64
+
+
+@dataclass
+class Result:
+    f: float = 0.0
+    g: np.ndarray = None
+    r: np.ndarray = None
+    outer: np.ndarray = None
+    inner: np.ndarray = None
+    values: np.ndarray = None
+    shape: tuple = (0, 0)
+    phases: dict = field(default_factory=dict)
+
+
+def _terms_array(terms):
+    keep = []
+    arr = (_Term * len(terms))()
+    for i, t in enumerate(terms):
+        conn = np.ascontiguousarray(t.conn, dtype=np.int32).reshape(len(t.conn), -1)
+        data = np.ascontiguousarray(t.data, dtype=np.float64).reshape(len(t.conn), -1)
+        keep += [conn, data]
+        arr[i] = _Term(t.kind, conn.shape[0], conn.ctypes.data, data.ctypes.data, data.shape[1])
+    return arr, keep
+
+
+def _collect(L, h, want_matrix):
+    if not h:
+        raise RuntimeError(L.oracle_last_error().decode())
+    try:
+        res = Result(f=L.oracle_result_f(h))
+        ng, nr = L.oracle_result_g_size(h), L.oracle_result_r_size(h)
+        res.g = np.empty(ng)
+        res.r = np.empty(nr)
+        rows, cols, nnz = L.oracle_result_rows(h), L.oracle_result_cols(h), L.oracle_result_nnz(h)
+        res.shape = (rows, cols)
+        if want_matrix:
+            res.outer = np.empty(cols + 1, dtype=np.int32)
+            res.inner = np.empty(nnz, dtype=np.int32)
+            res.values = np.empty(nnz)
+        L.oracle_result_copy(h, res.g.ctypes.data, res.r.ctypes.data,
+                             res.outer.ctypes.data if want_matrix else None,
+                             res.inner.ctypes.data if want_matrix else None,
+                             res.values.ctypes.data if want_matrix else None)
+        t = (ctypes.c_double * 3)()
+        n = (ctypes.c_int64 * 2)()
+        L.oracle_result_phases(h, t, n)
+        res.phases = {"eval_s": t[0], "accumulate_s": t[1], "compress_s": t[2],
+                      "n_decomposed": n[0], "n_rebuilt": n[1]}
+        return res
+    finally:
+        L.oracle_result_free(h)
+
+
+EVAL, GRADIENT, DERIVATIVES, HESSIAN_PROJ = 0, 1, 2, 3
+
+
+def scalar_eval(d, n_vertices, terms, mode, x, eps=1e-9, n_threads=-1):
+    """Reference semantics of ScalarFunction::eval* (Detail/ScalarFunctionImpl.hh:256-416).
+    H is returned as compressed-column arrays (== CSR of the structurally symmetric Hessian)."""
+    L = lib()
+    arr, keep = _terms_array(terms)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    assert x.size == d * n_vertices
+    h = L.oracle_scalar_eval(d, n_vertices, len(terms), ctypes.addressof(arr), mode, x.ctypes.data, eps, n_threads)
+    return _collect(L, h, mode >= 2)
+
+
+V_EVAL, V_JACOBIAN, V_SOS, V_SOS_DERIVATIVES = 0, 1, 2, 3
+
+
+def vector_eval(d, n_vertices, terms, mode, x, n_threads=-1):
+    """Reference semantics of VectorFunction::eval* (Detail/VectorFunctionImpl.hh:143-301). J is CSC (m x n)."""
+    L = lib()
+    arr, keep = _terms_array(terms)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    h = L.oracle_vector_eval(d, n_vertices, len(terms), ctypes.addressof(arr), mode, x.ctypes.data, n_threads)
+    return _collect(L, h, mode in (1, 3))
+
+
+def project(H, eps=1e-9):
+    """project_positive_definite (Utils/HessianProjection.hh:48-101) on one dense symmetric matrix."""
+    A = np.array(H, dtype=np.float64, order="C")
+    code = lib().oracle_project(A.shape[0], A.ctypes.data, eps)
+    if code < 0:
+        raise RuntimeError(lib().oracle_last_error().decode())
+    return A, code
+
+
+def scalar_case(name, params, k, n_out_max=3):
+    """Run one known-answer scalar case; returns list of (val, grad[k], Hess[k,k])."""
+    p = np.zeros(16)
+    p[:len(params)] = params
+    out = np.zeros(n_out_max * (1 + k + k * k) + 64)
+    n = lib().oracle_scalar_case(name.encode(), p.ctypes.data, out.ctypes.data)
+    if n < 0:
+        raise RuntimeError(f"scalar case {name}: code {n} {lib().oracle_last_error().decode()}")
+    res, o = [], 0
+    for _ in range(n):
+        val = out[o]
+        grad = out[o + 1:o + 1 + k].copy()
+        hess = out[o + 1 + k:o + 1 + k + k * k].reshape(k, k).copy()
+        res.append((val, grad, hess))
+        o += 1 + k + k * k
+    return res
+
+
+def default_threads():
+    return lib().oracle_default_threads()
+
+
+def max_threads():
+    return lib().oracle_max_threads()
