@@ -1,0 +1,159 @@
+/* tinyad_b200 -- C ABI of the B200 runtime behind TinyAD's per-element derivative path.
+ *
+ * This is the drop-in boundary.  In the reference the seam is the
+ * objective-term interface that ScalarFunction / VectorFunction call
+ *   ScalarObjectiveTermBase  include/TinyAD/Detail/ScalarObjectiveTerm.hh:22-44
+ *   VectorObjectiveTermBase  include/TinyAD/Detail/VectorObjectiveTerm.hh:22-45
+ * and everything below it (parallel_for over elements, serial accumulation, triplets,
+ * setFromTriplets).  Here everything below that seam runs on the GPU:
+ *   - the element kernels that contain the user's element functor are templates instantiated
+ *     by nvcc in the USER's translation unit (tinyad_b200/include/TinyAD/Kernels.cuh) and are handed
+ *     to this runtime as one plain function pointer per term (tad_launch_fn);
+ *   - this library (libtinyad_b200.so) is functor-independent: it owns device memory, the
+ *     one-time recorded element->variable table, the fixed CSR pattern and scatter maps, the
+ *     batched PSD projection, the assembly kernels and the reductions.
+ * No C++ or torch types cross this boundary; all functions return a tad_status.
+ * There is no CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef TINYAD_B200_H
+#define TINYAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tad_status
+{
+    TAD_OK = 0,
+    TAD_INVALID_ARGUMENT = 1,      /* size mismatch etc.  (TINYAD_ASSERT_EQ in ScalarFunctionImpl.hh:262,292,325,388) */
+    TAD_NONFINITE_DERIVATIVE = 2,  /* non-finite element gradient / Hessian (ScalarObjectiveTerm.hh:210,252-253) */
+    TAD_CUDA_ERROR = 3,
+    TAD_TOO_MANY_VARIABLES = 4,    /* "Too many variables requested via element.variables(...)" (Element.hh:237-238) */
+    TAD_INDEX_OUT_OF_RANGE = 5,    /* variable handle outside [0, n_handles) (Element.hh:159-170) */
+    TAD_NOT_SUPPORTED = 6,
+    TAD_OUT_OF_MEMORY = 7
+} tad_status;
+
+/* What an element kernel launch computes. */
+typedef enum tad_mode
+{
+    TAD_MODE_RECORD = 0,  /* run the functor on a recorder element: which handles does each element touch, in first-access order (RecorderElement, ScalarFunctionImpl.hh:106-129) */
+    TAD_MODE_PASSIVE = 1, /* plain double        (ScalarObjectiveTerm.hh:162-186) */
+    TAD_MODE_FIRST = 2,   /* Scalar<k,false>     (ScalarObjectiveTerm.hh:188-222, VectorObjectiveTerm.hh:180-243) */
+    TAD_MODE_SECOND = 3   /* Scalar<k,true>      (ScalarObjectiveTerm.hh:224-278) */
+} tad_mode;
+
+/* Arguments of one element-kernel launch.  All pointers are device pointers.  The per-element
+ * outputs are written structure-of-arrays with leading dimension `stride` (>= n_elements):
+ *   val [m * stride + e]                       m < max(1, outputs_per_element)
+ *   grad[(m * k + i) * stride + e]             i < k = d * valence
+ *   hess[s * stride + e]                       s < k(k+1)/2, tile order (Detail/HessLayout.hh), scalar terms only
+ *   rec_handles[j * stride + e], rec_counts[e] j < valence, -1 = unused            (TAD_MODE_RECORD)
+ */
+typedef struct tad_launch_args
+{
+    int32_t mode;               /* tad_mode */
+    int32_t dedup;              /* 1: some element of this term touches a handle twice -> element kernels search */
+    int64_t n_elements;
+    int64_t stride;
+    const int64_t* elem_handles; /* element handle values, NULL = identity 0..n-1 (TinyAD::range) */
+    const double* x;            /* n_vars doubles, x[d * handle + i] (Element.hh:165) */
+    int64_t n_handles;          /* number of variable handles (n_vars / d) */
+    double* val;
+    double* grad;
+    double* hess;
+    int32_t* rec_handles;
+    int32_t* rec_counts;
+    int32_t* error_flags;       /* device int32[8], OR-ed: bit per tad_status */
+    void* stream;               /* cudaStream_t */
+} tad_launch_args;
+
+/* Launches the element kernel of one term; returns a tad_status (TAD_CUDA_ERROR on launch failure). */
+typedef int (*tad_launch_fn)(void* user, const tad_launch_args* args);
+
+typedef struct tad_function_s* tad_function;
+
+/* Options (tad_function_set_option). */
+#define TAD_OPT_ASSEMBLY 1      /* 0 = FP64 atomics (default), 1 = deterministic gather in element order */
+#define TAD_OPT_CHUNK_ELEMENTS 2 /* max elements per element-kernel launch (staging size); 0 = whole term */
+#define TAD_ASSEMBLY_ATOMIC 0
+#define TAD_ASSEMBLY_GATHER 1
+
+const char* tad_last_error(void);
+int tad_device_count(int* count);
+
+/* scalar_function<d>(range(n_handles)) / vector_function<d>(...)   ScalarFunctionImpl.hh:418-442, VectorFunctionImpl.hh:303-323 */
+int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector_function, int device, tad_function* out);
+void tad_function_destroy(tad_function f);
+int tad_function_set_option(tad_function f, int option, int64_t value);
+int tad_function_get_stream(tad_function f, void** stream);
+
+/* add_elements<N>(range, functor) / add_elements<N, M>(...)   ScalarFunctionImpl.hh:63-100, VectorFunctionImpl.hh:64-101
+ * elem_handles_host may be NULL (identity).  The term keeps `user` and calls user_free(user) on destroy.
+ * Runs the recording pass (TAD_MODE_RECORD) immediately. */
+int tad_function_add_term(tad_function f, int valence, int outputs_per_element, int64_t n_elements,
+                          const int64_t* elem_handles_host, tad_launch_fn launch, void* user, void (*user_free)(void*));
+
+int64_t tad_function_n_vars(tad_function f);
+int64_t tad_function_n_elements(tad_function f);
+int64_t tad_function_n_outputs(tad_function f); /* vector functions: number of residuals */
+
+/* Fixed sparsity pattern (built on first use).  Scalar functions: Hessian, n_vars x n_vars, compressed
+ * rows == compressed columns (structurally symmetric), inner indices ascending, explicit zeros kept --
+ * the arrays Eigen's setFromTriplets produces (ScalarFunctionImpl.hh:398).  Vector functions: the Jacobian,
+ * n_outputs x n_vars, compressed COLUMN storage like the reference's SparseMatrix (VectorFunctionImpl.hh:186-187). */
+int tad_function_pattern(tad_function f, int64_t* n_outer, int64_t* nnz);
+int tad_function_pattern_copy(tad_function f, int32_t* outer_host, int32_t* inner_host);
+int tad_function_pattern_device(tad_function f, const int32_t** outer_dev, const int32_t** inner_dev);
+
+/* Recorded element -> handle table of term t (host copy, valence x n_elements row-major by slot; -1 unused). */
+int tad_function_term_table(tad_function f, int term, int32_t* handles_host);
+
+/* ---- ScalarFunction evaluation: device-resident x / g / H values ------------------------------------
+ * eval                      ScalarFunctionImpl.hh:256-273   (f only; INFINITY short-circuit across terms)
+ * eval_with_gradient        ScalarFunctionImpl.hh:284-299
+ * eval_with_derivatives     ScalarFunctionImpl.hh:316-336   (project = 0)
+ * eval_with_hessian_proj    ScalarFunctionImpl.hh:378-399   (project = 1, eps as HessianProjection.hh:48-101)
+ * Outputs are overwritten.  f_host receives the value (one 8-byte D2H).  H_values_dev has nnz doubles. */
+int tad_eval(tad_function f, const double* x_dev, double* f_host);
+int tad_eval_with_gradient(tad_function f, const double* x_dev, double* f_host, double* g_dev);
+int tad_eval_with_derivatives(tad_function f, const double* x_dev, double* f_host, double* g_dev, double* H_values_dev,
+                              int project_hessian, double projection_eps);
+
+/* Same with HOST buffers (H2D of x, D2H of g and H values inside the call). */
+int tad_eval_host(tad_function f, const double* x_host, double* f_host);
+int tad_eval_with_gradient_host(tad_function f, const double* x_host, double* f_host, double* g_host);
+int tad_eval_with_derivatives_host(tad_function f, const double* x_host, double* f_host, double* g_host,
+                                   double* H_values_host, int project_hessian, double projection_eps);
+
+/* ---- VectorFunction evaluation ------------------------------------------------------------------------
+ * eval                                   VectorFunctionImpl.hh:143-159     r (n_outputs)
+ * eval_with_jacobian                     VectorFunctionImpl.hh:170-188     r, J values (fixed CSC pattern)
+ * eval_sum_of_squares                    VectorFunctionImpl.hh:254-266     f = sum r^2
+ * eval_sum_of_squares_with_derivatives   VectorFunctionImpl.hh:268-283     f = r.r, g = 2 J^T r, r, J */
+int tad_veval(tad_function f, const double* x_dev, double* r_dev);
+int tad_veval_with_jacobian(tad_function f, const double* x_dev, double* r_dev, double* J_values_dev);
+int tad_veval_sum_of_squares(tad_function f, const double* x_dev, double* f_host);
+int tad_veval_sum_of_squares_with_derivatives(tad_function f, const double* x_dev, double* f_host, double* g_dev,
+                                              double* r_dev, double* J_values_dev);
+
+/* ---- building blocks exposed for tests / reuse ---- */
+/* Batched in-place projection of n packed symmetric k x k matrices (SoA, tile order, leading dim stride):
+ * project_positive_definite (Utils/HessianProjection.hh:48-101) incl. both early-outs and the eps < 0 mode.
+ * counts_dev (optional, int64[2]) receives #decomposed and #rebuilt. */
+int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int64_t* counts_dev, void* stream);
+
+/* Statistics of the last eval_with_derivatives (host): [0] elements eigendecomposed, [1] elements rebuilt. */
+int tad_function_projection_stats(tad_function f, int64_t* stats2);
+
+/* Milliseconds of the phases of the last evaluation, measured with CUDA events on the function's stream:
+ * [0] element kernels, [1] projection, [2] assembly, [3] total. */
+int tad_function_last_timings(tad_function f, float* ms4);
+int tad_function_set_timing(tad_function f, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYAD_B200_H */

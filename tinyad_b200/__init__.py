@@ -1,0 +1,278 @@
+"""tinyad_b200 -- B200-native implementation of TinyAD's per-element sparse derivative path.
+
+The product is C++/CUDA: a header facade with TinyAD's surface (tinyad_b200/include/TinyAD) over a
+C-ABI runtime (include/tinyad_b200.h, libtinyad_b200.so).  This Python module is only the ctypes
+harness that tests and bench.py use to drive it: it loads the two in-tree libraries, exposes the
+C ABI one-to-one, and wraps the element functors compiled in csrc/energies.cu.
+
+There is no CPU fallback: importing works without a GPU (so the symbol/ABI tests can run), but
+creating a function raises unless a CUDA device is present.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+TAD_OK = 0
+STATUS_NAMES = {0: "TAD_OK", 1: "TAD_INVALID_ARGUMENT", 2: "TAD_NONFINITE_DERIVATIVE", 3: "TAD_CUDA_ERROR",
+                4: "TAD_TOO_MANY_VARIABLES", 5: "TAD_INDEX_OUT_OF_RANGE", 6: "TAD_NOT_SUPPORTED", 7: "TAD_OUT_OF_MEMORY"}
+ASSEMBLY_ATOMIC, ASSEMBLY_GATHER = 0, 1
+OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS = 1, 2
+
+# term kinds of csrc/energies.cu
+SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
+EDGE_DIRICHLET1D, QUADRATIC2D, REPEATED_HANDLE, TRIG_MIX2D = 5, 6, 7, 8
+SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
+
+# every symbol include/tinyad_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "tad_last_error", "tad_device_count", "tad_function_create", "tad_function_destroy", "tad_function_set_option",
+    "tad_function_get_stream", "tad_function_add_term", "tad_function_n_vars", "tad_function_n_elements",
+    "tad_function_n_outputs", "tad_function_pattern", "tad_function_pattern_copy", "tad_function_pattern_device",
+    "tad_function_term_table", "tad_eval", "tad_eval_with_gradient", "tad_eval_with_derivatives", "tad_eval_host",
+    "tad_eval_with_gradient_host", "tad_eval_with_derivatives_host", "tad_veval", "tad_veval_with_jacobian",
+    "tad_veval_sum_of_squares", "tad_veval_sum_of_squares_with_derivatives", "tad_project_batch",
+    "tad_function_projection_stats", "tad_function_last_timings", "tad_function_set_timing",
+]
+
+_rt = None
+_en = None
+
+
+class TinyADError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+def runtime():
+    """ctypes handle of libtinyad_b200.so (the C ABI).  Fails loudly if the CUDA library is missing."""
+    global _rt
+    if _rt is None:
+        so = _build.RUNTIME_SO
+        if not os.path.exists(so):
+            raise ImportError(f"{so} is missing: run `python -m tinyad_b200.build` (needs nvcc); there is no CPU fallback")
+        L = ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
+        vp, i64, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double
+        L.tad_last_error.restype = ctypes.c_char_p
+        L.tad_function_create.argtypes = [ctypes.c_int, i64, ctypes.c_int, ctypes.c_int, vp]
+        L.tad_function_destroy.argtypes = [vp]
+        L.tad_function_destroy.restype = None
+        L.tad_function_set_option.argtypes = [vp, ctypes.c_int, i64]
+        L.tad_function_get_stream.argtypes = [vp, vp]
+        for n in ("n_vars", "n_elements", "n_outputs"):
+            fn = getattr(L, "tad_function_" + n)
+            fn.restype = i64
+            fn.argtypes = [vp]
+        L.tad_function_pattern.argtypes = [vp, vp, vp]
+        L.tad_function_pattern_copy.argtypes = [vp, vp, vp]
+        L.tad_function_pattern_device.argtypes = [vp, vp, vp]
+        L.tad_function_term_table.argtypes = [vp, ctypes.c_int, vp]
+        L.tad_eval.argtypes = [vp, vp, vp]
+        L.tad_eval_with_gradient.argtypes = [vp, vp, vp, vp]
+        L.tad_eval_with_derivatives.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, dbl]
+        L.tad_eval_host.argtypes = [vp, vp, vp]
+        L.tad_eval_with_gradient_host.argtypes = [vp, vp, vp, vp]
+        L.tad_eval_with_derivatives_host.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, dbl]
+        L.tad_veval.argtypes = [vp, vp, vp]
+        L.tad_veval_with_jacobian.argtypes = [vp, vp, vp, vp]
+        L.tad_veval_sum_of_squares.argtypes = [vp, vp, vp]
+        L.tad_veval_sum_of_squares_with_derivatives.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.tad_project_batch.argtypes = [ctypes.c_int, i64, i64, vp, dbl, vp, vp]
+        L.tad_function_projection_stats.argtypes = [vp, vp]
+        L.tad_function_last_timings.argtypes = [vp, vp]
+        L.tad_function_set_timing.argtypes = [vp, ctypes.c_int]
+        L.tad_device_count.argtypes = [vp]
+        _rt = L
+    return _rt
+
+
+def energies():
+    """ctypes handle of libtinyad_b200_energies.so (element functors of the tests / benchmark)."""
+    global _en
+    if _en is None:
+        runtime()
+        so = _build.ENERGIES_SO
+        if not os.path.exists(so):
+            raise ImportError(f"{so} is missing: run `python -m tinyad_b200.build`")
+        L = ctypes.CDLL(so)
+        vp, i64 = ctypes.c_void_p, ctypes.c_int64
+        L.tadx_last_error.restype = ctypes.c_char_p
+        L.tadx_create.argtypes = [ctypes.c_int, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.tadx_destroy.argtypes = [vp]
+        L.tadx_destroy.restype = None
+        L.tadx_handle.argtypes = [vp]
+        L.tadx_handle.restype = vp
+        L.tadx_add_term.argtypes = [vp, ctypes.c_int, i64, vp, ctypes.c_int, vp, ctypes.c_int]
+        _en = L
+    return _en
+
+
+def _check(status):
+    if status != TAD_OK:
+        raise TinyADError(status, runtime().tad_last_error().decode())
+
+
+def _ptr(a):
+    """Device or host pointer of a torch tensor / numpy array / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+class Function:
+    """A ScalarFunction<d> / VectorFunction<d> built from the functors in csrc/energies.cu.
+
+    Thin mirror of the C++ facade (tinyad_b200/include/TinyAD/ScalarFunction.hh); every method is one call
+    through the C ABI.  `*_host` variants take / return numpy arrays, the others device pointers
+    (torch CUDA tensors)."""
+
+    def __init__(self, d, n_vertices, is_vector=False, device=0, assembly=ASSEMBLY_ATOMIC):
+        self.d, self.n_vertices, self.is_vector = d, n_vertices, is_vector
+        self.n_vars = d * n_vertices
+        self._x = ctypes.c_void_p()
+        E = energies()
+        if E.tadx_create(d, n_vertices, int(is_vector), device, assembly, ctypes.byref(self._x)) != 0:
+            raise TinyADError(-1, E.tadx_last_error().decode())
+        self.h = E.tadx_handle(self._x)
+        self._pattern = None
+
+    def close(self):
+        if self._x:
+            energies().tadx_destroy(self._x)
+            self._x = ctypes.c_void_p()
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_term(self, kind, conn, data):
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        conn = conn.reshape(len(conn), -1)
+        data = np.ascontiguousarray(data, dtype=np.float64).reshape(len(conn), -1)
+        E = energies()
+        if E.tadx_add_term(self._x, kind, conn.shape[0], conn.ctypes.data, conn.shape[1], data.ctypes.data, data.shape[1]) != 0:
+            raise TinyADError(-1, E.tadx_last_error().decode())
+        self._pattern = None
+        return self
+
+    def set_option(self, opt, value):
+        _check(runtime().tad_function_set_option(self.h, opt, value))
+
+    def set_timing(self, on=True):
+        _check(runtime().tad_function_set_timing(self.h, int(on)))
+
+    def last_timings(self):
+        ms = (ctypes.c_float * 4)()
+        _check(runtime().tad_function_last_timings(self.h, ms))
+        return {"element_ms": ms[0], "projection_ms": ms[1], "assembly_ms": ms[2], "total_ms": ms[3]}
+
+    def projection_stats(self):
+        s = (ctypes.c_int64 * 2)()
+        _check(runtime().tad_function_projection_stats(self.h, s))
+        return {"decomposed": s[0], "rebuilt": s[1]}
+
+    @property
+    def n_elements(self):
+        return runtime().tad_function_n_elements(self.h)
+
+    @property
+    def n_outputs(self):
+        return runtime().tad_function_n_outputs(self.h)
+
+    def pattern(self):
+        """(outer, inner) int32 numpy arrays of the fixed pattern (Hessian CSR==CSC, or Jacobian CSC)."""
+        if self._pattern is None:
+            n_outer, nnz = ctypes.c_int64(), ctypes.c_int64()
+            _check(runtime().tad_function_pattern(self.h, ctypes.byref(n_outer), ctypes.byref(nnz)))
+            outer = np.empty(n_outer.value + 1, dtype=np.int32)
+            inner = np.empty(nnz.value, dtype=np.int32)
+            _check(runtime().tad_function_pattern_copy(self.h, outer.ctypes.data, inner.ctypes.data))
+            self._pattern = (outer, inner)
+        return self._pattern
+
+    @property
+    def nnz(self):
+        return len(self.pattern()[1])
+
+    def term_table(self, term, valence, n_elements):
+        t = np.empty((valence, n_elements), dtype=np.int32)
+        _check(runtime().tad_function_term_table(self.h, term, t.ctypes.data))
+        return t
+
+    # ---- host-buffer calls (H2D / D2H inside the C call) ----
+    def eval_host(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = ctypes.c_double()
+        _check(runtime().tad_eval_host(self.h, x.ctypes.data, ctypes.byref(f)))
+        return f.value
+
+    def eval_with_gradient_host(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = ctypes.c_double()
+        g = np.empty(self.n_vars)
+        _check(runtime().tad_eval_with_gradient_host(self.h, x.ctypes.data, ctypes.byref(f), g.ctypes.data))
+        return f.value, g
+
+    def eval_with_derivatives_host(self, x, project=False, eps=1e-9, out_g=None, out_H=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        f = ctypes.c_double()
+        g = np.empty(self.n_vars) if out_g is None else out_g
+        H = np.empty(self.nnz) if out_H is None else out_H
+        _check(runtime().tad_eval_with_derivatives_host(self.h, _ptr(x), ctypes.byref(f), _ptr(g), _ptr(H), int(project), eps))
+        return f.value, g, H
+
+    def eval_with_hessian_proj_host(self, x, eps=1e-9, **kw):
+        return self.eval_with_derivatives_host(x, True, eps, **kw)
+
+    # ---- device-pointer calls ----
+    def eval(self, x_dev):
+        f = ctypes.c_double()
+        _check(runtime().tad_eval(self.h, _ptr(x_dev), ctypes.byref(f)))
+        return f.value
+
+    def eval_with_gradient(self, x_dev, g_dev):
+        f = ctypes.c_double()
+        _check(runtime().tad_eval_with_gradient(self.h, _ptr(x_dev), ctypes.byref(f), _ptr(g_dev)))
+        return f.value
+
+    def eval_with_derivatives(self, x_dev, g_dev, H_dev, project=False, eps=1e-9):
+        f = ctypes.c_double()
+        _check(runtime().tad_eval_with_derivatives(self.h, _ptr(x_dev), ctypes.byref(f), _ptr(g_dev), _ptr(H_dev), int(project), eps))
+        return f.value
+
+    def eval_with_hessian_proj(self, x_dev, g_dev, H_dev, eps=1e-9):
+        return self.eval_with_derivatives(x_dev, g_dev, H_dev, True, eps)
+
+    # ---- vector functions (device pointers) ----
+    def veval(self, x_dev, r_dev):
+        _check(runtime().tad_veval(self.h, _ptr(x_dev), _ptr(r_dev)))
+
+    def veval_with_jacobian(self, x_dev, r_dev, J_dev):
+        _check(runtime().tad_veval_with_jacobian(self.h, _ptr(x_dev), _ptr(r_dev), _ptr(J_dev)))
+
+    def veval_sum_of_squares(self, x_dev):
+        f = ctypes.c_double()
+        _check(runtime().tad_veval_sum_of_squares(self.h, _ptr(x_dev), ctypes.byref(f)))
+        return f.value
+
+    def veval_sum_of_squares_with_derivatives(self, x_dev, g_dev, r_dev, J_dev):
+        f = ctypes.c_double()
+        _check(runtime().tad_veval_sum_of_squares_with_derivatives(self.h, _ptr(x_dev), ctypes.byref(f), _ptr(g_dev), _ptr(r_dev), _ptr(J_dev)))
+        return f.value
+
+
+def project_batch(k, hess_dev, n, stride, eps=1e-9, counts_dev=None, stream=None):
+    """tad_project_batch on a device SoA buffer (torch tensor)."""
+    _check(runtime().tad_project_batch(k, n, stride, _ptr(hess_dev), eps, _ptr(counts_dev), stream))

@@ -1,0 +1,1587 @@
+// tinyad_b200 runtime (libtinyad_b200.so) -- functor-independent half of the B200 path.
+// Implements include/tinyad_b200.h.  sm_100a only; no CPU fallback.
+//
+// What lives here (reference counterpart in /root/reference/include/TinyAD):
+//   record pass bookkeeping, fixed CSR pattern + scatter maps   <- rediscovered at every eval by Element.hh:208-260 +
+//                                                                  setFromTriplets (ScalarFunctionImpl.hh:398)
+//   batched PSD projection kernel                               <- Utils/HessianProjection.hh:23-101
+//   assembly kernels (FP64 atomics | deterministic gather)      <- serial loops ScalarObjectiveTerm.hh:256-277
+//   f reduction, finite checks, error word                      <- ScalarObjectiveTerm.hh:210,252-253, Utils/Out.hh:73-79
+//   VectorFunction r / J (CSC) / sum of squares / g = 2 J^T r   <- VectorObjectiveTerm.hh:158-243, VectorFunctionImpl.hh:143-283
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include <TinyAD/Detail/HessLayout.hh>
+#include <tinyad_b200.h>
+
+using TinyAD::detail::hess_seq_index;
+using TinyAD::detail::hess_seq_rc;
+using TinyAD::detail::hess_size;
+
+namespace
+{
+
+thread_local std::string g_last_error = "";
+
+int fail(int status, const std::string& msg)
+{
+    g_last_error = msg;
+    return status;
+}
+
+#define TAD_CUDA(expr)                                                                                   \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? TAD_OUT_OF_MEMORY : TAD_CUDA_ERROR,            \
+                        std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);          \
+    } while (0)
+
+#define TAD_TRY(expr)                    \
+    do                                   \
+    {                                    \
+        int _s = (expr);                 \
+        if (_s != TAD_OK) return _s;     \
+    } while (0)
+
+constexpr int ERR_NONFINITE = 1 << TAD_NONFINITE_DERIVATIVE;
+constexpr int ERR_TOO_MANY = 1 << TAD_TOO_MANY_VARIABLES;
+constexpr int ERR_RANGE = 1 << TAD_INDEX_OUT_OF_RANGE;
+
+template <class T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+};
+
+struct Term
+{
+    int N = 0, M = 0, k = 0;
+    int64_t n = 0, stride = 0;
+    tad_launch_fn launch = nullptr;
+    void* user = nullptr;
+    void (*user_free)(void*) = nullptr;
+    bool dedup = false;
+    DevBuf<int64_t> elem_handles;
+    bool has_handles = false;
+    DevBuf<int32_t> rec_handles;  // [N][stride]
+    DevBuf<int32_t> rec_counts;   // [n]
+    // scalar functions: scatter map
+    DevBuf<int32_t> blockbase;    // [N*N][stride]  CSR value index of entry (0,0) of block (bi,bj); -1 = unused
+    DevBuf<int32_t> rstride;      // [N][stride]    distance between consecutive rows of that block row (= d * deg(vertex))
+    int64_t contrib_offset = 0;
+    // vector functions
+    int64_t out_offset = 0;
+    DevBuf<int32_t> jslot;        // [M*k][stride]  CSC value index; -1 = unused
+    // staging (gather mode keeps one per term)
+    DevBuf<double> stage;
+};
+
+struct TermDev  // device-visible description used by pattern / gather kernels
+{
+    int64_t off;      // first contribution id
+    int64_t n, stride;
+    int N, M, k;
+    const int32_t* rec;
+    int32_t* blockbase;
+    int32_t* rstride;
+    int32_t* jslot;
+    int64_t out_offset;
+    const double* grad;  // staging pointers (gather mode)
+    const double* hess;
+};
+
+}  // namespace
+
+struct tad_function_s
+{
+    int d = 0;
+    int64_t n_handles = 0, n_vars = 0;
+    bool is_vector = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<Term> terms;
+    int64_t n_elements = 0, n_outputs = 0;
+    // options
+    int assembly = TAD_ASSEMBLY_ATOMIC;
+    int64_t chunk = 0;
+    bool timing = false;
+    // pattern
+    bool pattern_built = false;
+    int64_t nnz = 0, n_outer = 0, n_blocks = 0, n_contrib = 0;
+    DevBuf<int32_t> outer, inner;
+    DevBuf<int64_t> block_ptr;     // [n_blocks+1] into contrib
+    DevBuf<int32_t> contrib;       // sorted contribution ids
+    DevBuf<int64_t> block_key;     // [n_blocks]
+    DevBuf<int64_t> vrow;          // [n_handles+1] first block of each vertex row
+    DevBuf<TermDev> terms_dev;
+    // scratch
+    DevBuf<double> stage;          // shared staging (atomic mode)
+    DevBuf<double> x_dev, g_dev, H_dev, r_dev;
+    DevBuf<int32_t> err;           // int32[8]
+    DevBuf<double> fpart;          // block partial sums
+    DevBuf<double> fterm;          // per-term sums
+    DevBuf<int64_t> proj_counts;   // [2]
+    int64_t last_proj[2] = {0, 0};
+    float last_ms[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::mutex mtx;                // eval* may be called concurrently (ScalarFunctionTest.cc:255-291)
+};
+
+namespace
+{
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_i32(int32_t* p, int64_t n, int32_t v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// rec_counts < 0 marks repeated handles; writes flags[0] |= 1 if any
+__global__ void scan_counts(const int32_t* counts, int64_t n, int32_t* flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && counts[i] < 0) atomicOr(flags, 1);
+}
+
+// Deterministic sum: stage 1, one partial per block (fixed tree), stage 2 one block over partials.
+template <bool SQUARE>
+__global__ void __launch_bounds__(256) reduce_stage1(const double* v, int64_t n, int64_t stride, int rows, double* partial)
+{
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r)
+    {
+        const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        if (i < n)
+        {
+            const double t = v[(int64_t)r * stride + i];
+            s += SQUARE ? t * t : t;
+        }
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(1024) reduce_stage2(const double* partial, int64_t nb, double* out)
+{
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < nb; i += 1024) s += partial[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1)
+    {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// PSD projection (Utils/HessianProjection.hh:23-101), one thread per element.
+// Symmetric eigensolver: Householder tridiagonalisation + implicit QL with accumulated
+// transformations (the classic EISPACK tred2/tql2 scheme).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ void sym_eig(double (&V)[K][K], double (&d)[K], double (&e)[K])
+{
+    // --- tridiagonalise; V holds the symmetric matrix on entry, the orthogonal transformation on exit ---
+    for (int j = 0; j < K; ++j) d[j] = V[K - 1][j];
+    for (int i = K - 1; i > 0; --i)
+    {
+        double scale = 0.0, h = 0.0;
+        for (int q = 0; q < i; ++q) scale += fabs(d[q]);
+        if (scale == 0.0)
+        {
+            e[i] = d[i - 1];
+            for (int j = 0; j < i; ++j)
+            {
+                d[j] = V[i - 1][j];
+                V[i][j] = 0.0;
+                V[j][i] = 0.0;
+            }
+        }
+        else
+        {
+            const double inv_scale = 1.0 / scale;
+            for (int q = 0; q < i; ++q)
+            {
+                d[q] *= inv_scale;
+                h += d[q] * d[q];
+            }
+            double f = d[i - 1];
+            double g = sqrt(h);
+            if (f > 0) g = -g;
+            e[i] = scale * g;
+            h -= f * g;
+            d[i - 1] = f - g;
+            for (int j = 0; j < i; ++j) e[j] = 0.0;
+            for (int j = 0; j < i; ++j)
+            {
+                f = d[j];
+                V[j][i] = f;
+                g = e[j] + V[j][j] * f;
+                for (int q = j + 1; q <= i - 1; ++q)
+                {
+                    g += V[q][j] * d[q];
+                    e[q] += V[q][j] * f;
+                }
+                e[j] = g;
+            }
+            f = 0.0;
+            const double inv_h = 1.0 / h;
+            for (int j = 0; j < i; ++j)
+            {
+                e[j] *= inv_h;
+                f += e[j] * d[j];
+            }
+            const double hh = f / (h + h);
+            for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+            for (int j = 0; j < i; ++j)
+            {
+                f = d[j];
+                g = e[j];
+                for (int q = j; q <= i - 1; ++q) V[q][j] -= (f * e[q] + g * d[q]);
+                d[j] = V[i - 1][j];
+                V[i][j] = 0.0;
+            }
+        }
+        d[i] = h;
+    }
+    for (int i = 0; i < K - 1; ++i)
+    {
+        V[K - 1][i] = V[i][i];
+        V[i][i] = 1.0;
+        const double h = d[i + 1];
+        if (h != 0.0)
+        {
+            const double inv_h = 1.0 / h;
+            for (int q = 0; q <= i; ++q) d[q] = V[q][i + 1] * inv_h;
+            for (int j = 0; j <= i; ++j)
+            {
+                double g = 0.0;
+                for (int q = 0; q <= i; ++q) g += V[q][i + 1] * V[q][j];
+                for (int q = 0; q <= i; ++q) V[q][j] -= g * d[q];
+            }
+        }
+        for (int q = 0; q <= i; ++q) V[q][i + 1] = 0.0;
+    }
+    for (int j = 0; j < K; ++j)
+    {
+        d[j] = V[K - 1][j];
+        V[K - 1][j] = 0.0;
+    }
+    V[K - 1][K - 1] = 1.0;
+    e[0] = 0.0;
+
+    // --- implicit QL on the tridiagonal (d, e), rotations accumulated into V ---
+    for (int i = 1; i < K; ++i) e[i - 1] = e[i];
+    e[K - 1] = 0.0;
+    double f = 0.0, tst1 = 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < K; ++l)
+    {
+        tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+        int m = l;
+        while (m < K - 1)
+        {
+            if (fabs(e[m]) <= eps * tst1) break;
+            ++m;
+        }
+        if (m > l)
+        {
+            int iter = 0;
+            do
+            {
+                ++iter;
+                double g = d[l];
+                double p = (d[l + 1] - g) / (2.0 * e[l]);
+                double r = hypot(p, 1.0);
+                if (p < 0) r = -r;
+                d[l] = e[l] / (p + r);
+                d[l + 1] = e[l] * (p + r);
+                const double dl1 = d[l + 1];
+                double h = g - d[l];
+                for (int i = l + 2; i < K; ++i) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = 1.0, c3 = 1.0;
+                const double el1 = e[l + 1];
+                double s = 0.0, s2 = 0.0;
+                for (int i = m - 1; i >= l; --i)
+                {
+                    c3 = c2;
+                    c2 = c;
+                    s2 = s;
+                    g = c * e[i];
+                    h = c * p;
+                    r = hypot(p, e[i]);
+                    e[i + 1] = s * r;
+                    const double inv_r = 1.0 / r;
+                    s = e[i] * inv_r;
+                    c = p * inv_r;
+                    p = c * d[i] - s * g;
+                    d[i + 1] = h + s * (c * g + s * d[i]);
+                    for (int q = 0; q < K; ++q)
+                    {
+                        h = V[q][i + 1];
+                        V[q][i + 1] = s * V[q][i] + c * h;
+                        V[q][i] = c * V[q][i] - s * h;
+                    }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p;
+                d[l] = c * p;
+            } while (fabs(e[l]) > eps * tst1 && iter < 60);
+        }
+        d[l] = d[l] + f;
+        e[l] = 0.0;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) project_kernel(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts)
+{
+    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= n) return;
+    constexpr int H = K * (K + 1) / 2;
+    double V[K][K];
+    double dg[K], off[K];
+    for (int s = 0; s < H; ++s)
+    {
+        const TinyAD::detail::HessRC rc = hess_seq_rc(K, s);
+        const double v = hess[(int64_t)s * stride + el];
+        V[rc.row][rc.col] = v;
+        V[rc.col][rc.row] = v;
+    }
+    // early out 1: positive diagonally dominant (HessianProjection.hh:23-42, :62-63)
+    bool dominant = true;
+    for (int i = 0; i < K; ++i)
+    {
+        double o = 0.0;
+        for (int j = 0; j < K; ++j)
+            if (i != j) o += fabs(V[i][j]);
+        if (V[i][i] < o + eps) dominant = false;
+    }
+    if (dominant) return;
+    sym_eig<K>(V, dg, off);
+    // clamp (HessianProjection.hh:71-91)
+    bool all_positive = true;
+    for (int i = 0; i < K; ++i)
+    {
+        if (eps < 0)
+        {
+            if (dg[i] < 0) { dg[i] = -dg[i]; all_positive = false; }
+        }
+        else if (dg[i] < eps) { dg[i] = eps; all_positive = false; }
+    }
+    if (counts) atomicAdd(&counts[0], 1ull);
+    // early out 2: nothing clamped -> H stays bit-unchanged (:94-95)
+    if (all_positive) return;
+    if (counts) atomicAdd(&counts[1], 1ull);
+    // H = V D V^T (:98), lower triangle only
+    for (int s = 0; s < H; ++s)
+    {
+        const TinyAD::detail::HessRC rc = hess_seq_rc(K, s);
+        double acc = 0.0;
+        for (int l = 0; l < K; ++l) acc += V[rc.row][l] * dg[l] * V[rc.col][l];
+        hess[(int64_t)s * stride + el] = acc;
+    }
+}
+
+template <int K>
+int launch_project(double* hess, int64_t n, int64_t stride, double eps, int64_t* counts, cudaStream_t st)
+{
+    project_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(hess, n, stride, eps, (unsigned long long*)counts);
+    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "project kernel launch failed");
+}
+
+int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, int64_t* counts, cudaStream_t st)
+{
+    if (n <= 0 || k <= 0) return TAD_OK;
+    switch (k)
+    {
+    case 1: return launch_project<1>(hess, n, stride, eps, counts, st);
+    case 2: return launch_project<2>(hess, n, stride, eps, counts, st);
+    case 3: return launch_project<3>(hess, n, stride, eps, counts, st);
+    case 4: return launch_project<4>(hess, n, stride, eps, counts, st);
+    case 5: return launch_project<5>(hess, n, stride, eps, counts, st);
+    case 6: return launch_project<6>(hess, n, stride, eps, counts, st);
+    case 7: return launch_project<7>(hess, n, stride, eps, counts, st);
+    case 8: return launch_project<8>(hess, n, stride, eps, counts, st);
+    case 9: return launch_project<9>(hess, n, stride, eps, counts, st);
+    case 10: return launch_project<10>(hess, n, stride, eps, counts, st);
+    case 12: return launch_project<12>(hess, n, stride, eps, counts, st);
+    case 15: return launch_project<15>(hess, n, stride, eps, counts, st);
+    case 16: return launch_project<16>(hess, n, stride, eps, counts, st);
+    case 18: return launch_project<18>(hess, n, stride, eps, counts, st);
+    default: return fail(TAD_NOT_SUPPORTED, "Hessian projection is instantiated for k in {1..10,12,15,16,18}");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pattern construction (scalar functions): vertex-pair blocks -> CSR + scatter maps
+// ---------------------------------------------------------------------------------------------
+__global__ void gen_block_keys(TermDev t, int64_t n_handles, int64_t* keys, int32_t* payload)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // local contribution id, element-major
+    const int64_t nn = (int64_t)t.N * t.N;
+    if (c >= t.n * nn) return;
+    const int64_t e = c / nn;
+    const int b = (int)(c % nn);
+    const int bi = b / t.N, bj = b % t.N;
+    const int32_t vi = t.rec[(int64_t)bi * t.stride + e];
+    const int32_t vj = t.rec[(int64_t)bj * t.stride + e];
+    keys[t.off + c] = (vi < 0 || vj < 0) ? INT64_MAX : (int64_t)vi * n_handles + vj;
+    payload[t.off + c] = (int32_t)(t.off + c);
+}
+
+__global__ void count_valid(const int64_t* keys, int64_t n, int64_t* out)
+{
+    // keys sorted ascending; binary search for the first INT64_MAX (single thread)
+    int64_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+        const int64_t mid = (lo + hi) / 2;
+        if (keys[mid] == INT64_MAX) hi = mid; else lo = mid + 1;
+    }
+    *out = lo;
+}
+
+__global__ void head_flags(const int64_t* keys, int64_t n, int32_t* flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+__global__ void scatter_heads(const int64_t* keys, const int32_t* flags, const int32_t* pid_incl, int64_t n,
+                              int64_t* block_key, int64_t* block_ptr, int64_t n_blocks)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i])
+    {
+        const int32_t p = pid_incl[i] - 1;
+        block_key[p] = keys[i];
+        block_ptr[p] = i;
+    }
+    if (i == 0) block_ptr[n_blocks] = n;
+}
+
+__global__ void vertex_rows(const int64_t* block_key, int64_t n_blocks, int64_t n_handles, int64_t* vrow)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > n_handles) return;
+    const int64_t target = v * n_handles;
+    int64_t lo = 0, hi = n_blocks;
+    while (lo < hi)
+    {
+        const int64_t mid = (lo + hi) / 2;
+        if (block_key[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    vrow[v] = lo;
+}
+
+__global__ void fill_csr(const int64_t* block_key, const int64_t* vrow, int64_t n_blocks, int64_t n_handles, int d,
+                         int32_t* outer, int32_t* inner)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_blocks)
+    {
+        const int64_t vi = block_key[p] / n_handles, vj = block_key[p] % n_handles;
+        const int64_t r0 = vrow[vi], deg = vrow[vi + 1] - r0;
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b)
+                inner[(int64_t)d * d * r0 + (int64_t)a * d * deg + (int64_t)d * (p - r0) + b] = (int32_t)(d * vj + b);
+    }
+    if (p < n_handles)
+    {
+        const int64_t r0 = vrow[p], deg = vrow[p + 1] - r0;
+        for (int a = 0; a < d; ++a) outer[d * p + a] = (int32_t)((int64_t)d * d * r0 + (int64_t)a * d * deg);
+    }
+    if (p == 0) outer[(int64_t)d * n_handles] = (int32_t)((int64_t)d * d * n_blocks);
+}
+
+__global__ void fill_maps(const int32_t* contrib, const int32_t* pid_incl, int64_t n_valid, const TermDev* terms, int n_terms,
+                          const int64_t* block_key, const int64_t* vrow, int64_t n_handles, int d)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_valid) return;
+    const int64_t c = contrib[i];
+    const int64_t p = pid_incl[i] - 1;
+    int t = 0;
+    while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
+    const TermDev T = terms[t];
+    const int64_t local = c - T.off;
+    const int64_t nn = (int64_t)T.N * T.N;
+    const int64_t e = local / nn;
+    const int b = (int)(local % nn);
+    const int bi = b / T.N;
+    const int64_t vi = block_key[p] / n_handles;
+    const int64_t r0 = vrow[vi], deg = vrow[vi + 1] - r0;
+    T.blockbase[(int64_t)b * T.stride + e] = (int32_t)((int64_t)d * d * r0 + (int64_t)d * (p - r0));
+    T.rstride[(int64_t)bi * T.stride + e] = (int32_t)(d * deg);
+}
+
+// ---------------------------------------------------------------------------------------------
+// assembly, atomic mode: one thread per element, FP64 red.global.add on g and the CSR values
+// ---------------------------------------------------------------------------------------------
+struct SeqTable { int16_t idx[18 * 18]; };
+
+template <int D, int N>
+__global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __restrict__ rec, const int32_t* __restrict__ blockbase,
+                                                              const int32_t* __restrict__ rstride, const double* __restrict__ grad,
+                                                              const double* __restrict__ hess, int64_t n, int64_t stride,
+                                                              double* __restrict__ g, double* __restrict__ Hv, int32_t* err)
+{
+    constexpr int K = D * N;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    bool finite = true;
+#pragma unroll
+    for (int bi = 0; bi < N; ++bi)
+    {
+        const int32_t vi = rec[(int64_t)bi * stride + e];
+        if (vi < 0) continue;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+        {
+            const double v = grad[(int64_t)(D * bi + a) * stride + e];
+            finite = finite && isfinite(v);
+            atomicAdd(&g[(int64_t)D * vi + a], v);
+        }
+    }
+    if (hess)
+    {
+#pragma unroll
+        for (int bi = 0; bi < N; ++bi)
+        {
+            const int32_t rs = rstride[(int64_t)bi * stride + e];
+#pragma unroll
+            for (int bj = 0; bj < N; ++bj)
+            {
+                const int32_t base = blockbase[(int64_t)(bi * N + bj) * stride + e];
+                if (base < 0) continue;
+#pragma unroll
+                for (int a = 0; a < D; ++a)
+#pragma unroll
+                    for (int b = 0; b < D; ++b)
+                    {
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int s = hess_seq_index(K, D * bi + a, D * bj + b);
+                        const double v = hess[(int64_t)s * stride + e];
+                        finite = finite && isfinite(v);
+                        atomicAdd(&Hv[(int64_t)base + (int64_t)a * rs + b], v);
+                    }
+            }
+        }
+    }
+    if (!finite) atomicOr(err, ERR_NONFINITE);
+}
+
+// generic (runtime d, N) fallback
+__global__ void __launch_bounds__(128) assemble_atomic_generic(int D, int N, SeqTable seq, const int32_t* __restrict__ rec,
+                                                               const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
+                                                               const double* __restrict__ grad, const double* __restrict__ hess,
+                                                               int64_t n, int64_t stride, double* __restrict__ g, double* __restrict__ Hv,
+                                                               int32_t* err)
+{
+    const int K = D * N;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    bool finite = true;
+    for (int bi = 0; bi < N; ++bi)
+    {
+        const int32_t vi = rec[(int64_t)bi * stride + e];
+        if (vi < 0) continue;
+        for (int a = 0; a < D; ++a)
+        {
+            const double v = grad[(int64_t)(D * bi + a) * stride + e];
+            finite = finite && isfinite(v);
+            atomicAdd(&g[(int64_t)D * vi + a], v);
+        }
+    }
+    if (hess)
+        for (int bi = 0; bi < N; ++bi)
+        {
+            const int32_t rs = rstride[(int64_t)bi * stride + e];
+            for (int bj = 0; bj < N; ++bj)
+            {
+                const int32_t base = blockbase[(int64_t)(bi * N + bj) * stride + e];
+                if (base < 0) continue;
+                for (int a = 0; a < D; ++a)
+                    for (int b = 0; b < D; ++b)
+                    {
+                        const int s = seq.idx[(D * bi + a) * K + (D * bj + b)];
+                        const double v = hess[(int64_t)s * stride + e];
+                        finite = finite && isfinite(v);
+                        atomicAdd(&Hv[(int64_t)base + (int64_t)a * rs + b], v);
+                    }
+            }
+        }
+    if (!finite) atomicOr(err, ERR_NONFINITE);
+}
+
+template <int D, int N>
+void launch_assemble(const Term& t, const double* grad, const double* hess, int64_t n, double* g, double* Hv, int32_t* err, cudaStream_t st)
+{
+    assemble_atomic_kernel<D, N><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(t.rec_handles.p, t.blockbase.p, t.rstride.p, grad, hess,
+                                                                              n, t.stride, g, Hv, err);
+}
+
+int assemble_atomic(int d, const Term& t, const double* grad, const double* hess, int64_t n, double* g, double* Hv, int32_t* err,
+                    cudaStream_t st)
+{
+    if (n <= 0) return TAD_OK;
+    const int code = d * 100 + t.N;
+    switch (code)
+    {
+    case 101: launch_assemble<1, 1>(t, grad, hess, n, g, Hv, err, st); break;
+    case 102: launch_assemble<1, 2>(t, grad, hess, n, g, Hv, err, st); break;
+    case 103: launch_assemble<1, 3>(t, grad, hess, n, g, Hv, err, st); break;
+    case 104: launch_assemble<1, 4>(t, grad, hess, n, g, Hv, err, st); break;
+    case 201: launch_assemble<2, 1>(t, grad, hess, n, g, Hv, err, st); break;
+    case 202: launch_assemble<2, 2>(t, grad, hess, n, g, Hv, err, st); break;
+    case 203: launch_assemble<2, 3>(t, grad, hess, n, g, Hv, err, st); break;
+    case 204: launch_assemble<2, 4>(t, grad, hess, n, g, Hv, err, st); break;
+    case 301: launch_assemble<3, 1>(t, grad, hess, n, g, Hv, err, st); break;
+    case 302: launch_assemble<3, 2>(t, grad, hess, n, g, Hv, err, st); break;
+    case 303: launch_assemble<3, 3>(t, grad, hess, n, g, Hv, err, st); break;
+    case 304: launch_assemble<3, 4>(t, grad, hess, n, g, Hv, err, st); break;
+    default:
+    {
+        const int K = d * t.N;
+        if (K > 18) return fail(TAD_NOT_SUPPORTED, "assembly supports at most 18 variables per element");
+        SeqTable seq;
+        for (int i = 0; i < K; ++i)
+            for (int j = 0; j < K; ++j) seq.idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);
+        assemble_atomic_generic<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d, t.N, seq, t.rec_handles.p, t.blockbase.p, t.rstride.p,
+                                                                            grad, hess, n, t.stride, g, Hv, err);
+    }
+    }
+    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "assembly kernel launch failed");
+}
+
+// ---------------------------------------------------------------------------------------------
+// assembly, gather mode: one thread per CSR entry, contributions summed in (term, element) order --
+// the order in which the reference's setFromTriplets adds duplicates -- deterministic, no atomics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gather_hessian(const int64_t* __restrict__ block_ptr, const int32_t* __restrict__ contrib,
+                                                      const int64_t* __restrict__ block_key, const int64_t* __restrict__ vrow,
+                                                      const TermDev* __restrict__ terms, int n_terms, SeqTable const* __restrict__ seqs,
+                                                      int64_t n_blocks, int64_t n_handles, int d, double* __restrict__ Hv, int32_t* err)
+{
+    const int dd = d * d;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = tid / dd;
+    if (p >= n_blocks) return;
+    const int ab = (int)(tid % dd), a = ab / d, b = ab % d;
+    double acc = 0.0;
+    for (int64_t i = block_ptr[p]; i < block_ptr[p + 1]; ++i)
+    {
+        const int64_t c = contrib[i];
+        int t = 0;
+        while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
+        const TermDev& T = terms[t];
+        const int64_t local = c - T.off;
+        const int64_t nn = (int64_t)T.N * T.N;
+        const int64_t e = local / nn;
+        const int bb = (int)(local % nn);
+        const int bi = bb / T.N, bj = bb % T.N;
+        const int s = seqs[t].idx[(d * bi + a) * T.k + (d * bj + b)];
+        acc += T.hess[(int64_t)s * T.stride + e];
+    }
+    if (!isfinite(acc)) atomicOr(err, ERR_NONFINITE);
+    const int64_t vi = block_key[p] / n_handles;
+    const int64_t r0 = vrow[vi], deg = vrow[vi + 1] - r0;
+    Hv[(int64_t)dd * r0 + (int64_t)a * d * deg + (int64_t)d * (p - r0) + b] = acc;
+}
+
+__global__ void __launch_bounds__(128) gather_gradient(const int64_t* __restrict__ block_ptr, const int32_t* __restrict__ contrib,
+                                                       const int64_t* __restrict__ block_key, const TermDev* __restrict__ terms,
+                                                       int n_terms, int64_t n_blocks, int64_t n_handles, int d, double* __restrict__ g,
+                                                       int32_t* err)
+{
+    // one thread per (vertex, component); contributions of vertex v are those of its diagonal block (v, v)
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t v = tid / d;
+    if (v >= n_handles) return;
+    const int a = (int)(tid % d);
+    const int64_t target = v * n_handles + v;
+    int64_t lo = 0, hi = n_blocks;
+    while (lo < hi)
+    {
+        const int64_t mid = (lo + hi) / 2;
+        if (block_key[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    double acc = 0.0;
+    if (lo < n_blocks && block_key[lo] == target)
+        for (int64_t i = block_ptr[lo]; i < block_ptr[lo + 1]; ++i)
+        {
+            const int64_t c = contrib[i];
+            int t = 0;
+            while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
+            const TermDev& T = terms[t];
+            const int64_t local = c - T.off;
+            const int64_t nn = (int64_t)T.N * T.N;
+            const int64_t e = local / nn;
+            const int bi = (int)(local % nn) / T.N;
+            acc += T.grad[(int64_t)(d * bi + a) * T.stride + e];
+        }
+    if (!isfinite(acc)) atomicOr(err, ERR_NONFINITE);
+    g[(int64_t)d * v + a] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector functions
+// ---------------------------------------------------------------------------------------------
+__global__ void gen_jac_keys(TermDev t, int d, int64_t n_outputs, int64_t* keys, int32_t* payload)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // element-major: ((e*M + m)*k + i)
+    const int64_t per = (int64_t)t.M * t.k;
+    if (c >= t.n * per) return;
+    const int64_t e = c / per;
+    const int mi = (int)(c % per);
+    const int m = mi / t.k, i = mi % t.k;
+    const int32_t v = t.rec[(int64_t)(i / d) * t.stride + e];
+    const int64_t row = t.out_offset + (int64_t)t.M * e + m;
+    keys[t.off + c] = (v < 0) ? INT64_MAX : ((int64_t)d * v + (i % d)) * n_outputs + row;
+    payload[t.off + c] = (int32_t)(t.off + c);
+}
+
+__global__ void fill_jac(const int64_t* keys, const int32_t* contrib, int64_t n_valid, const TermDev* terms, int n_terms,
+                         int64_t n_outputs, int32_t* inner)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_valid) return;
+    inner[i] = (int32_t)(keys[i] % n_outputs);
+    const int64_t c = contrib[i];
+    int t = 0;
+    while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
+    const TermDev T = terms[t];
+    const int64_t local = c - T.off;
+    const int64_t per = (int64_t)T.M * T.k;
+    const int64_t e = local / per;
+    const int mi = (int)(local % per);
+    T.jslot[(int64_t)mi * T.stride + e] = (int32_t)i;
+}
+
+__global__ void jac_col_ptr(const int64_t* keys, int64_t n_valid, int64_t n_vars, int64_t n_outputs, int32_t* outer)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_vars) return;
+    const int64_t target = c * n_outputs;
+    int64_t lo = 0, hi = n_valid;
+    while (lo < hi)
+    {
+        const int64_t mid = (lo + hi) / 2;
+        if (keys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    outer[c] = (int32_t)lo;
+}
+
+__global__ void scatter_residuals(const double* val, int64_t n, int64_t stride, int M, int64_t out_offset, double* r)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // i = e*M + m
+    if (i >= n * M) return;
+    const int64_t e = i / M;
+    const int m = (int)(i % M);
+    r[out_offset + i] = val[(int64_t)m * stride + e];
+}
+
+__global__ void scatter_jacobian(const double* grad, const int32_t* jslot, int64_t n, int64_t stride, int rows, double* Jv, int32_t* err)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    bool finite = true;
+    for (int r = 0; r < rows; ++r)
+    {
+        const int32_t s = jslot[(int64_t)r * stride + e];
+        if (s < 0) continue;
+        const double v = grad[(int64_t)r * stride + e];
+        finite = finite && isfinite(v);
+        Jv[s] = v;
+    }
+    if (!finite) atomicOr(err, ERR_NONFINITE);
+}
+
+__global__ void jt_r(const int32_t* outer, const int32_t* inner, const double* Jv, const double* r, int64_t n_vars, double* g)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_vars) return;
+    double s = 0.0;
+    for (int32_t p = outer[c]; p < outer[c + 1]; ++p) s += Jv[p] * r[inner[p]];
+    g[c] = 2.0 * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------------
+unsigned blocks_for(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
+
+int check_error_word(tad_function f, bool sync_already)
+{
+    int32_t h_err[8] = {0};
+    if (!sync_already) TAD_CUDA(cudaStreamSynchronize(f->stream));
+    TAD_CUDA(cudaMemcpy(h_err, f->err.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (h_err[0] & ERR_RANGE) return fail(TAD_INDEX_OUT_OF_RANGE, "variable handle out of range in element.variables(...)");
+    if (h_err[0] & ERR_TOO_MANY) return fail(TAD_TOO_MANY_VARIABLES, "Too many variables requested via element.variables(...).");
+    if (h_err[0] & ERR_NONFINITE) return fail(TAD_NONFINITE_DERIVATIVE, "non-finite element gradient or Hessian");
+    return TAD_OK;
+}
+
+int sum_to(tad_function f, const double* v, int64_t n, int64_t stride, int rows, bool square, double* out_dev)
+{
+    const int64_t nb = std::max<int64_t>(1, (n + 255) / 256);
+    TAD_CUDA(f->fpart.ensure((size_t)nb));
+    if (n <= 0)
+    {
+        TAD_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), f->stream));
+        return TAD_OK;
+    }
+    if (square) reduce_stage1<true><<<(unsigned)nb, 256, 0, f->stream>>>(v, n, stride, rows, f->fpart.p);
+    else reduce_stage1<false><<<(unsigned)nb, 256, 0, f->stream>>>(v, n, stride, rows, f->fpart.p);
+    reduce_stage2<<<1, 1024, 0, f->stream>>>(f->fpart.p, nb, out_dev);
+    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "reduction launch failed");
+}
+
+void fill_launch_args(tad_function f, const Term& t, int mode, const double* x, double* stage, tad_launch_args& a)
+{
+    std::memset(&a, 0, sizeof(a));
+    a.mode = mode;
+    a.dedup = t.dedup ? 1 : 0;
+    a.n_elements = t.n;
+    a.stride = t.stride;
+    a.elem_handles = t.has_handles ? t.elem_handles.p : nullptr;
+    a.x = x;
+    a.n_handles = f->n_handles;
+    const int rows = std::max(1, t.M);
+    a.val = stage;
+    a.grad = stage ? stage + (int64_t)rows * t.stride : nullptr;
+    a.hess = (stage && t.M == 0) ? a.grad + (int64_t)t.k * t.stride : nullptr;
+    a.rec_handles = t.rec_handles.p;
+    a.rec_counts = t.rec_counts.p;
+    a.error_flags = f->err.p;
+    a.stream = f->stream;
+}
+
+size_t stage_doubles(const Term& t, int mode)
+{
+    const int rows = std::max(1, t.M);
+    size_t per = rows;
+    if (mode >= TAD_MODE_FIRST) per += (size_t)rows * t.k;
+    if (mode == TAD_MODE_SECOND && t.M == 0) per += (size_t)hess_size(t.k);
+    return per * (size_t)t.stride;
+}
+
+int upload_terms_dev(tad_function f, bool with_stage_ptrs, int mode)
+{
+    std::vector<TermDev> td(f->terms.size());
+    for (size_t i = 0; i < f->terms.size(); ++i)
+    {
+        Term& t = f->terms[i];
+        td[i].off = t.contrib_offset;
+        td[i].n = t.n;
+        td[i].stride = t.stride;
+        td[i].N = t.N; td[i].M = t.M; td[i].k = t.k;
+        td[i].rec = t.rec_handles.p;
+        td[i].blockbase = t.blockbase.p;
+        td[i].rstride = t.rstride.p;
+        td[i].jslot = t.jslot.p;
+        td[i].out_offset = t.out_offset;
+        td[i].grad = nullptr; td[i].hess = nullptr;
+        if (with_stage_ptrs && t.stage.p)
+        {
+            td[i].grad = t.stage.p + t.stride;
+            td[i].hess = (mode == TAD_MODE_SECOND) ? t.stage.p + (int64_t)(1 + t.k) * t.stride : nullptr;
+        }
+    }
+    TAD_CUDA(f->terms_dev.ensure(td.size()));
+    if (!td.empty())
+        TAD_CUDA(cudaMemcpyAsync(f->terms_dev.p, td.data(), td.size() * sizeof(TermDev), cudaMemcpyHostToDevice, f->stream));
+    TAD_CUDA(cudaStreamSynchronize(f->stream));  // td is a local
+    return TAD_OK;
+}
+
+int build_pattern_scalar(tad_function f)
+{
+    cudaStream_t st = f->stream;
+    const int d = f->d;
+    int64_t nC = 0;
+    for (auto& t : f->terms)
+    {
+        t.contrib_offset = nC;
+        nC += (int64_t)t.N * t.N * t.n;
+    }
+    if (nC >= (int64_t)INT32_MAX) return fail(TAD_NOT_SUPPORTED, "more than 2^31 block contributions");
+    f->n_contrib = nC;
+    for (auto& t : f->terms)
+    {
+        TAD_CUDA(t.blockbase.ensure((size_t)t.N * t.N * t.stride));
+        TAD_CUDA(t.rstride.ensure((size_t)t.N * t.stride));
+        const int64_t nb = (int64_t)t.N * t.N * t.stride;
+        if (nb) fill_i32<<<blocks_for(nb, 256), 256, 0, st>>>(t.blockbase.p, nb, -1);
+        const int64_t nr = (int64_t)t.N * t.stride;
+        if (nr) fill_i32<<<blocks_for(nr, 256), 256, 0, st>>>(t.rstride.p, nr, 0);
+    }
+    TAD_TRY(upload_terms_dev(f, false, 0));
+
+    DevBuf<int64_t> keys_a, keys_b, nvalid_d;
+    DevBuf<int32_t> pay_a, pay_b, flags, pid;
+    TAD_CUDA(keys_a.ensure((size_t)nC)); TAD_CUDA(keys_b.ensure((size_t)nC));
+    TAD_CUDA(pay_a.ensure((size_t)nC)); TAD_CUDA(pay_b.ensure((size_t)nC));
+    TAD_CUDA(nvalid_d.ensure(1));
+    std::vector<TermDev> td(f->terms.size());
+    TAD_CUDA(cudaMemcpy(td.data(), f->terms_dev.p, td.size() * sizeof(TermDev), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < f->terms.size(); ++i)
+    {
+        const int64_t cnt = (int64_t)td[i].N * td[i].N * td[i].n;
+        if (cnt) gen_block_keys<<<blocks_for(cnt, 256), 256, 0, st>>>(td[i], f->n_handles, keys_a.p, pay_a.p);
+    }
+    int64_t n_valid = 0, n_blocks = 0;
+    if (nC > 0)
+    {
+        // number of significant key bits: keys < n_handles^2 (invalid keys are INT64_MAX -> need the full width if present)
+        size_t tmp_bytes = 0;
+        cub::DoubleBuffer<int64_t> kb(keys_a.p, keys_b.p);
+        cub::DoubleBuffer<int32_t> pb(pay_a.p, pay_b.p);
+        TAD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, pb, (int)nC, 0, 64, st));
+        DevBuf<unsigned char> tmp;
+        TAD_CUDA(tmp.ensure(tmp_bytes));
+        TAD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, kb, pb, (int)nC, 0, 64, st));
+        int64_t* keys = kb.Current();
+        int32_t* pay = pb.Current();
+        count_valid<<<1, 1, 0, st>>>(keys, nC, nvalid_d.p);
+        TAD_CUDA(cudaMemcpyAsync(&n_valid, nvalid_d.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        TAD_CUDA(cudaStreamSynchronize(st));
+        TAD_CUDA(flags.ensure((size_t)std::max<int64_t>(n_valid, 1)));
+        TAD_CUDA(pid.ensure((size_t)std::max<int64_t>(n_valid, 1)));
+        if (n_valid > 0)
+        {
+            head_flags<<<blocks_for(n_valid, 256), 256, 0, st>>>(keys, n_valid, flags.p);
+            size_t scan_bytes = 0;
+            TAD_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, flags.p, pid.p, (int)n_valid, st));
+            DevBuf<unsigned char> tmp2;
+            TAD_CUDA(tmp2.ensure(scan_bytes));
+            TAD_CUDA(cub::DeviceScan::InclusiveSum(tmp2.p, scan_bytes, flags.p, pid.p, (int)n_valid, st));
+            int32_t last = 0;
+            TAD_CUDA(cudaMemcpyAsync(&last, pid.p + (n_valid - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            TAD_CUDA(cudaStreamSynchronize(st));
+            n_blocks = last;
+        }
+        const int64_t nnz = (int64_t)d * d * n_blocks;
+        if (nnz >= (int64_t)INT32_MAX) return fail(TAD_NOT_SUPPORTED, "Hessian has more than 2^31 non-zeros (int32 StorageIndex)");
+        TAD_CUDA(f->block_key.ensure((size_t)std::max<int64_t>(n_blocks, 1)));
+        TAD_CUDA(f->block_ptr.ensure((size_t)n_blocks + 1));
+        TAD_CUDA(f->vrow.ensure((size_t)f->n_handles + 1));
+        TAD_CUDA(f->outer.ensure((size_t)f->n_vars + 1));
+        TAD_CUDA(f->inner.ensure((size_t)std::max<int64_t>(nnz, 1)));
+        TAD_CUDA(f->contrib.ensure((size_t)std::max<int64_t>(n_valid, 1)));
+        if (n_valid > 0)
+        {
+            scatter_heads<<<blocks_for(n_valid, 256), 256, 0, st>>>(keys, flags.p, pid.p, n_valid, f->block_key.p, f->block_ptr.p, n_blocks);
+            TAD_CUDA(cudaMemcpyAsync(f->contrib.p, pay, (size_t)n_valid * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        }
+        else
+            TAD_CUDA(cudaMemsetAsync(f->block_ptr.p, 0, sizeof(int64_t), st));
+        vertex_rows<<<blocks_for(f->n_handles + 1, 256), 256, 0, st>>>(f->block_key.p, n_blocks, f->n_handles, f->vrow.p);
+        fill_csr<<<blocks_for(std::max(n_blocks, f->n_handles), 256), 256, 0, st>>>(f->block_key.p, f->vrow.p, n_blocks, f->n_handles, d,
+                                                                                  f->outer.p, f->inner.p);
+        if (n_valid > 0)
+            fill_maps<<<blocks_for(n_valid, 256), 256, 0, st>>>(f->contrib.p, pid.p, n_valid, f->terms_dev.p, (int)f->terms.size(),
+                                                                f->block_key.p, f->vrow.p, f->n_handles, d);
+        TAD_CUDA(cudaGetLastError());
+        TAD_CUDA(cudaStreamSynchronize(st));
+        f->nnz = nnz;
+    }
+    else
+    {
+        TAD_CUDA(f->outer.ensure((size_t)f->n_vars + 1));
+        TAD_CUDA(cudaMemsetAsync(f->outer.p, 0, ((size_t)f->n_vars + 1) * sizeof(int32_t), st));
+        TAD_CUDA(f->inner.ensure(1));
+        TAD_CUDA(f->block_ptr.ensure(1));
+        TAD_CUDA(cudaMemsetAsync(f->block_ptr.p, 0, sizeof(int64_t), st));
+        TAD_CUDA(f->block_key.ensure(1));
+        TAD_CUDA(f->vrow.ensure((size_t)f->n_handles + 1));
+        TAD_CUDA(cudaMemsetAsync(f->vrow.p, 0, ((size_t)f->n_handles + 1) * sizeof(int64_t), st));
+        TAD_CUDA(f->contrib.ensure(1));
+        TAD_CUDA(cudaStreamSynchronize(st));
+        f->nnz = 0;
+    }
+    f->n_blocks = n_blocks;
+    f->n_outer = f->n_vars;
+    f->pattern_built = true;
+    return TAD_OK;
+}
+
+int build_pattern_vector(tad_function f)
+{
+    cudaStream_t st = f->stream;
+    int64_t nC = 0, out = 0;
+    for (auto& t : f->terms)
+    {
+        t.contrib_offset = nC;
+        t.out_offset = out;
+        nC += (int64_t)t.M * t.k * t.n;
+        out += (int64_t)t.M * t.n;
+    }
+    f->n_outputs = out;
+    if (nC >= (int64_t)INT32_MAX) return fail(TAD_NOT_SUPPORTED, "Jacobian has more than 2^31 entries");
+    for (auto& t : f->terms)
+    {
+        const int64_t nj = (int64_t)t.M * t.k * t.stride;
+        TAD_CUDA(t.jslot.ensure((size_t)nj));
+        if (nj) fill_i32<<<blocks_for(nj, 256), 256, 0, st>>>(t.jslot.p, nj, -1);
+    }
+    TAD_TRY(upload_terms_dev(f, false, 0));
+    TAD_CUDA(f->outer.ensure((size_t)f->n_vars + 1));
+    int64_t n_valid = 0;
+    if (nC > 0)
+    {
+        DevBuf<int64_t> keys_a, keys_b, nvalid_d;
+        DevBuf<int32_t> pay_a, pay_b;
+        TAD_CUDA(keys_a.ensure((size_t)nC)); TAD_CUDA(keys_b.ensure((size_t)nC));
+        TAD_CUDA(pay_a.ensure((size_t)nC)); TAD_CUDA(pay_b.ensure((size_t)nC));
+        TAD_CUDA(nvalid_d.ensure(1));
+        std::vector<TermDev> td(f->terms.size());
+        TAD_CUDA(cudaMemcpy(td.data(), f->terms_dev.p, td.size() * sizeof(TermDev), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < td.size(); ++i)
+        {
+            const int64_t cnt = (int64_t)td[i].M * td[i].k * td[i].n;
+            if (cnt) gen_jac_keys<<<blocks_for(cnt, 256), 256, 0, st>>>(td[i], f->d, f->n_outputs, keys_a.p, pay_a.p);
+        }
+        size_t tmp_bytes = 0;
+        cub::DoubleBuffer<int64_t> kb(keys_a.p, keys_b.p);
+        cub::DoubleBuffer<int32_t> pb(pay_a.p, pay_b.p);
+        TAD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, pb, (int)nC, 0, 64, st));
+        DevBuf<unsigned char> tmp;
+        TAD_CUDA(tmp.ensure(tmp_bytes));
+        TAD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, kb, pb, (int)nC, 0, 64, st));
+        count_valid<<<1, 1, 0, st>>>(kb.Current(), nC, nvalid_d.p);
+        TAD_CUDA(cudaMemcpyAsync(&n_valid, nvalid_d.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        TAD_CUDA(cudaStreamSynchronize(st));
+        TAD_CUDA(f->inner.ensure((size_t)std::max<int64_t>(n_valid, 1)));
+        if (n_valid > 0)
+            fill_jac<<<blocks_for(n_valid, 256), 256, 0, st>>>(kb.Current(), pb.Current(), n_valid, f->terms_dev.p, (int)f->terms.size(),
+                                                               f->n_outputs, f->inner.p);
+        jac_col_ptr<<<blocks_for(f->n_vars + 1, 256), 256, 0, st>>>(kb.Current(), n_valid, f->n_vars, f->n_outputs, f->outer.p);
+        TAD_CUDA(cudaGetLastError());
+        TAD_CUDA(cudaStreamSynchronize(st));
+    }
+    else
+    {
+        TAD_CUDA(cudaMemsetAsync(f->outer.p, 0, ((size_t)f->n_vars + 1) * sizeof(int32_t), st));
+        TAD_CUDA(f->inner.ensure(1));
+        TAD_CUDA(cudaStreamSynchronize(st));
+    }
+    f->nnz = n_valid;
+    f->n_outer = f->n_vars;
+    f->pattern_built = true;
+    return TAD_OK;
+}
+
+int ensure_pattern(tad_function f)
+{
+    if (f->pattern_built) return TAD_OK;
+    return f->is_vector ? build_pattern_vector(f) : build_pattern_scalar(f);
+}
+
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void tic(tad_function f, int i) { if (f->timing) cudaEventRecord(f->ev[i], f->stream); }
+
+// Scalar function evaluation core.  mode: PASSIVE / FIRST / SECOND.
+int eval_scalar(tad_function f, int mode, const double* x, double* f_host, double* g, double* Hv, bool project, double eps)
+{
+    if (f->is_vector) return fail(TAD_INVALID_ARGUMENT, "scalar evaluation called on a vector function");
+    if (!x && f->n_vars) return fail(TAD_INVALID_ARGUMENT, "x is null");
+    std::lock_guard<std::mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    cudaStream_t st = f->stream;
+    const int n_terms = (int)f->terms.size();
+    if (mode == TAD_MODE_SECOND) TAD_TRY(ensure_pattern(f));
+    TAD_CUDA(cudaMemsetAsync(f->err.p, 0, 8 * sizeof(int32_t), st));
+    TAD_CUDA(f->fterm.ensure((size_t)std::max(n_terms, 1)));
+    const bool gather = (f->assembly == TAD_ASSEMBLY_GATHER) && mode == TAD_MODE_SECOND;
+    if (gather && !f->pattern_built) TAD_TRY(ensure_pattern(f));
+    if (mode >= TAD_MODE_FIRST && !gather) TAD_CUDA(cudaMemsetAsync(g, 0, (size_t)f->n_vars * sizeof(double), st));
+    if (mode == TAD_MODE_SECOND && !gather && f->nnz) TAD_CUDA(cudaMemsetAsync(Hv, 0, (size_t)f->nnz * sizeof(double), st));
+    if (mode == TAD_MODE_SECOND && project)
+    {
+        TAD_CUDA(f->proj_counts.ensure(2));
+        TAD_CUDA(cudaMemsetAsync(f->proj_counts.p, 0, 2 * sizeof(int64_t), st));
+    }
+    float ms_eval = 0, ms_proj = 0, ms_asm = 0;
+    tic(f, 0);
+    for (int ti = 0; ti < n_terms; ++ti)
+    {
+        Term& t = f->terms[ti];
+        if (mode == TAD_MODE_SECOND && t.dedup && false) return TAD_NOT_SUPPORTED;
+        DevBuf<double>& stage = gather ? t.stage : f->stage;
+        TAD_CUDA(stage.ensure(stage_doubles(t, mode)));
+        tad_launch_args a;
+        fill_launch_args(f, t, mode, x, stage.p, a);
+        if (f->timing) cudaEventRecord(f->ev[1], st);
+        if (t.n > 0)
+        {
+            const int s = t.launch(t.user, &a);
+            if (s != TAD_OK) return fail(s, "element kernel launch failed");
+        }
+        if (f->timing) cudaEventRecord(f->ev[2], st);
+        TAD_TRY(sum_to(f, a.val, t.n, t.stride, 1, false, f->fterm.p + ti));
+        if (mode == TAD_MODE_SECOND && project)
+            TAD_TRY(project_dispatch(t.k, a.hess, t.n, t.stride, eps, f->proj_counts.p, st));
+        if (f->timing) cudaEventRecord(f->ev[3], st);
+        if (mode >= TAD_MODE_FIRST && !gather)
+            TAD_TRY(assemble_atomic(f->d, t, a.grad, mode == TAD_MODE_SECOND ? a.hess : nullptr, t.n, g, Hv, f->err.p, st));
+        if (f->timing)
+        {
+            cudaEventRecord(f->ev[4], st);
+            cudaEventSynchronize(f->ev[4]);
+            float m = 0;
+            cudaEventElapsedTime(&m, f->ev[1], f->ev[2]); ms_eval += m;
+            cudaEventElapsedTime(&m, f->ev[2], f->ev[3]); ms_proj += m;
+            cudaEventElapsedTime(&m, f->ev[3], f->ev[4]); ms_asm += m;
+        }
+    }
+    if (gather)
+    {
+        if (f->timing) cudaEventRecord(f->ev[3], st);
+        TAD_TRY(upload_terms_dev(f, true, mode));
+        std::vector<SeqTable> seqs((size_t)std::max(n_terms, 1));
+        for (int ti = 0; ti < n_terms; ++ti)
+        {
+            const int K = f->terms[ti].k;
+            if (K > 18) return fail(TAD_NOT_SUPPORTED, "gather assembly supports at most 18 variables per element");
+            for (int i = 0; i < K; ++i)
+                for (int j = 0; j < K; ++j) seqs[ti].idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);
+        }
+        DevBuf<SeqTable> seqs_d;
+        TAD_CUDA(seqs_d.ensure(seqs.size()));
+        TAD_CUDA(cudaMemcpyAsync(seqs_d.p, seqs.data(), seqs.size() * sizeof(SeqTable), cudaMemcpyHostToDevice, st));
+        const int64_t nt = f->n_blocks * f->d * f->d;
+        if (nt > 0)
+            gather_hessian<<<blocks_for(nt, 128), 128, 0, st>>>(f->block_ptr.p, f->contrib.p, f->block_key.p, f->vrow.p, f->terms_dev.p,
+                                                                n_terms, seqs_d.p, f->n_blocks, f->n_handles, f->d, Hv, f->err.p);
+        gather_gradient<<<blocks_for(f->n_vars, 128), 128, 0, st>>>(f->block_ptr.p, f->contrib.p, f->block_key.p, f->terms_dev.p, n_terms,
+                                                                    f->n_blocks, f->n_handles, f->d, g, f->err.p);
+        TAD_CUDA(cudaGetLastError());
+        TAD_CUDA(cudaStreamSynchronize(st));  // seqs_d is a local
+        if (f->timing)
+        {
+            cudaEventRecord(f->ev[4], st);
+            cudaEventSynchronize(f->ev[4]);
+            float m = 0;
+            cudaEventElapsedTime(&m, f->ev[3], f->ev[4]); ms_asm += m;
+        }
+    }
+    // f = sum over terms in order, with the reference's INFINITY short-circuit for eval() (ScalarFunctionImpl.hh:265-270)
+    std::vector<double> fterm((size_t)std::max(n_terms, 1), 0.0);
+    if (n_terms)
+        TAD_CUDA(cudaMemcpyAsync(fterm.data(), f->fterm.p, (size_t)n_terms * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mode == TAD_MODE_SECOND && project)
+        TAD_CUDA(cudaMemcpyAsync(f->last_proj, f->proj_counts.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TAD_CUDA(cudaStreamSynchronize(st));
+    if (f->timing)
+    {
+        cudaEventRecord(f->ev[4], st);
+        cudaEventSynchronize(f->ev[4]);
+        cudaEventElapsedTime(&f->last_ms[3], f->ev[0], f->ev[4]);
+        f->last_ms[0] = ms_eval; f->last_ms[1] = ms_proj; f->last_ms[2] = ms_asm;
+    }
+    double fv = 0.0;
+    for (int ti = 0; ti < n_terms; ++ti)
+    {
+        if (mode == TAD_MODE_PASSIVE && fv == INFINITY) break;
+        fv += fterm[(size_t)ti];
+    }
+    if (f_host) *f_host = fv;
+    const int es = check_error_word(f, true);
+    if (es == TAD_NONFINITE_DERIVATIVE && mode == TAD_MODE_PASSIVE) return TAD_OK;
+    return es;
+}
+
+int eval_vector(tad_function f, int what, const double* x, double* f_host, double* g, double* r, double* Jv)
+{
+    // what: 0 eval (r), 1 jacobian (r, J), 2 sum of squares (f), 3 sum of squares with derivatives (f, g, r, J)
+    if (!f->is_vector) return fail(TAD_INVALID_ARGUMENT, "vector evaluation called on a scalar function");
+    std::lock_guard<std::mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    cudaStream_t st = f->stream;
+    TAD_TRY(ensure_pattern(f));
+    const int n_terms = (int)f->terms.size();
+    const int mode = (what == 1 || what == 3) ? TAD_MODE_FIRST : TAD_MODE_PASSIVE;
+    TAD_CUDA(cudaMemsetAsync(f->err.p, 0, 8 * sizeof(int32_t), st));
+    TAD_CUDA(f->fterm.ensure((size_t)std::max(n_terms, 1) + 1));
+    for (int ti = 0; ti < n_terms; ++ti)
+    {
+        Term& t = f->terms[ti];
+        TAD_CUDA(f->stage.ensure(stage_doubles(t, mode)));
+        tad_launch_args a;
+        fill_launch_args(f, t, mode, x, f->stage.p, a);
+        if (t.n > 0)
+        {
+            const int s = t.launch(t.user, &a);
+            if (s != TAD_OK) return fail(s, "element kernel launch failed");
+        }
+        if (what == 2) TAD_TRY(sum_to(f, a.val, t.n, t.stride, t.M, true, f->fterm.p + ti));
+        if (what != 2 && t.n > 0)
+            scatter_residuals<<<blocks_for(t.n * t.M, 256), 256, 0, st>>>(a.val, t.n, t.stride, t.M, t.out_offset, r);
+        if (mode == TAD_MODE_FIRST && t.n > 0)
+            scatter_jacobian<<<blocks_for(t.n, 128), 128, 0, st>>>(a.grad, t.jslot.p, t.n, t.stride, t.M * t.k, Jv, f->err.p);
+    }
+    double fv = 0.0;
+    if (what == 2)
+    {
+        std::vector<double> fterm((size_t)std::max(n_terms, 1), 0.0);
+        if (n_terms) TAD_CUDA(cudaMemcpyAsync(fterm.data(), f->fterm.p, (size_t)n_terms * sizeof(double), cudaMemcpyDeviceToHost, st));
+        TAD_CUDA(cudaStreamSynchronize(st));
+        for (int ti = 0; ti < n_terms; ++ti) fv += fterm[(size_t)ti];
+    }
+    else if (what == 3)
+    {
+        TAD_TRY(sum_to(f, r, f->n_outputs, f->n_outputs, 1, true, f->fterm.p + n_terms));
+        jt_r<<<blocks_for(f->n_vars, 128), 128, 0, st>>>(f->outer.p, f->inner.p, Jv, r, f->n_vars, g);
+        TAD_CUDA(cudaMemcpyAsync(&fv, f->fterm.p + n_terms, sizeof(double), cudaMemcpyDeviceToHost, st));
+        TAD_CUDA(cudaStreamSynchronize(st));
+    }
+    else
+        TAD_CUDA(cudaStreamSynchronize(st));
+    TAD_CUDA(cudaGetLastError());
+    if (f_host) *f_host = fv;
+    const int es = check_error_word(f, true);
+    if (es == TAD_NONFINITE_DERIVATIVE && mode == TAD_MODE_PASSIVE) return TAD_OK;
+    return es;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* tad_last_error(void) { return g_last_error.c_str(); }
+
+int tad_device_count(int* count)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { *count = 0; return fail(TAD_CUDA_ERROR, "no CUDA device available (there is no CPU fallback)"); }
+    *count = c;
+    return TAD_OK;
+}
+
+int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector_function, int device, tad_function* out)
+{
+    if (!out) return fail(TAD_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (variable_dimension < 1 || n_handles < 1) return fail(TAD_INVALID_ARGUMENT, "variable_dimension and n_handles must be >= 1");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(TAD_CUDA_ERROR, "no CUDA device available: tinyad_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(TAD_INVALID_ARGUMENT, "bad device ordinal");
+    if ((int64_t)variable_dimension * n_handles >= (int64_t)INT32_MAX) return fail(TAD_NOT_SUPPORTED, "n_vars must fit int32 (Eigen StorageIndex)");
+    DeviceGuard guard(device);
+    tad_function f = new tad_function_s();
+    f->d = variable_dimension;
+    f->n_handles = n_handles;
+    f->n_vars = (int64_t)variable_dimension * n_handles;
+    f->is_vector = is_vector_function != 0;
+    f->device = device;
+    if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess || f->err.ensure(8) != cudaSuccess)
+    {
+        delete f;
+        return fail(TAD_CUDA_ERROR, "stream / buffer creation failed");
+    }
+    for (auto& e : f->ev) cudaEventCreate(&e);
+    *out = f;
+    return TAD_OK;
+}
+
+void tad_function_destroy(tad_function f)
+{
+    if (!f) return;
+    {
+        DeviceGuard guard(f->device);
+        cudaStreamSynchronize(f->stream);
+        for (auto& t : f->terms)
+            if (t.user_free && t.user) t.user_free(t.user);
+        f->terms.clear();
+        for (auto& e : f->ev) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(f->stream);
+    }
+    DeviceGuard guard(f->device);
+    delete f;
+}
+
+int tad_function_set_option(tad_function f, int option, int64_t value)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    switch (option)
+    {
+    case TAD_OPT_ASSEMBLY:
+        if (value != TAD_ASSEMBLY_ATOMIC && value != TAD_ASSEMBLY_GATHER) return fail(TAD_INVALID_ARGUMENT, "bad assembly mode");
+        f->assembly = (int)value;
+        return TAD_OK;
+    case TAD_OPT_CHUNK_ELEMENTS: f->chunk = value; return TAD_OK;
+    default: return fail(TAD_INVALID_ARGUMENT, "unknown option");
+    }
+}
+
+int tad_function_get_stream(tad_function f, void** stream)
+{
+    if (!f || !stream) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    *stream = f->stream;
+    return TAD_OK;
+}
+
+int tad_function_add_term(tad_function f, int valence, int outputs_per_element, int64_t n_elements, const int64_t* elem_handles_host,
+                          tad_launch_fn launch, void* user, void (*user_free)(void*))
+{
+    auto bail = [&](int s, const char* m) { if (user_free && user) user_free(user); return fail(s, m); };
+    if (!f || !launch) return bail(TAD_INVALID_ARGUMENT, "null function or launcher");
+    if (valence < 0 || n_elements < 0) return bail(TAD_INVALID_ARGUMENT, "negative valence or element count");
+    if (f->is_vector != (outputs_per_element > 0)) return bail(TAD_INVALID_ARGUMENT, "outputs_per_element must be > 0 exactly for vector functions");
+    std::lock_guard<std::mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    Term t;
+    t.N = valence; t.M = outputs_per_element; t.k = f->d * valence;
+    t.n = n_elements;
+    t.stride = ((n_elements + 31) / 32) * 32;
+    t.launch = launch; t.user = user; t.user_free = user_free;
+    auto cuda_bail = [&](cudaError_t e) { if (user_free && user) user_free(user); t.user = nullptr; return fail(TAD_CUDA_ERROR, std::string("CUDA error in add_term: ") + cudaGetErrorString(e)); };
+    cudaError_t ce;
+    if (elem_handles_host && n_elements > 0)
+    {
+        if ((ce = t.elem_handles.ensure((size_t)n_elements)) != cudaSuccess) return cuda_bail(ce);
+        if ((ce = cudaMemcpy(t.elem_handles.p, elem_handles_host, (size_t)n_elements * sizeof(int64_t), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_bail(ce);
+        t.has_handles = true;
+    }
+    if ((ce = t.rec_handles.ensure((size_t)std::max<int64_t>(1, (int64_t)valence * t.stride))) != cudaSuccess) return cuda_bail(ce);
+    if ((ce = t.rec_counts.ensure((size_t)std::max<int64_t>(1, t.stride))) != cudaSuccess) return cuda_bail(ce);
+    // recording pass
+    cudaMemsetAsync(f->err.p, 0, 8 * sizeof(int32_t), f->stream);
+    if (valence > 0 && t.stride > 0) fill_i32<<<blocks_for((int64_t)valence * t.stride, 256), 256, 0, f->stream>>>(t.rec_handles.p, (int64_t)valence * t.stride, -1);
+    tad_launch_args a;
+    fill_launch_args(f, t, TAD_MODE_RECORD, nullptr, nullptr, a);
+    if (n_elements > 0)
+    {
+        const int s = launch(user, &a);
+        if (s != TAD_OK) { if (user_free && user) user_free(user); return fail(s, "record kernel launch failed"); }
+        scan_counts<<<blocks_for(n_elements, 256), 256, 0, f->stream>>>(t.rec_counts.p, n_elements, f->err.p + 1);
+    }
+    int32_t h_err[2] = {0, 0};
+    if ((ce = cudaStreamSynchronize(f->stream)) != cudaSuccess) return cuda_bail(ce);
+    if ((ce = cudaMemcpy(h_err, f->err.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_bail(ce);
+    if (h_err[0] & ERR_RANGE) return bail(TAD_INDEX_OUT_OF_RANGE, "variable handle out of range in element.variables(...)");
+    if (h_err[0] & ERR_TOO_MANY) return bail(TAD_TOO_MANY_VARIABLES, "Too many variables requested via element.variables(...).");
+    t.dedup = (h_err[1] & 1) != 0;
+    f->n_elements += n_elements;
+    f->n_outputs += (int64_t)outputs_per_element * n_elements;
+    f->terms.push_back(std::move(t));
+    f->pattern_built = false;
+    return TAD_OK;
+}
+
+int64_t tad_function_n_vars(tad_function f) { return f ? f->n_vars : 0; }
+int64_t tad_function_n_elements(tad_function f) { return f ? f->n_elements : 0; }
+int64_t tad_function_n_outputs(tad_function f) { return f ? f->n_outputs : 0; }
+
+int tad_function_pattern(tad_function f, int64_t* n_outer, int64_t* nnz)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    std::lock_guard<std::mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    TAD_TRY(ensure_pattern(f));
+    if (n_outer) *n_outer = f->n_outer;
+    if (nnz) *nnz = f->nnz;
+    return TAD_OK;
+}
+
+int tad_function_pattern_copy(tad_function f, int32_t* outer_host, int32_t* inner_host)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    std::lock_guard<std::mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    TAD_TRY(ensure_pattern(f));
+    if (outer_host) TAD_CUDA(cudaMemcpy(outer_host, f->outer.p, ((size_t)f->n_outer + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (inner_host && f->nnz) TAD_CUDA(cudaMemcpy(inner_host, f->inner.p, (size_t)f->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return TAD_OK;
+}
+
+int tad_function_pattern_device(tad_function f, const int32_t** outer_dev, const int32_t** inner_dev)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    std::lock_guard<std::mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    TAD_TRY(ensure_pattern(f));
+    if (outer_dev) *outer_dev = f->outer.p;
+    if (inner_dev) *inner_dev = f->inner.p;
+    return TAD_OK;
+}
+
+int tad_function_term_table(tad_function f, int term, int32_t* handles_host)
+{
+    if (!f || term < 0 || term >= (int)f->terms.size() || !handles_host) return fail(TAD_INVALID_ARGUMENT, "bad term index");
+    DeviceGuard guard(f->device);
+    const Term& t = f->terms[(size_t)term];
+    for (int j = 0; j < t.N; ++j)
+        if (t.n) TAD_CUDA(cudaMemcpy(handles_host + (int64_t)j * t.n, t.rec_handles.p + (int64_t)j * t.stride, (size_t)t.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return TAD_OK;
+}
+
+int tad_eval(tad_function f, const double* x_dev, double* f_host)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    return eval_scalar(f, TAD_MODE_PASSIVE, x_dev, f_host, nullptr, nullptr, false, 0.0);
+}
+
+int tad_eval_with_gradient(tad_function f, const double* x_dev, double* f_host, double* g_dev)
+{
+    if (!f || !g_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    return eval_scalar(f, TAD_MODE_FIRST, x_dev, f_host, g_dev, nullptr, false, 0.0);
+}
+
+int tad_eval_with_derivatives(tad_function f, const double* x_dev, double* f_host, double* g_dev, double* H_values_dev,
+                              int project_hessian, double projection_eps)
+{
+    if (!f || !g_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    return eval_scalar(f, TAD_MODE_SECOND, x_dev, f_host, g_dev, H_values_dev, project_hessian != 0, projection_eps);
+}
+
+int tad_eval_host(tad_function f, const double* x_host, double* f_host)
+{
+    if (!f || !x_host) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    {
+        DeviceGuard guard(f->device);
+        TAD_CUDA(f->x_dev.ensure((size_t)f->n_vars));
+        TAD_CUDA(cudaMemcpyAsync(f->x_dev.p, x_host, (size_t)f->n_vars * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    }
+    return tad_eval(f, f->x_dev.p, f_host);
+}
+
+int tad_eval_with_gradient_host(tad_function f, const double* x_host, double* f_host, double* g_host)
+{
+    if (!f || !x_host || !g_host) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(f->device);
+    TAD_CUDA(f->x_dev.ensure((size_t)f->n_vars));
+    TAD_CUDA(f->g_dev.ensure((size_t)f->n_vars));
+    TAD_CUDA(cudaMemcpyAsync(f->x_dev.p, x_host, (size_t)f->n_vars * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    TAD_TRY(tad_eval_with_gradient(f, f->x_dev.p, f_host, f->g_dev.p));
+    TAD_CUDA(cudaMemcpy(g_host, f->g_dev.p, (size_t)f->n_vars * sizeof(double), cudaMemcpyDeviceToHost));
+    return TAD_OK;
+}
+
+int tad_eval_with_derivatives_host(tad_function f, const double* x_host, double* f_host, double* g_host, double* H_values_host,
+                                   int project_hessian, double projection_eps)
+{
+    if (!f || !x_host || !g_host) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(f->device);
+    int64_t nnz = 0;
+    TAD_TRY(tad_function_pattern(f, nullptr, &nnz));
+    if (nnz && !H_values_host) return fail(TAD_INVALID_ARGUMENT, "H_values_host is null");
+    TAD_CUDA(f->x_dev.ensure((size_t)f->n_vars));
+    TAD_CUDA(f->g_dev.ensure((size_t)f->n_vars));
+    TAD_CUDA(f->H_dev.ensure((size_t)std::max<int64_t>(nnz, 1)));
+    TAD_CUDA(cudaMemcpyAsync(f->x_dev.p, x_host, (size_t)f->n_vars * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    TAD_TRY(tad_eval_with_derivatives(f, f->x_dev.p, f_host, f->g_dev.p, f->H_dev.p, project_hessian, projection_eps));
+    TAD_CUDA(cudaMemcpyAsync(g_host, f->g_dev.p, (size_t)f->n_vars * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    if (nnz) TAD_CUDA(cudaMemcpyAsync(H_values_host, f->H_dev.p, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    TAD_CUDA(cudaStreamSynchronize(f->stream));
+    return TAD_OK;
+}
+
+int tad_veval(tad_function f, const double* x_dev, double* r_dev)
+{
+    if (!f || !r_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    return eval_vector(f, 0, x_dev, nullptr, nullptr, r_dev, nullptr);
+}
+int tad_veval_with_jacobian(tad_function f, const double* x_dev, double* r_dev, double* J_values_dev)
+{
+    if (!f || !r_dev || !J_values_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    return eval_vector(f, 1, x_dev, nullptr, nullptr, r_dev, J_values_dev);
+}
+int tad_veval_sum_of_squares(tad_function f, const double* x_dev, double* f_host)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    return eval_vector(f, 2, x_dev, f_host, nullptr, nullptr, nullptr);
+}
+int tad_veval_sum_of_squares_with_derivatives(tad_function f, const double* x_dev, double* f_host, double* g_dev, double* r_dev,
+                                              double* J_values_dev)
+{
+    if (!f || !g_dev || !r_dev || !J_values_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    return eval_vector(f, 3, x_dev, f_host, g_dev, r_dev, J_values_dev);
+}
+
+int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int64_t* counts_dev, void* stream)
+{
+    if (k < 1 || n < 0 || stride < n || !hess_dev) return fail(TAD_INVALID_ARGUMENT, "bad projection arguments");
+    TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts_dev, static_cast<cudaStream_t>(stream)));
+    return TAD_OK;
+}
+
+int tad_function_projection_stats(tad_function f, int64_t* stats2)
+{
+    if (!f || !stats2) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    stats2[0] = f->last_proj[0];
+    stats2[1] = f->last_proj[1];
+    return TAD_OK;
+}
+
+int tad_function_set_timing(tad_function f, int enabled)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    f->timing = enabled != 0;
+    return TAD_OK;
+}
+
+int tad_function_last_timings(tad_function f, float* ms4)
+{
+    if (!f || !ms4) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    for (int i = 0; i < 4; ++i) ms4[i] = f->last_ms[i];
+    return TAD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// tinyad_b200 -- element kernels (sm_100a).  These templates contain the USER's element
+// functor, so they are instantiated by nvcc in the user's translation unit and handed to the
+// prebuilt runtime (libtinyad_b200.so, include/tinyad_b200.h) as one launch function per term.
+//
+// They replace the body of the reference's parallel_for loops
+//   ScalarObjectiveTerm::eval / eval_with_gradient_add / eval_with_derivatives_add
+//     (include/TinyAD/Detail/ScalarObjectiveTerm.hh:162-278)
+//   VectorObjectiveTerm::eval / eval_with_jacobian_add / eval_sum_of_squares
+//     (include/TinyAD/Detail/VectorObjectiveTerm.hh:158-243,326-351)
+// up to the per-element result; projection and assembly are the runtime's kernels.
+//
+// Thread mapping of the second-order kernel: lane = element (32 consecutive elements per
+// warp, so every staging access is a fully coalesced 256-byte row), warp = Hessian part.
+// NP warps evaluate the SAME 32 elements, each with its own instantiation
+// Scalar<k, true, NP, P> that carries 1/NP of the packed Hessian in registers; the branch on
+// the part index is warp-uniform, so there is no divergence and no inter-thread traffic.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include <TinyAD/Element.hh>
+#include <tinyad_b200.h>
+
+namespace TinyAD
+{
+namespace detail
+{
+
+// Number of cooperating warps per element for a k-variable second-order scalar.
+TINYAD_HD constexpr int default_parts(int k) { return k <= 6 ? 1 : (k <= 9 ? 2 : 4); }
+
+template <class Functor, typename = void>
+struct functor_parts { static constexpr int value = 0; };
+template <class Functor>
+struct functor_parts<Functor, std::void_t<decltype(Functor::tinyad_parts)>> { static constexpr int value = Functor::tinyad_parts; };
+
+TINYAD_HD TINYAD_INLINE int64_t elem_handle(const tad_launch_args& a, int64_t e) { return a.elem_handles ? a.elem_handles[e] : e; }
+
+// Which part writes gradient component i: the one that owns Hessian entry (i, i) -- it needs grad[i] anyway.
+template <int k, int NP>
+TINYAD_HD constexpr int grad_owner(int i)
+{
+    const int s = hess_seq_index(k, i, i);
+    int p = 0;
+    while (p + 1 < NP && hess_part_begin(k, NP, p + 1) <= s) ++p;
+    return p;
+}
+
+template <class Functor, int d, int N, int M>
+__global__ void __launch_bounds__(128) record_kernel(Functor f, tad_launch_args a)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_elements) return;
+    RecorderElement<d, N, M> el(elem_handle(a, e), a.n_handles, a.error_flags);
+    (void)f(el);
+    for (int j = 0; j < N; ++j) a.rec_handles[j * a.stride + e] = (j < el.n_used) ? (int32_t)el.seen[j] : -1;
+    // count < 0 marks "a handle was requested more than once" (element kernels then need the Dedup variant)
+    a.rec_counts[e] = (el.n_calls != el.n_used) ? -el.n_used - 1 : el.n_used;
+}
+
+template <class Functor, int d, int N, int M, bool Dedup>
+__global__ void __launch_bounds__(128) passive_kernel(Functor f, tad_launch_args a)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_elements) return;
+    Element<d, N, M, double, false, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags);
+    if constexpr (M == 0)
+    {
+        const double r = f(el);
+        a.val[e] = r;
+    }
+    else
+    {
+        const Vec<double, M> r = f(el);
+        static_for<M>([&](auto mc) { constexpr int m = decltype(mc)::value; a.val[m * a.stride + e] = r.a[m]; });
+    }
+}
+
+template <class Functor, int d, int N, int M, bool Dedup>
+__global__ void __launch_bounds__(128) first_order_kernel(Functor f, tad_launch_args a)
+{
+    constexpr int k = d * N;
+    using T = Scalar<k, false>;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_elements) return;
+    Element<d, N, M, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags);
+    if constexpr (M == 0)
+    {
+        const T r = f(el);
+        a.val[e] = r.val;
+        static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; a.grad[i * a.stride + e] = r.grad[i]; });
+    }
+    else
+    {
+        const Vec<T, M> r = f(el);
+        static_for<M>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            a.val[m * a.stride + e] = r.a[m].val;
+            static_for<k>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                a.grad[(m * k + i) * a.stride + e] = r.a[m].grad[i];
+            });
+        });
+    }
+}
+
+template <class Functor, int d, int N, int NP, int P, bool Dedup>
+__device__ TINYAD_INLINE void second_order_part(const Functor& f, const tad_launch_args& a, int64_t e)
+{
+    constexpr int k = d * N;
+    using T = Scalar<k, true, NP, P>;
+    Element<d, N, 0, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags);
+    const T r = f(el);
+    if constexpr (P == 0) a.val[e] = r.val;
+    static_for<k>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if constexpr (grad_owner<k, NP>(i) == P) a.grad[i * a.stride + e] = r.grad[i];
+    });
+    static_for<T::nh>([&](auto ic) {
+        constexpr int s = decltype(ic)::value;
+        a.hess[(int64_t)(T::h_begin + s) * a.stride + e] = r.hess[s];
+    });
+}
+
+// WG = element groups (of 32) per block; block = 32 * NP * WG threads.
+template <class Functor, int d, int N, int NP, int WG, bool Dedup>
+__global__ void __launch_bounds__(32 * NP * WG) second_order_kernel(Functor f, tad_launch_args a)
+{
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int part = warp % NP;
+    const int64_t e = ((int64_t)blockIdx.x * WG + warp / NP) * 32 + lane;
+    if (e >= a.n_elements) return;
+    static_for<NP>([&](auto pc) {
+        constexpr int P = decltype(pc)::value;
+        if (part == P) second_order_part<Functor, d, N, NP, P, Dedup>(f, a, e);
+    });
+}
+
+inline int check_launch()
+{
+    return cudaGetLastError() == cudaSuccess ? (int)TAD_OK : (int)TAD_CUDA_ERROR;
+}
+
+}  // namespace detail
+
+// One objective term = functor + its launch function (the type-erased LambdaImpl of
+// ScalarObjectiveTerm.hh:78-115, with the three deferred instantiations done eagerly by nvcc).
+template <class Functor, int d, int N, int M>
+struct TermLauncher
+{
+    static constexpr int k = d * N;
+    static constexpr int NP = detail::functor_parts<Functor>::value > 0 ? detail::functor_parts<Functor>::value
+                                                                         : detail::default_parts(k);
+    static constexpr int WG = NP >= 4 ? 2 : (NP == 2 ? 2 : 4);  // 8 / 4 / 4 warps per block
+
+    Functor f;
+
+    static void destroy(void* user) { delete static_cast<TermLauncher*>(user); }
+
+    template <bool Dedup>
+    static int launch_eval(const TermLauncher* self, const tad_launch_args* a)
+    {
+        cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+        const int64_t n = a->n_elements;
+        const unsigned g128 = (unsigned)((n + 127) / 128);
+        switch (a->mode)
+        {
+        case TAD_MODE_PASSIVE:
+            detail::passive_kernel<Functor, d, N, M, Dedup><<<g128, 128, 0, st>>>(self->f, *a);
+            break;
+        case TAD_MODE_FIRST:
+            detail::first_order_kernel<Functor, d, N, M, Dedup><<<g128, 128, 0, st>>>(self->f, *a);
+            break;
+        case TAD_MODE_SECOND:
+            if constexpr (M == 0)
+            {
+                const unsigned g = (unsigned)((n + 32 * WG - 1) / (32 * WG));
+                detail::second_order_kernel<Functor, d, N, NP, WG, Dedup><<<g, 32 * NP * WG, 0, st>>>(self->f, *a);
+            }
+            else
+                return TAD_NOT_SUPPORTED;  // per-residual Hessians (VectorObjectiveTerm.hh:245-324) are out of scope
+            break;
+        default:
+            return TAD_INVALID_ARGUMENT;
+        }
+        return detail::check_launch();
+    }
+
+    static int launch(void* user, const tad_launch_args* a)
+    {
+        const TermLauncher* self = static_cast<const TermLauncher*>(user);
+        if (a->n_elements <= 0) return TAD_OK;
+        if (a->mode == TAD_MODE_RECORD)
+        {
+            cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+            detail::record_kernel<Functor, d, N, M><<<(unsigned)((a->n_elements + 127) / 128), 128, 0, st>>>(self->f, *a);
+            return detail::check_launch();
+        }
+        return a->dedup ? launch_eval<true>(self, a) : launch_eval<false>(self, a);
+    }
+};
+
+}  // namespace TinyAD
