@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- projected-Hessian assembly throughput of the tet Double<12> path (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this framework, one B200
+  torchrun ... bench.py --gpus N ...                        # N ranks, weak scaling over z-slabs
+  python bench.py --impl reference ...                      # the reference's CPU/OpenMP algorithm (oracle port)
+
+A "step" is one eval_with_hessian_proj over the whole mesh: x is resident in HBM, f / g / CSR values are
+left in HBM (`value`); `e2e` times the same call through the host-buffer C ABI (pinned host x, g, H values;
+H2D + D2H inside the timed region).  Pattern / scatter-map construction is one-time setup and reported apart.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "proj-Hessian assembled elements/s (tet Double<12>)"
+UNIT = "elements/s"
+# algorithmic work per tet (packed-symmetric flop count; compulsory HBM bytes)
+FLOPS_AD_TET, FLOPS_PROJ_TET, BYTES_TET = 41823.0, 17712.0, 353.0
+FLOPS_AD_TRI, FLOPS_PROJ_TRI, BYTES_TRI = 3943.0, 2268.0, 216.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c1", "small"],
+                    help="c2: Kuhn cube n=55 (998,250 tets) per GPU [default]; c5: n=119 (10.1M tets) split over the GPUs; "
+                         "c1: 512^2 triangle grid; small: n=16 smoke size")
+    ap.add_argument("--assembly", default="atomic", choices=["atomic", "gather"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-n", type=int, default=22, help="cube edge of the CPU-baseline sample (22 -> 63,888 tets)")
+    return ap.parse_args()
+
+
+def workload_mesh(name, rank, world):
+    """Returns (d, kind, V, conn, data, x, description).  For world > 1 each rank gets a z-slab."""
+    import tinyad_b200 as tad
+    from tinyad_b200 import meshes
+    if name == "c1":
+        V, F = meshes.grid_2d(512)
+        return 2, tad.SYMDIRICHLET2D, V, F, meshes.tri_rest_data(V, F), meshes.deform(V, 1.0 / 512, seed=0), "C1: 512x512 grid, 524,288 triangles, Double<6>"
+    n = {"c2": 55, "c5": 119, "small": 16}[name]
+    if name == "c5":                      # strong: n=119 cube, z-layers split over the ranks
+        lo = (119 * rank) // world
+        hi = (119 * (rank + 1)) // world
+        nz_total, z0, nz = 119, lo, hi - lo
+        desc = f"C5: Kuhn cube n=119 (10,110,954 tets) split in {world} z-slab(s), Double<12>"
+    else:                                 # weak: each rank owns an n x n x n block of an n x n x (n*world) lattice
+        nz_total, z0, nz = n * world, n * rank, n
+        desc = f"{name.upper()}: Kuhn cube n={n} ({6 * n ** 3:,} tets) per GPU, Double<12>"
+    V, T = meshes.kuhn_cube(n, n, nz, z0=z0, nz_total=nz_total)
+    x = meshes.deform(V, 1.0 / n, seed=0)
+    return 3, tad.SYMDIRICHLET3D, V, T, meshes.tet_rest_data(V, T), x, desc
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(sample_n, threads):
+    """Times the CPU oracle (port of the reference's OpenMP eval_with_hessian_proj) on an n^3 Kuhn cube sample."""
+    import oracle
+    import tinyad_b200 as tad
+    from tinyad_b200 import meshes
+    V, T = meshes.kuhn_cube(sample_n)
+    data = meshes.tet_rest_data(V, T)
+    x = meshes.deform(V, 1.0 / sample_n, seed=0).reshape(-1)
+    terms = [oracle.Term(oracle.SYMDIRICHLET3D, T, data)]
+    oracle.scalar_eval(3, len(V), terms, oracle.HESSIAN_PROJ, x[: 3 * len(V)], n_threads=threads)  # warm-up
+    times, phases = [], None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r = oracle.scalar_eval(3, len(V), terms, oracle.HESSIAN_PROJ, x, n_threads=threads)
+        times.append(time.perf_counter() - t0)
+        phases = r.phases
+    t = float(np.median(times))
+    return {"value": len(T) / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"Kuhn cube n={sample_n} ({len(T):,} tets), same energy / eps, median of 3 after 1 warm-up; oracle = C++ restatement "
+                      f"(reference needs Eigen, not installed)",
+            "phases_s": {k: phases[k] for k in ("eval_s", "accumulate_s", "compress_s")}, "seconds": t}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, all host threads), same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    threads = oracle.max_threads()
+    n = args.cpu_sample_n
+    oracle.lib()
+    times = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_baseline_step(n, threads) if i else cpu_baseline_step(n, threads)
+        if i >= args.warmup:
+            times.append(res[1])
+    n_el = res[0]
+    t = float(np.mean(times))
+    value = n_el / t
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"bounded sample of C2: Kuhn cube n={n} ({n_el:,} tets) per step, eval_with_hessian_proj, eps=1e-9"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"n={n} cube per step; oracle port of the reference's OpenMP path (reference itself needs Eigen, absent here)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+_cpu_cache = {}
+
+
+def cpu_baseline_step(n, threads):
+    import oracle
+    from tinyad_b200 import meshes
+    if n not in _cpu_cache:
+        V, T = meshes.kuhn_cube(n)
+        _cpu_cache[n] = (len(V), [oracle.Term(oracle.SYMDIRICHLET3D, T, meshes.tet_rest_data(V, T))],
+                         meshes.deform(V, 1.0 / n, seed=0).reshape(-1), len(T))
+    nv, terms, x, nt = _cpu_cache[n]
+    t0 = time.perf_counter()
+    oracle.scalar_eval(3, nv, terms, oracle.HESSIAN_PROJ, x, n_threads=threads)
+    return nt, time.perf_counter() - t0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import tinyad_b200 as tad
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: tinyad_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    d, kind, V, conn, data, X, desc = workload_mesh(args.workload, rank, world)
+    n_el = len(conn)
+    assembly = tad.ASSEMBLY_GATHER if args.assembly == "gather" else tad.ASSEMBLY_ATOMIC
+
+    t0 = time.perf_counter()
+    fn = tad.Function(d, len(V), device=local_rank, assembly=assembly)
+    fn.add_term(kind, conn, data)
+    nnz = fn.nnz                       # builds the pattern + scatter maps
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    x_host = torch.from_numpy(X.reshape(-1).copy()).pin_memory()
+    x_dev = x_host.cuda()
+    g_dev = torch.empty(fn.n_vars, dtype=torch.float64, device="cuda")
+    H_dev = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    g_host = torch.empty(fn.n_vars, dtype=torch.float64).pin_memory()
+    H_host = torch.empty(nnz, dtype=torch.float64).pin_memory()
+    fsum = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def step():
+        f = fn.eval_with_hessian_proj(x_dev, g_dev, H_dev)
+        if world > 1:                   # the only data-path collective of the sharded run: f (g / halo rows: see DESIGN.md)
+            fsum[0] = f
+            dist.all_reduce(fsum)
+        return f
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream_ptr = tad.ctypes.c_void_p()
+    tad.runtime().tad_function_get_stream(fn.h, tad.ctypes.byref(stream_ptr))
+    ext = torch.cuda.ExternalStream(stream_ptr.value)
+    t0 = time.perf_counter()
+    ev0.record(ext)
+    for _ in range(args.steps):
+        f = step()
+    ev1.record(ext)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    clocks = sampler.stop()
+    t_step = torch.tensor([dev_s / args.steps], dtype=torch.float64, device="cuda")
+    n_total = torch.tensor([float(n_el)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_total)
+    t_step, n_total = t_step.item(), n_total.item()
+
+    # ---- e2e through the host-buffer C ABI (pinned buffers; H2D x, D2H g + H values inside) ----
+    for _ in range(2):
+        fn.eval_with_hessian_proj_host(x_host.numpy(), out_g=g_host.numpy(), out_H=H_host.numpy())
+    barrier()
+    te = time.perf_counter()
+    e2e_steps = max(3, args.steps // 4)
+    for _ in range(e2e_steps):
+        fn.eval_with_hessian_proj_host(x_host.numpy(), out_g=g_host.numpy(), out_H=H_host.numpy())
+    barrier()
+    e2e_t = torch.tensor([(time.perf_counter() - te) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_t = e2e_t.item()
+
+    # ---- per-kernel durations (CUDA events on the function's stream, separate short pass) ----
+    fn.set_timing(True)
+    phase = {"element_ms": [], "projection_ms": [], "assembly_ms": [], "total_ms": []}
+    for _ in range(5):
+        fn.eval_with_hessian_proj(x_dev, g_dev, H_dev)
+        for k, v in fn.last_timings().items():
+            phase[k].append(v)
+    fn.set_timing(False)
+    phase = {k: float(np.median(v)) for k, v in phase.items()}
+    stats = fn.projection_stats()
+    phi = stats["rebuilt"] / max(1, n_el)
+
+    if rank == 0:
+        fp64_peak = tad.fp64_peak_tflops(local_rank, 0.5)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tet = d == 3
+        flops_el = (FLOPS_AD_TET + phi * FLOPS_PROJ_TET) if tet else (FLOPS_AD_TRI + phi * FLOPS_PROJ_TRI)
+        bytes_el = BYTES_TET if tet else BYTES_TRI
+        k_ms = {"element": phase["element_ms"], "projection": phase["projection_ms"], "assembly": phase["assembly_ms"]}
+        dominant = max(k_ms, key=k_ms.get)
+        dom_flops = {"element": FLOPS_AD_TET if tet else FLOPS_AD_TRI, "projection": phi * (FLOPS_PROJ_TET if tet else FLOPS_PROJ_TRI),
+                     "assembly": 0.0}[dominant]
+        dom_s = k_ms[dominant] * 1e-3
+        if dominant == "assembly":      # pure scatter: HBM-side roofline
+            achieved = bytes_el * n_el / dom_s / 1e9
+            roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak}
+        else:
+            achieved = dom_flops * n_el / dom_s / 1e12
+            roof = {"bound": "fp64", "kernel": dominant, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak}
+        roof["traffic"] = None
+        roof["peak_source"] = "FP64: DFMA-chain microbenchmark run in this process (measured); HBM: MEASURED_PEAKS.json" if peaks else "HBM fallback 6650 GB/s"
+        step_tflops = flops_el * n_el / t_step / 1e12
+        roof["whole_step"] = {"fp64_tflops": step_tflops, "frac_of_fp64_peak": step_tflops / fp64_peak,
+                              "hbm_gbs": bytes_el * n_el / t_step / 1e9, "frac_of_hbm_peak": bytes_el * n_el / t_step / 1e9 / hbm_peak,
+                              "algorithmic_flops_per_element": flops_el, "algorithmic_bytes_per_element": bytes_el, "phi_projected": phi}
+        roof["kernel_ms"] = k_ms
+        line = {
+            "metric": METRIC, "value": n_total / t_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong" if args.workload == "c5" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "elements_total": int(n_total), "elements_per_gpu": n_el, "nnz_per_gpu": int(nnz),
+                       "eps": 1e-9, "assembly": args.assembly, "partition": "z-slabs, one per rank" if world > 1 else "none",
+                       "l2": "no flush: per-step working set (staging + CSR values) exceeds the 126 MB L2" if n_el > 200000 else "small workload, L2-resident",
+                       "setup_s_pattern_and_maps": setup_s},
+            "e2e": {"value": n_total / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(8 * fn.n_vars), "d2h_bytes_per_step": int(8 * (fn.n_vars + nnz + 1)),
+                    "ms_per_step": e2e_t * 1e3},
+            "gpu_launches": 5 * args.steps,
+            "clocks": clocks, "roofline": roof, "wall_s_timed_region": wall, "f": f,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            import oracle
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample_n, oracle.max_threads())
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

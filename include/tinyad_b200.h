@@ -145,6 +145,10 @@ int tad_veval_sum_of_squares_with_derivatives(tad_function f, const double* x_de
  * counts_dev (optional, int64[2]) receives #decomposed and #rebuilt. */
 int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int64_t* counts_dev, void* stream);
 
+/* FP64 (DFMA) throughput of the device in TFLOP/s, best burst over ~`seconds` of back-to-back launches of an
+ * FMA-chain kernel.  This is the measured denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */
+int tad_bench_fp64_peak(int device, double seconds, double* tflops);
+
 /* Statistics of the last eval_with_derivatives (host): [0] elements eigendecomposed, [1] elements rebuilt. */
 int tad_function_projection_stats(tad_function f, int64_t* stats2);
 

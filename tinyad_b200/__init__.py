@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "tad_function_term_table", "tad_eval", "tad_eval_with_gradient", "tad_eval_with_derivatives", "tad_eval_host",
     "tad_eval_with_gradient_host", "tad_eval_with_derivatives_host", "tad_veval", "tad_veval_with_jacobian",
     "tad_veval_sum_of_squares", "tad_veval_sum_of_squares_with_derivatives", "tad_project_batch",
-    "tad_function_projection_stats", "tad_function_last_timings", "tad_function_set_timing",
+    "tad_function_projection_stats", "tad_function_last_timings", "tad_function_set_timing", "tad_bench_fp64_peak",
 ]
 
 _rt = None
@@ -87,6 +87,7 @@ def runtime():
         L.tad_function_last_timings.argtypes = [vp, vp]
         L.tad_function_set_timing.argtypes = [vp, ctypes.c_int]
         L.tad_device_count.argtypes = [vp]
+        L.tad_bench_fp64_peak.argtypes = [ctypes.c_int, dbl, vp]
         _rt = L
     return _rt
 
@@ -276,3 +277,10 @@ class Function:
 def project_batch(k, hess_dev, n, stride, eps=1e-9, counts_dev=None, stream=None):
     """tad_project_batch on a device SoA buffer (torch tensor)."""
     _check(runtime().tad_project_batch(k, n, stride, _ptr(hess_dev), eps, _ptr(counts_dev), stream))
+
+
+def fp64_peak_tflops(device=0, seconds=0.5):
+    """Measured DFMA throughput (TFLOP/s) -- the FP64 roofline denominator."""
+    t = ctypes.c_double()
+    _check(runtime().tad_bench_fp64_peak(device, seconds, ctypes.byref(t)))
+    return t.value

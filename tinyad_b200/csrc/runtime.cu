@@ -851,6 +851,26 @@ __global__ void jt_r(const int32_t* outer, const int32_t* inner, const double* J
     g[c] = 2.0 * s;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe microbenchmark (roofline denominator): 8 independent DFMA chains per thread
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------------
@@ -1559,6 +1579,39 @@ int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double
 {
     if (k < 1 || n < 0 || stride < n || !hess_dev) return fail(TAD_INVALID_ARGUMENT, "bad projection arguments");
     TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts_dev, static_cast<cudaStream_t>(stream)));
+    return TAD_OK;
+}
+
+int tad_bench_fp64_peak(int device, double seconds, double* tflops)
+{
+    if (!tflops) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    TAD_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevBuf<double> out;
+    TAD_CUDA(out.ensure(1));
+    cudaEvent_t e0, e1;
+    TAD_CUDA(cudaEventCreate(&e0));
+    TAD_CUDA(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    const double flop_per_launch = 2.0 * 64.0 * iters * 256.0 * blocks;
+    fp64_peak_kernel<<<blocks, 256>>>(out.p, iters, 1.0000001, 1e-9);  // warm-up
+    TAD_CUDA(cudaDeviceSynchronize());
+    double best = 0.0, elapsed = 0.0;
+    while (elapsed < seconds)
+    {
+        cudaEventRecord(e0);
+        for (int r = 0; r < 4; ++r) fp64_peak_kernel<<<blocks, 256>>>(out.p, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        TAD_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::max(best, 4.0 * flop_per_launch / (ms * 1e-3) / 1e12);
+        elapsed += ms * 1e-3;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
     return TAD_OK;
 }
 

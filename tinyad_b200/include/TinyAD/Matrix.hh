@@ -12,6 +12,9 @@
 namespace TinyAD
 {
 
+template <typename T, int R>
+struct Inverse;
+
 template <typename T, int R, int C>
 struct Mat
 {
@@ -119,40 +122,13 @@ struct Mat
                  - m(0, 1) * (m(1, 0) * m(2, 2) - m(1, 2) * m(2, 0))
                  + m(0, 2) * (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0));
     }
-    // Eigen fixed-size inverse: adjugate times 1/det
-    TINYAD_HD TINYAD_INLINE Mat inverse() const
+    // Eigen fixed-size inverse (adjugate times 1/det), returned as a lazy expression like Eigen does:
+    // `Mat<T,3,3> Ji = J.inverse();` materialises it, `J.inverse().squaredNorm()` streams entry by entry
+    // so that only a handful of active scalars are live at a time (register pressure, Double<12>).
+    TINYAD_HD TINYAD_INLINE Inverse<T, R> inverse() const
     {
         static_assert(R == C && (R == 1 || R == 2 || R == 3), "inverse: 1x1, 2x2 or 3x3");
-        const Mat& m = *this;
-        Mat r;
-        if constexpr (R == 1) r.a[0] = 1.0 / a[0];
-        else if constexpr (R == 2)
-        {
-            const T invdet = 1.0 / m.determinant();
-            r(0, 0) = m(1, 1) * invdet;
-            r(1, 0) = -m(1, 0) * invdet;
-            r(0, 1) = -m(0, 1) * invdet;
-            r(1, 1) = m(0, 0) * invdet;
-        }
-        else
-        {
-            // cofactor (i,j) = m(i+1,j+1) m(i+2,j+2) - m(i+1,j+2) m(i+2,j+1) (indices mod 3)
-            const T c00 = m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1);
-            const T c10 = m(2, 1) * m(0, 2) - m(2, 2) * m(0, 1);
-            const T c20 = m(0, 1) * m(1, 2) - m(0, 2) * m(1, 1);
-            const T det = c00 * m(0, 0) + c10 * m(1, 0) + c20 * m(2, 0);
-            const T invdet = 1.0 / det;
-            r(0, 0) = c00 * invdet;
-            r(0, 1) = c10 * invdet;
-            r(0, 2) = c20 * invdet;
-            r(1, 0) = (m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2)) * invdet;
-            r(1, 1) = (m(2, 2) * m(0, 0) - m(2, 0) * m(0, 2)) * invdet;
-            r(1, 2) = (m(0, 2) * m(1, 0) - m(0, 0) * m(1, 2)) * invdet;
-            r(2, 0) = (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0)) * invdet;
-            r(2, 1) = (m(2, 0) * m(0, 1) - m(2, 1) * m(0, 0)) * invdet;
-            r(2, 2) = (m(0, 0) * m(1, 1) - m(0, 1) * m(1, 0)) * invdet;
-        }
-        return r;
+        return Inverse<T, R>(*this);
     }
 };
 
@@ -162,6 +138,80 @@ template <typename T> using Vector2 = Mat<T, 2, 1>;
 template <typename T> using Vector3 = Mat<T, 3, 1>;
 template <typename T> using Matrix2 = Mat<T, 2, 2>;
 template <typename T> using Matrix3 = Mat<T, 3, 3>;
+
+template <typename T, int R>
+struct Inverse
+{
+    Mat<T, R, R> m;
+    T invdet;
+
+    TINYAD_HD TINYAD_INLINE explicit Inverse(const Mat<T, R, R>& _m) : m(_m)
+    {
+        if constexpr (R == 1) invdet = 1.0 / m.a[0];
+        else if constexpr (R == 2) invdet = 1.0 / m.determinant();
+        else
+        {
+            // det from the first-column cofactors, like Eigen's compute_inverse_size3_helper
+            const T det = cof<0, 0>() * m(0, 0) + cof<1, 0>() * m(1, 0) + cof<2, 0>() * m(2, 0);
+            invdet = 1.0 / det;
+        }
+    }
+    // cofactor (i,j) = m(i+1,j+1) m(i+2,j+2) - m(i+1,j+2) m(i+2,j+1) (indices mod 3)
+    template <int i, int j>
+    TINYAD_HD TINYAD_INLINE T cof() const
+    {
+        constexpr int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1);
+    }
+    // entry (i, j) of the inverse
+    template <int i, int j>
+    TINYAD_HD TINYAD_INLINE T coeff() const
+    {
+        if constexpr (R == 1) return invdet;
+        else if constexpr (R == 2)
+        {
+            if constexpr (i == 0 && j == 0) return m(1, 1) * invdet;
+            else if constexpr (i == 1 && j == 0) return -m(1, 0) * invdet;
+            else if constexpr (i == 0 && j == 1) return -m(0, 1) * invdet;
+            else return m(0, 0) * invdet;
+        }
+        else
+            return cof<j, i>() * invdet;
+    }
+    TINYAD_HD TINYAD_INLINE Mat<T, R, R> eval() const
+    {
+        Mat<T, R, R> r;
+        detail::static_for<R * R>([&](auto ic) {
+            constexpr int l = decltype(ic)::value;
+            r.a[l] = this->template coeff<l % R, l / R>();
+        });
+        return r;
+    }
+    TINYAD_HD TINYAD_INLINE operator Mat<T, R, R>() const { return eval(); }
+    TINYAD_HD TINYAD_INLINE T operator()(int i, int j) const { return eval()(i, j); }
+    TINYAD_HD TINYAD_INLINE T squaredNorm() const
+    {
+        T s = sqr(this->template coeff<0, 0>());
+        detail::static_for<R * R - 1>([&](auto ic) {
+            constexpr int l = decltype(ic)::value + 1;
+            s = s + sqr(this->template coeff<l % R, l / R>());
+        });
+        return s;
+    }
+    TINYAD_HD TINYAD_INLINE T norm() const { return sqrt(squaredNorm()); }
+    TINYAD_HD TINYAD_INLINE Mat<T, R, R> transpose() const { return eval().transpose(); }
+    TINYAD_HD TINYAD_INLINE T determinant() const { return invdet; }
+    TINYAD_HD TINYAD_INLINE T trace() const { return eval().trace(); }
+};
+
+template <typename T, typename U, int R, int C>
+TINYAD_HD TINYAD_INLINE auto operator*(const Mat<U, C, R>& x, const Inverse<T, R>& y) { return x * y.eval(); }
+template <typename T, typename U, int R, int C>
+TINYAD_HD TINYAD_INLINE auto operator*(const Inverse<T, R>& x, const Mat<U, R, C>& y) { return x.eval() * y; }
+template <typename T, int R>
+TINYAD_HD TINYAD_INLINE auto operator*(const double& s, const Inverse<T, R>& y) { return s * y.eval(); }
+template <typename T, int R>
+TINYAD_HD TINYAD_INLINE auto operator*(const Inverse<T, R>& y, const double& s) { return y.eval() * s; }
 
 template <typename T, typename U, int R, int C>
 TINYAD_HD TINYAD_INLINE auto operator+(const Mat<T, R, C>& x, const Mat<U, R, C>& y)
