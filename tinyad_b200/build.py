@@ -1,25 +1,30 @@
 """Builds the in-tree CUDA libraries for sm_100a with nvcc (cross-compiles without a GPU).
 
-  libtinyad_b200.so            csrc/runtime.cu   the C-ABI runtime (include/tinyad_b200.h)
-  libtinyad_b200_energies.so   csrc/energies.cu  element functors of the tests / benchmark (a "user TU")
+  libtinyad_b200.so            csrc/runtime.cu    the C-ABI runtime (include/tinyad_b200.h)
+  libtinyad_b200_energies.so   csrc/energies*.cu  element functors of the tests / benchmark (a "user TU");
+                                                  the Double<12> tet kernel is split into one object per Hessian part
+                                                  so that the heavy instantiations compile in parallel.
 """
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 NVCC = os.environ.get("TINYAD_NVCC", "/usr/local/cuda/bin/nvcc")
-COMMON = [
-    NVCC, "-std=c++17", "-O3", "-lineinfo",
+TET_PARTS = int(os.environ.get("TADX_TET_PARTS", "4"))
+FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-ccbin", "/usr/bin/g++",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "include"),
 ]
 
 RUNTIME_SO = os.path.join(HERE, "libtinyad_b200.so")
 ENERGIES_SO = os.path.join(HERE, "libtinyad_b200_energies.so")
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _newer(target, deps):
@@ -30,28 +35,41 @@ def _newer(target, deps):
 
 
 def _headers():
-    out = [os.path.join(ROOT, "include", "tinyad_b200.h")]
+    out = [os.path.join(ROOT, "include", "tinyad_b200.h"), os.path.join(HERE, "csrc", "energies.cuh"), os.path.abspath(__file__)]
     for base, _, files in os.walk(os.path.join(HERE, "include")):
         out += [os.path.join(base, f) for f in files]
     return out
 
 
+def _run(cmd, verbose):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+
+
 def build(force=False, verbose=False):
     hdrs = _headers()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    ptxas = ["-Xptxas", "-v"] if verbose else []
     jobs = []
     src = os.path.join(HERE, "csrc", "runtime.cu")
-    if force or _newer(RUNTIME_SO, [src] + hdrs):
-        jobs.append(COMMON + ["-o", RUNTIME_SO, src])
-    src = os.path.join(HERE, "csrc", "energies.cu")
-    if force or _newer(ENERGIES_SO, [src, RUNTIME_SO] + hdrs) or jobs:
-        jobs.append(COMMON + ["-Xptxas", "-v" if verbose else "-O3", "-o", ENERGIES_SO, src,
-                              "-L", HERE, "-ltinyad_b200", "-Xlinker", "-rpath=$ORIGIN"])
-    for cmd in jobs:
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    rebuild_runtime = force or _newer(RUNTIME_SO, [src] + hdrs[:1] + [os.path.join(HERE, "include", "TinyAD", "Detail", "HessLayout.hh")])
+    if rebuild_runtime:
+        jobs.append([NVCC] + FLAGS + ["-shared", "-o", RUNTIME_SO, src])
+    objs = []
+    units = [("energies.o", "energies.cu", [])] + [(f"energies_tet_part{p}.o", "energies_tet_part.cu", [f"-DTADX_PART={p}"]) for p in range(TET_PARTS)]
+    for obj, cu, defs in units:
+        o = os.path.join(OBJ_DIR, obj)
+        objs.append(o)
+        src = os.path.join(HERE, "csrc", cu)
+        if force or _newer(o, [src] + hdrs):
+            jobs.append([NVCC] + FLAGS + ptxas + [f"-DTADX_TET_PARTS={TET_PARTS}"] + defs + ["-c", "-o", o, src])
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        list(ex.map(lambda c: _run(c, verbose), jobs))
+    if jobs or not os.path.exists(ENERGIES_SO):
+        _run([NVCC] + FLAGS + ["-shared", "-o", ENERGIES_SO] + objs + ["-L", HERE, "-ltinyad_b200", "-Xlinker", "-rpath=$ORIGIN"], verbose)
     return RUNTIME_SO, ENERGIES_SO
 
 

@@ -11,6 +11,8 @@
 // of an element a near-square set of entries (few distinct row/col gradients needed).
 #pragma once
 
+// the unrolled bodies are generic lambdas; they must be inlined for the sparsity masks to fold
+#define TINYAD_LAMBDA_INLINE __attribute__((always_inline))
 #if defined(__CUDACC__)
 #define TINYAD_HD __host__ __device__
 #define TINYAD_INLINE __forceinline__

@@ -82,7 +82,7 @@ struct Element
         }
         const double* xv = x + d * vh;
         VariableVectorType v;
-        detail::static_for<d>([&](auto ic) {
+        detail::static_for<d>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
             if constexpr (active_mode)
             {
@@ -106,7 +106,7 @@ struct Element
             vh = 0;
         }
         PassiveVectorType v;
-        detail::static_for<d>([&](auto ic) { constexpr int i = decltype(ic)::value; v.a[i] = x[d * vh + i]; });
+        detail::static_for<d>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; v.a[i] = x[d * vh + i]; });
         return v;
     }
     TINYAD_HD TINYAD_INLINE double variable_passive(int64_t vh) const

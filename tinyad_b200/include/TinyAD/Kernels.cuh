@@ -9,11 +9,11 @@
 //     (include/TinyAD/Detail/VectorObjectiveTerm.hh:158-243,326-351)
 // up to the per-element result; projection and assembly are the runtime's kernels.
 //
-// Thread mapping of the second-order kernel: lane = element (32 consecutive elements per
-// warp, so every staging access is a fully coalesced 256-byte row), warp = Hessian part.
-// NP warps evaluate the SAME 32 elements, each with its own instantiation
-// Scalar<k, true, NP, P> that carries 1/NP of the packed Hessian in registers; the branch on
-// the part index is warp-uniform, so there is no divergence and no inter-thread traffic.
+// Thread mapping of the second-order kernels: thread = element (32 consecutive elements per
+// warp, so every staging access is a fully coalesced 256-byte row).  For large k the packed
+// Hessian is cut into NP parts and one kernel per part is launched, each instantiated for
+// Scalar<k, true, NP, P>, which carries val, the gradient and 1/NP of the Hessian in registers;
+// there is no divergence and no inter-thread traffic.
 #pragma once
 
 #include <cstdint>
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) passive_kernel(Functor f, tad_launch_args
     else
     {
         const Vec<double, M> r = f(el);
-        static_for<M>([&](auto mc) { constexpr int m = decltype(mc)::value; a.val[m * a.stride + e] = r.a[m]; });
+        static_for<M>([&](auto mc) TINYAD_LAMBDA_INLINE { constexpr int m = decltype(mc)::value; a.val[m * a.stride + e] = r.a[m]; });
     }
 }
 
@@ -89,15 +89,15 @@ __global__ void __launch_bounds__(128) first_order_kernel(Functor f, tad_launch_
     {
         const T r = f(el);
         a.val[e] = r.val;
-        static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; a.grad[i * a.stride + e] = r.grad[i]; });
+        static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; a.grad[i * a.stride + e] = r.grad[i]; });
     }
     else
     {
         const Vec<T, M> r = f(el);
-        static_for<M>([&](auto mc) {
+        static_for<M>([&](auto mc) TINYAD_LAMBDA_INLINE {
             constexpr int m = decltype(mc)::value;
             a.val[m * a.stride + e] = r.a[m].val;
-            static_for<k>([&](auto ic) {
+            static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
                 constexpr int i = decltype(ic)::value;
                 a.grad[(m * k + i) * a.stride + e] = r.a[m].grad[i];
             });
@@ -113,35 +113,53 @@ __device__ TINYAD_INLINE void second_order_part(const Functor& f, const tad_laun
     Element<d, N, 0, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags);
     const T r = f(el);
     if constexpr (P == 0) a.val[e] = r.val;
-    static_for<k>([&](auto ic) {
+    static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int i = decltype(ic)::value;
         if constexpr (grad_owner<k, NP>(i) == P) a.grad[i * a.stride + e] = r.grad[i];
     });
-    static_for<T::nh>([&](auto ic) {
+    static_for<T::nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int s = decltype(ic)::value;
         a.hess[(int64_t)(T::h_begin + s) * a.stride + e] = r.hess[s];
     });
 }
 
-// WG = element groups (of 32) per block; block = 32 * NP * WG threads.
-template <class Functor, int d, int N, int NP, int WG, bool Dedup>
-__global__ void __launch_bounds__(32 * NP * WG) second_order_kernel(Functor f, tad_launch_args a)
+inline int check_launch();
+
+// One kernel per Hessian part: all threads of a launch run the same instantiation
+// Scalar<k, true, NP, P>; thread = element, so staging accesses are coalesced 256-byte rows.
+template <class Functor, int d, int N, int NP, int P, bool Dedup>
+__global__ void __launch_bounds__(128) second_order_part_kernel(Functor f, tad_launch_args a)
 {
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int part = warp % NP;
-    const int64_t e = ((int64_t)blockIdx.x * WG + warp / NP) * 32 + lane;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= a.n_elements) return;
-    static_for<NP>([&](auto pc) {
-        constexpr int P = decltype(pc)::value;
-        if (part == P) second_order_part<Functor, d, N, NP, P, Dedup>(f, a, e);
-    });
+    second_order_part<Functor, d, N, NP, P, Dedup>(f, a, e);
 }
+
+// Host-side launch of one part.  A plain function template so that a heavy functor can spread its NP
+// instantiations over several translation units (`extern template` here, explicit instantiation there)
+// and compile them in parallel -- see csrc/energies_tet_part.cu.
+template <class Functor, int d, int N, int NP, int P, bool Dedup>
+int launch_second_order_part(const Functor& f, const tad_launch_args& a);
 
 inline int check_launch()
 {
     return cudaGetLastError() == cudaSuccess ? (int)TAD_OK : (int)TAD_CUDA_ERROR;
 }
+
+template <class Functor, int d, int N, int NP, int P, bool Dedup>
+int launch_second_order_part(const Functor& f, const tad_launch_args& a)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(a.stream);
+    second_order_part_kernel<Functor, d, N, NP, P, Dedup><<<(unsigned)((a.n_elements + 127) / 128), 128, 0, st>>>(f, a);
+    return check_launch();
+}
+
+// A functor may declare `static constexpr bool tinyad_unique_handles = true;` to promise that no element
+// requests the same handle twice; the run-time-search (Dedup) kernel variants are then not compiled.
+template <class Functor, typename = void>
+struct functor_unique_handles { static constexpr bool value = false; };
+template <class Functor>
+struct functor_unique_handles<Functor, std::void_t<decltype(Functor::tinyad_unique_handles)>> { static constexpr bool value = Functor::tinyad_unique_handles; };
 
 }  // namespace detail
 
@@ -153,7 +171,6 @@ struct TermLauncher
     static constexpr int k = d * N;
     static constexpr int NP = detail::functor_parts<Functor>::value > 0 ? detail::functor_parts<Functor>::value
                                                                          : detail::default_parts(k);
-    static constexpr int WG = NP >= 4 ? 2 : (NP == 2 ? 2 : 4);  // 8 / 4 / 4 warps per block
 
     Functor f;
 
@@ -176,8 +193,12 @@ struct TermLauncher
         case TAD_MODE_SECOND:
             if constexpr (M == 0)
             {
-                const unsigned g = (unsigned)((n + 32 * WG - 1) / (32 * WG));
-                detail::second_order_kernel<Functor, d, N, NP, WG, Dedup><<<g, 32 * NP * WG, 0, st>>>(self->f, *a);
+                int status = TAD_OK;
+                detail::static_for<NP>([&](auto pc) TINYAD_LAMBDA_INLINE {
+                    constexpr int P = decltype(pc)::value;
+                    if (status == TAD_OK) status = detail::launch_second_order_part<Functor, d, N, NP, P, Dedup>(self->f, *a);
+                });
+                return status;
             }
             else
                 return TAD_NOT_SUPPORTED;  // per-residual Hessians (VectorObjectiveTerm.hh:245-324) are out of scope
@@ -198,7 +219,9 @@ struct TermLauncher
             detail::record_kernel<Functor, d, N, M><<<(unsigned)((a->n_elements + 127) / 128), 128, 0, st>>>(self->f, *a);
             return detail::check_launch();
         }
-        return a->dedup ? launch_eval<true>(self, a) : launch_eval<false>(self, a);
+        if (!a->dedup) return launch_eval<false>(self, a);
+        if constexpr (detail::functor_unique_handles<Functor>::value) return TAD_NOT_SUPPORTED;
+        else return launch_eval<true>(self, a);
     }
 };
 

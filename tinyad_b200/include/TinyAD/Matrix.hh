@@ -24,13 +24,13 @@ struct Mat
 
     T a[R * C];
 
-    TINYAD_HD TINYAD_INLINE Mat() { detail::static_for<R * C>([&](auto ic) { a[decltype(ic)::value] = T(0.0); }); }
+    TINYAD_HD TINYAD_INLINE Mat() { detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { a[decltype(ic)::value] = T(0.0); }); }
     // Vec<T,2>(x, y), Vec<T,3>(x, y, z)
     TINYAD_HD TINYAD_INLINE Mat(const T& x, const T& y) { static_assert(R * C == 2, "size"); a[0] = x; a[1] = y; }
     TINYAD_HD TINYAD_INLINE Mat(const T& x, const T& y, const T& z) { static_assert(R * C == 3, "size"); a[0] = x; a[1] = y; a[2] = z; }
     // converting copy (e.g. Mat<double> -> Mat<Scalar>)
     template <typename U, typename = std::enable_if_t<!std::is_same<U, T>::value && std::is_convertible<U, T>::value>>
-    TINYAD_HD TINYAD_INLINE Mat(const Mat<U, R, C>& o) { detail::static_for<R * C>([&](auto ic) { a[decltype(ic)::value] = T(o.a[decltype(ic)::value]); }); }
+    TINYAD_HD TINYAD_INLINE Mat(const Mat<U, R, C>& o) { detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { a[decltype(ic)::value] = T(o.a[decltype(ic)::value]); }); }
 
     TINYAD_HD TINYAD_INLINE T& operator()(int i, int j) { return a[j * R + i]; }
     TINYAD_HD TINYAD_INLINE const T& operator()(int i, int j) const { return a[j * R + i]; }
@@ -48,47 +48,47 @@ struct Mat
     TINYAD_HD static constexpr int cols() { return C; }
     TINYAD_HD static constexpr int size() { return R * C; }
 
-    TINYAD_HD TINYAD_INLINE static Mat Constant(const T& v) { Mat m; detail::static_for<R * C>([&](auto ic) { m.a[decltype(ic)::value] = v; }); return m; }
+    TINYAD_HD TINYAD_INLINE static Mat Constant(const T& v) { Mat m; detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { m.a[decltype(ic)::value] = v; }); return m; }
     TINYAD_HD TINYAD_INLINE static Mat Zero() { return Mat(); }
     TINYAD_HD TINYAD_INLINE static Mat Identity()
     {
         Mat m;
-        detail::static_for<(R < C ? R : C)>([&](auto ic) { constexpr int i = decltype(ic)::value; m.a[i * R + i] = T(1.0); });
+        detail::static_for<(R < C ? R : C)>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; m.a[i * R + i] = T(1.0); });
         return m;
     }
 
     TINYAD_HD TINYAD_INLINE T squaredNorm() const
     {
         T s = a[0] * a[0];
-        detail::static_for<R * C - 1>([&](auto ic) { constexpr int i = decltype(ic)::value + 1; s = s + a[i] * a[i]; });
+        detail::static_for<R * C - 1>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value + 1; s = s + a[i] * a[i]; });
         return s;
     }
     TINYAD_HD TINYAD_INLINE T norm() const { return sqrt(squaredNorm()); }
     TINYAD_HD TINYAD_INLINE T sum() const
     {
         T s = a[0];
-        detail::static_for<R * C - 1>([&](auto ic) { constexpr int i = decltype(ic)::value + 1; s = s + a[i]; });
+        detail::static_for<R * C - 1>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value + 1; s = s + a[i]; });
         return s;
     }
     TINYAD_HD TINYAD_INLINE T trace() const
     {
         static_assert(R == C, "square");
         T s = a[0];
-        detail::static_for<R - 1>([&](auto ic) { constexpr int i = decltype(ic)::value + 1; s = s + a[i * R + i]; });
+        detail::static_for<R - 1>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value + 1; s = s + a[i * R + i]; });
         return s;
     }
     template <typename U>
     TINYAD_HD TINYAD_INLINE auto dot(const Mat<U, R, C>& o) const
     {
         auto s = a[0] * o.a[0];
-        detail::static_for<R * C - 1>([&](auto ic) { constexpr int i = decltype(ic)::value + 1; s = s + a[i] * o.a[i]; });
+        detail::static_for<R * C - 1>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value + 1; s = s + a[i] * o.a[i]; });
         return s;
     }
     template <typename U>
     TINYAD_HD TINYAD_INLINE auto cwiseProduct(const Mat<U, R, C>& o) const
     {
         Mat<decltype(a[0] * o.a[0]), R, C> r;
-        detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = a[i] * o.a[i]; });
+        detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = a[i] * o.a[i]; });
         return r;
     }
     template <typename U>
@@ -104,7 +104,7 @@ struct Mat
     TINYAD_HD TINYAD_INLINE Mat<T, C, R> transpose() const
     {
         Mat<T, C, R> t;
-        detail::static_for<R * C>([&](auto ic) { constexpr int l = decltype(ic)::value; constexpr int i = l % R, j = l / R; t.a[i * C + j] = a[l]; });
+        detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int l = decltype(ic)::value; constexpr int i = l % R, j = l / R; t.a[i * C + j] = a[l]; });
         return t;
     }
     TINYAD_HD TINYAD_INLINE Mat<T, R, 1> col(int j) const { Mat<T, R, 1> v; for (int i = 0; i < R; ++i) v.a[i] = a[j * R + i]; return v; }
@@ -181,7 +181,7 @@ struct Inverse
     TINYAD_HD TINYAD_INLINE Mat<T, R, R> eval() const
     {
         Mat<T, R, R> r;
-        detail::static_for<R * R>([&](auto ic) {
+        detail::static_for<R * R>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int l = decltype(ic)::value;
             r.a[l] = this->template coeff<l % R, l / R>();
         });
@@ -192,7 +192,7 @@ struct Inverse
     TINYAD_HD TINYAD_INLINE T squaredNorm() const
     {
         T s = sqr(this->template coeff<0, 0>());
-        detail::static_for<R * R - 1>([&](auto ic) {
+        detail::static_for<R * R - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int l = decltype(ic)::value + 1;
             s = s + sqr(this->template coeff<l % R, l / R>());
         });
@@ -217,32 +217,32 @@ template <typename T, typename U, int R, int C>
 TINYAD_HD TINYAD_INLINE auto operator+(const Mat<T, R, C>& x, const Mat<U, R, C>& y)
 {
     Mat<decltype(x.a[0] + y.a[0]), R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] + y.a[i]; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] + y.a[i]; });
     return r;
 }
 template <typename T, typename U, int R, int C>
 TINYAD_HD TINYAD_INLINE auto operator-(const Mat<T, R, C>& x, const Mat<U, R, C>& y)
 {
     Mat<decltype(x.a[0] - y.a[0]), R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] - y.a[i]; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] - y.a[i]; });
     return r;
 }
 template <typename T, int R, int C>
 TINYAD_HD TINYAD_INLINE Mat<T, R, C> operator-(const Mat<T, R, C>& x)
 {
     Mat<T, R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = -x.a[i]; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = -x.a[i]; });
     return r;
 }
 template <typename T, typename U, int R, int K, int C>
 TINYAD_HD TINYAD_INLINE auto operator*(const Mat<T, R, K>& x, const Mat<U, K, C>& y)
 {
     Mat<decltype(x.a[0] * y.a[0]), R, C> r;
-    detail::static_for<R * C>([&](auto ic) {
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int l = decltype(ic)::value;
         constexpr int i = l % R, j = l / R;
         auto s = x.a[i] * y.a[j * K];
-        detail::static_for<K - 1>([&](auto lc) { constexpr int q = decltype(lc)::value + 1; s = s + x.a[q * R + i] * y.a[j * K + q]; });
+        detail::static_for<K - 1>([&](auto lc) TINYAD_LAMBDA_INLINE { constexpr int q = decltype(lc)::value + 1; s = s + x.a[q * R + i] * y.a[j * K + q]; });
         r.a[l] = s;
     });
     return r;
@@ -252,35 +252,35 @@ template <typename T, int R, int C>
 TINYAD_HD TINYAD_INLINE Mat<T, R, C> operator*(const double& s, const Mat<T, R, C>& x)
 {
     Mat<T, R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = s * x.a[i]; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = s * x.a[i]; });
     return r;
 }
 template <typename T, int R, int C>
 TINYAD_HD TINYAD_INLINE Mat<T, R, C> operator*(const Mat<T, R, C>& x, const double& s)
 {
     Mat<T, R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] * s; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] * s; });
     return r;
 }
 template <typename T, int R, int C>
 TINYAD_HD TINYAD_INLINE Mat<T, R, C> operator/(const Mat<T, R, C>& x, const double& s)
 {
     Mat<T, R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] / s; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] / s; });
     return r;
 }
 template <int k, bool wh, int NP, int P, typename U, int R, int C>
 TINYAD_HD TINYAD_INLINE auto operator*(const Scalar<k, wh, NP, P>& s, const Mat<U, R, C>& x)
 {
     Mat<Scalar<k, wh, NP, P>, R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = s * x.a[i]; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = s * x.a[i]; });
     return r;
 }
 template <int k, bool wh, int NP, int P, typename U, int R, int C>
 TINYAD_HD TINYAD_INLINE auto operator*(const Mat<U, R, C>& x, const Scalar<k, wh, NP, P>& s)
 {
     Mat<Scalar<k, wh, NP, P>, R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] * s; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = x.a[i] * s; });
     return r;
 }
 
@@ -289,14 +289,14 @@ template <typename T, int R>
 TINYAD_HD TINYAD_INLINE Mat<T, R, 2> col_mat(const Mat<T, R, 1>& v0, const Mat<T, R, 1>& v1)
 {
     Mat<T, R, 2> M;
-    detail::static_for<R>([&](auto ic) { constexpr int i = decltype(ic)::value; M.a[i] = v0.a[i]; M.a[R + i] = v1.a[i]; });
+    detail::static_for<R>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; M.a[i] = v0.a[i]; M.a[R + i] = v1.a[i]; });
     return M;
 }
 template <typename T, int R>
 TINYAD_HD TINYAD_INLINE Mat<T, R, 3> col_mat(const Mat<T, R, 1>& v0, const Mat<T, R, 1>& v1, const Mat<T, R, 1>& v2)
 {
     Mat<T, R, 3> M;
-    detail::static_for<R>([&](auto ic) { constexpr int i = decltype(ic)::value; M.a[i] = v0.a[i]; M.a[R + i] = v1.a[i]; M.a[2 * R + i] = v2.a[i]; });
+    detail::static_for<R>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; M.a[i] = v0.a[i]; M.a[R + i] = v1.a[i]; M.a[2 * R + i] = v2.a[i]; });
     return M;
 }
 
@@ -305,7 +305,7 @@ template <int k, bool wh, int NP, int P, int R, int C>
 TINYAD_HD TINYAD_INLINE Mat<double, R, C> to_passive(const Mat<Scalar<k, wh, NP, P>, R, C>& A)
 {
     Mat<double, R, C> r;
-    detail::static_for<R * C>([&](auto ic) { constexpr int i = decltype(ic)::value; r.a[i] = A.a[i].val; });
+    detail::static_for<R * C>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; r.a[i] = A.a[i].val; });
     return r;
 }
 template <int R, int C>

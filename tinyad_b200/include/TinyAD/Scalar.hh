@@ -99,14 +99,14 @@ struct Scalar
     TINYAD_HD TINYAD_INLINE Scalar(double _val, int _idx) : val(_val), gm(1u << _idx)
     {
         zero_derivs();
-        detail::static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; grad[i] = (i == _idx) ? 1.0 : 0.0; });
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; grad[i] = (i == _idx) ? 1.0 : 0.0; });
     }
     // Active variable whose index is only known at run time: dense masks, no mask-dependent branches.
     TINYAD_HD TINYAD_INLINE static Scalar active_dense(double _val, int _idx)
     {
         Scalar res(_val);
         res.gm = g_all;
-        detail::static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; res.grad[i] = (i == _idx) ? 1.0 : 0.0; });
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; res.grad[i] = (i == _idx) ? 1.0 : 0.0; });
         return res;
     }
 
@@ -143,11 +143,11 @@ struct Scalar
         Scalar res;
         res.val = f;
         res.gm = a.gm;
-        detail::static_for<k>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
             if (a.g(i)) res.grad[i] = df * a.grad[i];
         });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             constexpr int i = Scalar::row(e), j = Scalar::col(e);
             double hv = 0.0;
@@ -164,8 +164,8 @@ struct Scalar
         Scalar res;
         res.val = -a.val;
         res.gm = a.gm;
-        detail::static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; if (a.g(i)) res.grad[i] = -a.grad[i]; });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; if (a.g(i)) res.grad[i] = -a.grad[i]; });
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             if (a.h(e)) { res.hess[e] = -a.hess[e]; res.set_h(e); }
         });
@@ -177,8 +177,8 @@ struct Scalar
         res.val = a.val * a.val;
         res.gm = a.gm;
         const double two_a = 2.0 * a.val;
-        detail::static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; if (a.g(i)) res.grad[i] = two_a * a.grad[i]; });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; if (a.g(i)) res.grad[i] = two_a * a.grad[i]; });
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             constexpr int i = Scalar::row(e), j = Scalar::col(e);
             double hv = 0.0;
@@ -195,14 +195,14 @@ struct Scalar
         Scalar res;
         res.val = Minus ? a.val - b.val : a.val + b.val;
         res.gm = a.gm | b.gm;
-        detail::static_for<k>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
             const bool ca = a.g(i), cb = b.g(i);
             if (ca && cb) res.grad[i] = Minus ? a.grad[i] - b.grad[i] : a.grad[i] + b.grad[i];
             else if (ca) res.grad[i] = a.grad[i];
             else if (cb) res.grad[i] = Minus ? -b.grad[i] : b.grad[i];
         });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             const bool ca = a.h(e), cb = b.h(e);
             if (ca && cb) res.hess[e] = Minus ? a.hess[e] - b.hess[e] : a.hess[e] + b.hess[e];
@@ -219,14 +219,14 @@ struct Scalar
         Scalar res;
         res.val = a.val * b.val;
         res.gm = a.gm | b.gm;
-        detail::static_for<k>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
             const bool ca = a.g(i), cb = b.g(i);
             if (ca && cb) res.grad[i] = b.val * a.grad[i] + a.val * b.grad[i];
             else if (ca) res.grad[i] = b.val * a.grad[i];
             else if (cb) res.grad[i] = a.val * b.grad[i];
         });
-        detail::static_for<nh>([&](auto ic) {  // Scalar.hh:765, same left-to-right order
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {  // Scalar.hh:765, same left-to-right order
             constexpr int e = decltype(ic)::value;
             constexpr int i = Scalar::row(e), j = Scalar::col(e);
             double hv = 0.0;
@@ -244,8 +244,8 @@ struct Scalar
         Scalar res;
         res.val = a.val * b;
         res.gm = a.gm;
-        detail::static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; if (a.g(i)) res.grad[i] = a.grad[i] * b; });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; if (a.g(i)) res.grad[i] = a.grad[i] * b; });
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             if (a.h(e)) { res.hess[e] = a.hess[e] * b; res.set_h(e); }
         });
@@ -258,14 +258,14 @@ struct Scalar
         Scalar res;
         res.val = a.val * inv_b;
         res.gm = a.gm | b.gm;
-        detail::static_for<k>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
             const bool ca = a.g(i), cb = b.g(i);
             if (ca && cb) res.grad[i] = (a.grad[i] - res.val * b.grad[i]) * inv_b;
             else if (ca) res.grad[i] = a.grad[i] * inv_b;
             else if (cb) res.grad[i] = -(res.val * b.grad[i]) * inv_b;
         });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             constexpr int i = Scalar::row(e), j = Scalar::col(e);
             double hv = 0.0;
@@ -286,8 +286,8 @@ struct Scalar
         res.val = a * inv_b;
         res.gm = b.gm;
         const double c = -res.val * inv_b;
-        detail::static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; if (b.g(i)) res.grad[i] = c * b.grad[i]; });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; if (b.g(i)) res.grad[i] = c * b.grad[i]; });
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             constexpr int i = Scalar::row(e), j = Scalar::col(e);
             double hv = 0.0;
@@ -309,14 +309,14 @@ struct Scalar
         res.val = ::atan2(y.val, x.val);
         res.gm = x.gm | y.gm;
         const double inv_v = 1.0 / (x.val * x.val + y.val * y.val);
-        detail::static_for<k>([&](auto ic) {
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
             const bool cy = y.g(i), cx = x.g(i);
             if (cy && cx) res.grad[i] = (x.val * y.grad[i] - y.val * x.grad[i]) * inv_v;
             else if (cy) res.grad[i] = (x.val * y.grad[i]) * inv_v;
             else if (cx) res.grad[i] = -(y.val * x.grad[i]) * inv_v;
         });
-        detail::static_for<nh>([&](auto ic) {
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int e = decltype(ic)::value;
             constexpr int i = Scalar::row(e), j = Scalar::col(e);
             // Entry (i,j), i >= j, of the reference's full matrix (du - grad dv^T)/v.  The antisymmetric
@@ -531,9 +531,9 @@ struct Scalar
 private:
     TINYAD_HD TINYAD_INLINE void zero_derivs()
     {
-        detail::static_for<k>([&](auto ic) { constexpr int i = decltype(ic)::value; grad[i] = 0.0; });
-        detail::static_for<nh>([&](auto ic) { constexpr int e = decltype(ic)::value; hess[e] = 0.0; });
-        detail::static_for<HW>([&](auto ic) { constexpr int w = decltype(ic)::value; hm[w] = 0ull; });
+        detail::static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; grad[i] = 0.0; });
+        detail::static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int e = decltype(ic)::value; hess[e] = 0.0; });
+        detail::static_for<HW>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int w = decltype(ic)::value; hm[w] = 0ull; });
     }
 };
 
