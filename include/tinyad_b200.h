@@ -78,6 +78,7 @@ typedef struct tad_function_s* tad_function;
 /* Options (tad_function_set_option). */
 #define TAD_OPT_ASSEMBLY 1      /* 0 = FP64 atomics (default), 1 = deterministic gather in element order */
 #define TAD_OPT_CHUNK_ELEMENTS 2 /* max elements per element-kernel launch (staging size); 0 = whole term */
+#define TAD_OPT_PROJECTION 3    /* 0 = low-rank update via selected eigenvectors (default), 1 = full eigendecomposition */
 #define TAD_ASSEMBLY_ATOMIC 0
 #define TAD_ASSEMBLY_GATHER 1
 
@@ -142,14 +143,16 @@ int tad_veval_sum_of_squares_with_derivatives(tad_function f, const double* x_de
 /* ---- building blocks exposed for tests / reuse ---- */
 /* Batched in-place projection of n packed symmetric k x k matrices (SoA, tile order, leading dim stride):
  * project_positive_definite (Utils/HessianProjection.hh:48-101) incl. both early-outs and the eps < 0 mode.
- * counts_dev (optional, int64[2]) receives #decomposed and #rebuilt. */
-int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int64_t* counts_dev, void* stream);
+ * method: 0 = fast path (tridiagonalisation + eigenvalues + inverse iteration for the clamped eigenpairs; the full
+ * solver only for elements that do not converge), 1 = full eigendecomposition for every element.
+ * counts_dev (optional, zeroed device int64[4]) receives #decomposed, #rebuilt, #handed to the full solver. */
+int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int method, int64_t* counts_dev, void* stream);
 
 /* FP64 (DFMA) throughput of the device in TFLOP/s, best burst over ~`seconds` of back-to-back launches of an
  * FMA-chain kernel.  This is the measured denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */
 int tad_bench_fp64_peak(int device, double seconds, double* tflops);
 
-/* Statistics of the last eval_with_derivatives (host): [0] elements eigendecomposed, [1] elements rebuilt. */
+/* Statistics of the last eval_with_derivatives (host int64[3]): elements eigendecomposed, rebuilt, handed to the full solver. */
 int tad_function_projection_stats(tad_function f, int64_t* stats2);
 
 /* Milliseconds of the phases of the last evaluation, measured with CUDA events on the function's stream:

@@ -1,0 +1,124 @@
+"""CPU: the device projection routine (Detail/Projection.hh is __host__ __device__) compiled for the host,
+checked against numpy.linalg.eigh and the oracle on random, degenerate, clustered and badly scaled matrices."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    src = os.path.join(HERE, "host", "host_projection.cc")
+    so = os.path.join(HERE, "host", "libhost_projection.so")
+    hdr = os.path.join(ROOT, "tinyad_b200", "include", "TinyAD", "Detail", "Projection.hh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "tinyad_b200", "include"),
+                        "-o", so, src], check=True)
+    L = ctypes.CDLL(so)
+    L.host_project.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
+    return L
+
+
+def pack(L, A):
+    k = A.shape[0]
+    out = np.zeros(k * (k + 1) // 2)
+    for i in range(k):
+        for j in range(i + 1):
+            out[L.host_seq_index(k, i, j)] = A[i, j]
+    return out
+
+
+def unpack(L, p, k):
+    A = np.zeros((k, k))
+    for i in range(k):
+        for j in range(i + 1):
+            A[i, j] = A[j, i] = p[L.host_seq_index(k, i, j)]
+    return A
+
+
+def reference_projection(A, eps):
+    w, V = np.linalg.eigh(A)
+    t = np.abs(w) if eps < 0 else np.maximum(w, eps)
+    return (V * t) @ V.T
+
+
+def matrices(k, rng):
+    out = []
+    for scale in (1.0, 1e-6, 1e6):
+        for _ in range(6):
+            A = rng.standard_normal((k, k)); A = (A + A.T) * scale
+            out.append(A)
+        B = rng.standard_normal((k, max(1, k - 3))); out.append(B @ B.T * scale)           # PSD, null space of dim 3
+        B = rng.standard_normal((k, max(1, k // 2))); out.append(-(B @ B.T) * scale)        # NSD, big null space
+        Q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+        w = np.concatenate([np.zeros(min(3, k)), rng.standard_normal(max(0, k - 3))])[:k]
+        out.append((Q * w) @ Q.T * scale)                                                  # exact triple zero eigenvalue
+        w = np.repeat(rng.standard_normal((k + 2) // 3), 3)[:k]
+        out.append((Q * w) @ Q.T * scale)                                                  # triple clusters everywhere
+        w = -np.abs(rng.standard_normal(k)) - 0.1
+        out.append((Q * w) @ Q.T * scale)                                                  # negative definite (all clamped)
+        D = np.diag(rng.standard_normal(k)); out.append(D * scale)                         # diagonal (T splits completely)
+        if k >= 4:
+            Bd = np.zeros((k, k)); h = k // 2
+            X = rng.standard_normal((h, h)); Bd[:h, :h] = X + X.T
+            Y = rng.standard_normal((k - h, k - h)); Bd[h:, h:] = Y + Y.T
+            out.append(Bd * scale)                                                         # block diagonal
+    out.append(np.zeros((k, k)))
+    out.append(-np.eye(k))
+    out.append(np.ones((k, k)))
+    return [0.5 * (A + A.T) for A in out]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 18])
+@pytest.mark.parametrize("eps", [1e-9, -1.0, 0.0])
+def test_projection_host(hostlib, k, eps):
+    rng = np.random.default_rng(1000 + k)
+    n_fallback = 0
+    mats = matrices(k, rng)
+    for idx, A in enumerate(mats):
+        p = pack(hostlib, A)
+        code = hostlib.host_project(k, p.ctypes.data, eps)
+        assert code in (0, 1, 2, 3), (k, idx, code)
+        got = unpack(hostlib, p, k)
+        if code == 3:
+            n_fallback += 1
+            assert np.array_equal(got, A)
+            continue
+        ora, ocode = oracle.project(A, eps)
+        # the reference's dominance early-out uses eps as given, even when negative (HessianProjection.hh:37,62)
+        ref = A if ocode == 0 else reference_projection(A, eps)
+        scale = max(np.abs(A).max(), abs(eps), 1e-300)
+        err = np.abs(got - ref).max() / scale
+        assert err <= 5e-12, (k, idx, code, err)
+        if code < 2:
+            assert np.array_equal(got, A)
+        assert (code == 0) == (ocode == 0)
+        assert np.abs(got - ora).max() / scale <= 5e-12
+    assert n_fallback <= len(mats) // 20, n_fallback
+
+
+def test_projection_host_element_hessians(hostlib):
+    """Element Hessians of the tet / triangle energies (translation null space -> clustered zero eigenvalues)."""
+    from problems import tet_problem, grid_problem
+    import scipy.sparse as sp
+    for (p, x), k in ((tet_problem(3, seed=4), 12), (grid_problem(6, seed=4), 6)):
+        kind, conn, data = p.terms[0]
+        for e in range(0, len(conn), 7):
+            # Hessian of one element through the oracle: a 1-element problem on its own vertices
+            loc = np.arange(conn.shape[1], dtype=np.int32)[None, :]
+            xe = x.reshape(-1, p.d)[conn[e]].reshape(-1)
+            r = oracle.scalar_eval(p.d, conn.shape[1], [oracle.Term(kind, loc, data[e:e + 1])], oracle.DERIVATIVES, xe)
+            A = sp.csc_matrix((r.values, r.inner, r.outer), shape=(k, k)).toarray()
+            A = 0.5 * (A + A.T)
+            pk = pack(hostlib, A)
+            code = hostlib.host_project(k, pk.ctypes.data, 1e-9)
+            assert code == 2
+            ref = reference_projection(A, 1e-9)
+            assert np.abs(unpack(hostlib, pk, k) - ref).max() <= 1e-11 * np.abs(A).max()

@@ -21,7 +21,7 @@ TAD_OK = 0
 STATUS_NAMES = {0: "TAD_OK", 1: "TAD_INVALID_ARGUMENT", 2: "TAD_NONFINITE_DERIVATIVE", 3: "TAD_CUDA_ERROR",
                 4: "TAD_TOO_MANY_VARIABLES", 5: "TAD_INDEX_OUT_OF_RANGE", 6: "TAD_NOT_SUPPORTED", 7: "TAD_OUT_OF_MEMORY"}
 ASSEMBLY_ATOMIC, ASSEMBLY_GATHER = 0, 1
-OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS = 1, 2
+OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION = 1, 2, 3
 
 # term kinds of csrc/energies.cu
 SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
@@ -82,7 +82,7 @@ def runtime():
         L.tad_veval_with_jacobian.argtypes = [vp, vp, vp, vp]
         L.tad_veval_sum_of_squares.argtypes = [vp, vp, vp]
         L.tad_veval_sum_of_squares_with_derivatives.argtypes = [vp, vp, vp, vp, vp, vp]
-        L.tad_project_batch.argtypes = [ctypes.c_int, i64, i64, vp, dbl, vp, vp]
+        L.tad_project_batch.argtypes = [ctypes.c_int, i64, i64, vp, dbl, ctypes.c_int, vp, vp]
         L.tad_function_projection_stats.argtypes = [vp, vp]
         L.tad_function_last_timings.argtypes = [vp, vp]
         L.tad_function_set_timing.argtypes = [vp, ctypes.c_int]
@@ -180,9 +180,9 @@ class Function:
         return {"element_ms": ms[0], "projection_ms": ms[1], "assembly_ms": ms[2], "total_ms": ms[3]}
 
     def projection_stats(self):
-        s = (ctypes.c_int64 * 2)()
+        s = (ctypes.c_int64 * 3)()
         _check(runtime().tad_function_projection_stats(self.h, s))
-        return {"decomposed": s[0], "rebuilt": s[1]}
+        return {"decomposed": s[0], "rebuilt": s[1], "full_solver": s[2]}
 
     @property
     def n_elements(self):
@@ -274,9 +274,9 @@ class Function:
         return f.value
 
 
-def project_batch(k, hess_dev, n, stride, eps=1e-9, counts_dev=None, stream=None):
-    """tad_project_batch on a device SoA buffer (torch tensor)."""
-    _check(runtime().tad_project_batch(k, n, stride, _ptr(hess_dev), eps, _ptr(counts_dev), stream))
+def project_batch(k, hess_dev, n, stride, eps=1e-9, method=0, counts_dev=None, stream=None):
+    """tad_project_batch on a device SoA buffer (torch tensor); counts_dev: zeroed int64[4]."""
+    _check(runtime().tad_project_batch(k, n, stride, _ptr(hess_dev), eps, method, _ptr(counts_dev), stream))
 
 
 def fp64_peak_tflops(device=0, seconds=0.5):

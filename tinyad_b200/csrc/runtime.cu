@@ -23,6 +23,7 @@
 #include <cub/cub.cuh>
 
 #include <TinyAD/Detail/HessLayout.hh>
+#include <TinyAD/Detail/Projection.hh>
 #include <tinyad_b200.h>
 
 using TinyAD::detail::hess_seq_index;
@@ -149,11 +150,15 @@ struct tad_function_s
     DevBuf<int32_t> err;           // int32[8]
     DevBuf<double> fpart;          // block partial sums
     DevBuf<double> fterm;          // per-term sums
-    DevBuf<int64_t> proj_counts;   // [2]
-    int64_t last_proj[2] = {0, 0};
+    DevBuf<unsigned long long> proj_counts;   // [4]: decomposed, rebuilt, fallback, -
+    DevBuf<int64_t> proj_list;     // elements handed to the full eigensolver
+    DevBuf<double> proj_scratch;   // R and W of the fast projection path
+    DevBuf<int32_t> proj_codes;
+    int projection_full = 0;       // option: 1 = always use the full eigensolver kernel
+    int64_t last_proj[3] = {0, 0, 0};
     float last_ms[4] = {0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    std::mutex mtx;                // eval* may be called concurrently (ScalarFunctionTest.cc:255-291)
+    std::recursive_mutex mtx;      // eval* may be called concurrently (ScalarFunctionTest.cc:255-291)
 };
 
 namespace
@@ -216,26 +221,77 @@ __global__ void __launch_bounds__(1024) reduce_stage2(const double* partial, int
 
 // ---------------------------------------------------------------------------------------------
 // PSD projection (Utils/HessianProjection.hh:23-101), one thread per element.
+//
 // Symmetric eigensolver: Householder tridiagonalisation + implicit QL with accumulated
-// transformations (the classic EISPACK tred2/tql2 scheme).
+// transformations (the classic EISPACK tred2/tql2 scheme; Eigen's SelfAdjointEigenSolver is the QR
+// flavour of the same method, any backward-stable variant gives the same projected matrix to
+// O(eps |H|)).  Data placement: the K x K work matrix and the tridiagonal live in SHARED memory,
+// laid out [entry][lane] so a warp's accesses are conflict-free 256-byte rows; per-thread local
+// arrays would spill to L2/DRAM (the first version did: 10 GB of DRAM writes per launch).
+//   * rotations are generated with one rsqrt instead of hypot + two divisions;
+//   * a QL sweep keeps the running column in registers, so each rotation reads and writes one
+//     column of V instead of two;
+//   * H is rebuilt as H + sum_j (clamp(l_j) - l_j) v_j v_j^T over the clamped eigenpairs only,
+//     which leaves H bit-unchanged when nothing is clamped (HessianProjection.hh:94-95).
 // ---------------------------------------------------------------------------------------------
 template <int K>
-__device__ void sym_eig(double (&V)[K][K], double (&d)[K], double (&e)[K])
+struct ProjSmem
 {
-    // --- tridiagonalise; V holds the symmetric matrix on entry, the orthogonal transformation on exit ---
-    for (int j = 0; j < K; ++j) d[j] = V[K - 1][j];
+    static constexpr int doubles_per_warp = (K * K + 2 * K) * 32;
+};
+
+// Full eigendecomposition of one element; S = this thread's column of the [entry][lane] shared-memory block.
+template <int K>
+__device__ void project_full_one(double* __restrict__ hp, int64_t stride, double eps, double* S, const int SS, unsigned long long* counts,
+                                 bool count_decomposed)
+{
+    constexpr int H = K * (K + 1) / 2;
+#define PV(i, j) S[((i) * K + (j)) * SS]
+#define PD(i) S[(K * K + (i)) * SS]
+#define PE(i) S[(K * K + K + (i)) * SS]
+    // ---- load, and early-out 1: positive diagonally dominant (HessianProjection.hh:23-42, :62-63) ----
+    {
+        double offsum[K], diag[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) offsum[i] = 0.0;
+#pragma unroll
+        for (int s = 0; s < H; ++s)
+        {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int r = hess_seq_rc(K, s).row, c = hess_seq_rc(K, s).col;
+            const double v = hp[(int64_t)s * stride];
+            PV(r, c) = v;
+            if (r != c)
+            {
+                PV(c, r) = v;
+                offsum[r] += fabs(v);
+                offsum[c] += fabs(v);
+            }
+            else
+                diag[r] = v;
+        }
+        bool dominant = true;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+            if (diag[i] < offsum[i] + eps) dominant = false;
+        if (dominant) return;
+    }
+
+    // ---- tridiagonalise; V holds the symmetric matrix on entry, the orthogonal transformation on exit ----
+    for (int j = 0; j < K; ++j) PD(j) = PV(K - 1, j);
     for (int i = K - 1; i > 0; --i)
     {
         double scale = 0.0, h = 0.0;
-        for (int q = 0; q < i; ++q) scale += fabs(d[q]);
+        for (int q = 0; q < i; ++q) scale += fabs(PD(q));
         if (scale == 0.0)
         {
-            e[i] = d[i - 1];
+            PE(i) = PD(i - 1);
             for (int j = 0; j < i; ++j)
             {
-                d[j] = V[i - 1][j];
-                V[i][j] = 0.0;
-                V[j][i] = 0.0;
+                PD(j) = PV(i - 1, j);
+                PV(i, j) = 0.0;
+                PV(j, i) = 0.0;
             }
         }
         else
@@ -243,215 +299,367 @@ __device__ void sym_eig(double (&V)[K][K], double (&d)[K], double (&e)[K])
             const double inv_scale = 1.0 / scale;
             for (int q = 0; q < i; ++q)
             {
-                d[q] *= inv_scale;
-                h += d[q] * d[q];
+                const double t = PD(q) * inv_scale;
+                PD(q) = t;
+                h += t * t;
             }
-            double f = d[i - 1];
+            double f = PD(i - 1);
             double g = sqrt(h);
             if (f > 0) g = -g;
-            e[i] = scale * g;
+            PE(i) = scale * g;
             h -= f * g;
-            d[i - 1] = f - g;
-            for (int j = 0; j < i; ++j) e[j] = 0.0;
+            PD(i - 1) = f - g;
+            for (int j = 0; j < i; ++j) PE(j) = 0.0;
             for (int j = 0; j < i; ++j)
             {
-                f = d[j];
-                V[j][i] = f;
-                g = e[j] + V[j][j] * f;
+                f = PD(j);
+                PV(j, i) = f;
+                g = PE(j) + PV(j, j) * f;
                 for (int q = j + 1; q <= i - 1; ++q)
                 {
-                    g += V[q][j] * d[q];
-                    e[q] += V[q][j] * f;
+                    const double vqj = PV(q, j);
+                    g += vqj * PD(q);
+                    PE(q) += vqj * f;
                 }
-                e[j] = g;
+                PE(j) = g;
             }
             f = 0.0;
             const double inv_h = 1.0 / h;
             for (int j = 0; j < i; ++j)
             {
-                e[j] *= inv_h;
-                f += e[j] * d[j];
+                const double t = PE(j) * inv_h;
+                PE(j) = t;
+                f += t * PD(j);
             }
             const double hh = f / (h + h);
-            for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+            for (int j = 0; j < i; ++j) PE(j) -= hh * PD(j);
             for (int j = 0; j < i; ++j)
             {
-                f = d[j];
-                g = e[j];
-                for (int q = j; q <= i - 1; ++q) V[q][j] -= (f * e[q] + g * d[q]);
-                d[j] = V[i - 1][j];
-                V[i][j] = 0.0;
+                f = PD(j);
+                g = PE(j);
+                for (int q = j; q <= i - 1; ++q) PV(q, j) -= (f * PE(q) + g * PD(q));
+                PD(j) = PV(i - 1, j);
+                PV(i, j) = 0.0;
             }
         }
-        d[i] = h;
+        PD(i) = h;
     }
     for (int i = 0; i < K - 1; ++i)
     {
-        V[K - 1][i] = V[i][i];
-        V[i][i] = 1.0;
-        const double h = d[i + 1];
+        PV(K - 1, i) = PV(i, i);
+        PV(i, i) = 1.0;
+        const double h = PD(i + 1);
         if (h != 0.0)
         {
             const double inv_h = 1.0 / h;
-            for (int q = 0; q <= i; ++q) d[q] = V[q][i + 1] * inv_h;
+            for (int q = 0; q <= i; ++q) PD(q) = PV(q, i + 1) * inv_h;
             for (int j = 0; j <= i; ++j)
             {
                 double g = 0.0;
-                for (int q = 0; q <= i; ++q) g += V[q][i + 1] * V[q][j];
-                for (int q = 0; q <= i; ++q) V[q][j] -= g * d[q];
+                for (int q = 0; q <= i; ++q) g += PV(q, i + 1) * PV(q, j);
+                for (int q = 0; q <= i; ++q) PV(q, j) -= g * PD(q);
             }
         }
-        for (int q = 0; q <= i; ++q) V[q][i + 1] = 0.0;
+        for (int q = 0; q <= i; ++q) PV(q, i + 1) = 0.0;
     }
     for (int j = 0; j < K; ++j)
     {
-        d[j] = V[K - 1][j];
-        V[K - 1][j] = 0.0;
+        PD(j) = PV(K - 1, j);
+        PV(K - 1, j) = 0.0;
     }
-    V[K - 1][K - 1] = 1.0;
-    e[0] = 0.0;
-
-    // --- implicit QL on the tridiagonal (d, e), rotations accumulated into V ---
-    for (int i = 1; i < K; ++i) e[i - 1] = e[i];
-    e[K - 1] = 0.0;
+    PV(K - 1, K - 1) = 1.0;
+    PE(0) = 0.0;
+    // ---- implicit QL on the tridiagonal (d, e), rotations accumulated into V ----
+    for (int i = 1; i < K; ++i) PE(i - 1) = PE(i);
+    PE(K - 1) = 0.0;
     double f = 0.0, tst1 = 0.0;
-    const double eps = 2.220446049250313e-16;
+    const double meps = 2.220446049250313e-16;
     for (int l = 0; l < K; ++l)
     {
-        tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+        tst1 = fmax(tst1, fabs(PD(l)) + fabs(PE(l)));
         int m = l;
         while (m < K - 1)
         {
-            if (fabs(e[m]) <= eps * tst1) break;
+            if (fabs(PE(m)) <= meps * tst1) break;
             ++m;
         }
         if (m > l)
         {
             int iter = 0;
+            double el_abs;
             do
             {
                 ++iter;
-                double g = d[l];
-                double p = (d[l + 1] - g) / (2.0 * e[l]);
-                double r = hypot(p, 1.0);
+                const double e_l = PE(l);
+                double g = PD(l);
+                double p = (PD(l + 1) - g) / (2.0 * e_l);
+                double r = (fabs(p) < 1e150) ? sqrt(fma(p, p, 1.0)) : fabs(p);
                 if (p < 0) r = -r;
-                d[l] = e[l] / (p + r);
-                d[l + 1] = e[l] * (p + r);
-                const double dl1 = d[l + 1];
-                double h = g - d[l];
-                for (int i = l + 2; i < K; ++i) d[i] -= h;
+                const double dl = e_l / (p + r);
+                const double dl1 = e_l * (p + r);
+                PD(l) = dl;
+                PD(l + 1) = dl1;
+                double h = g - dl;
+                for (int i = l + 2; i < K; ++i) PD(i) -= h;
                 f += h;
-                p = d[m];
+                p = PD(m);
                 double c = 1.0, c2 = 1.0, c3 = 1.0;
-                const double el1 = e[l + 1];
+                const double el1 = PE(l + 1);
                 double s = 0.0, s2 = 0.0;
+                double x[K];  // running column (column i+1 of V while the sweep moves down)
+#pragma unroll
+                for (int q = 0; q < K; ++q) x[q] = PV(q, m);
                 for (int i = m - 1; i >= l; --i)
                 {
                     c3 = c2;
                     c2 = c;
                     s2 = s;
-                    g = c * e[i];
+                    const double ei = PE(i), di = PD(i);
+                    g = c * ei;
                     h = c * p;
-                    r = hypot(p, e[i]);
-                    e[i + 1] = s * r;
-                    const double inv_r = 1.0 / r;
-                    s = e[i] * inv_r;
-                    c = p * inv_r;
-                    p = c * d[i] - s * g;
-                    d[i + 1] = h + s * (c * g + s * d[i]);
+                    const double t = fma(p, p, ei * ei);
+                    double rinv;
+                    if (t > 1e-280 && t < 1e280)
+                    {
+                        rinv = rsqrt(t);
+                        r = t * rinv;
+                    }
+                    else
+                    {
+                        r = hypot(p, ei);
+                        rinv = 1.0 / r;
+                    }
+                    PE(i + 1) = s * r;
+                    s = ei * rinv;
+                    c = p * rinv;
+                    p = c * di - s * g;
+                    PD(i + 1) = h + s * (c * g + s * di);
+#pragma unroll
                     for (int q = 0; q < K; ++q)
                     {
-                        h = V[q][i + 1];
-                        V[q][i + 1] = s * V[q][i] + c * h;
-                        V[q][i] = c * V[q][i] - s * h;
+                        const double y = PV(q, i);
+                        PV(q, i + 1) = s * y + c * x[q];
+                        x[q] = c * y - s * x[q];
                     }
                 }
-                p = -s * s2 * c3 * el1 * e[l] / dl1;
-                e[l] = s * p;
-                d[l] = c * p;
-            } while (fabs(e[l]) > eps * tst1 && iter < 60);
+#pragma unroll
+                for (int q = 0; q < K; ++q) PV(q, l) = x[q];
+                p = -s * s2 * c3 * el1 * e_l / dl1;
+                PE(l) = s * p;
+                PD(l) = c * p;
+                el_abs = fabs(s * p);
+            } while (el_abs > meps * tst1 && iter < 60);
         }
-        d[l] = d[l] + f;
-        e[l] = 0.0;
+        PD(l) = PD(l) + f;
+        PE(l) = 0.0;
     }
-}
 
-template <int K>
-__global__ void __launch_bounds__(128) project_kernel(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts)
-{
-    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (el >= n) return;
-    constexpr int H = K * (K + 1) / 2;
-    double V[K][K];
-    double dg[K], off[K];
-    for (int s = 0; s < H; ++s)
-    {
-        const TinyAD::detail::HessRC rc = hess_seq_rc(K, s);
-        const double v = hess[(int64_t)s * stride + el];
-        V[rc.row][rc.col] = v;
-        V[rc.col][rc.row] = v;
-    }
-    // early out 1: positive diagonally dominant (HessianProjection.hh:23-42, :62-63)
-    bool dominant = true;
-    for (int i = 0; i < K; ++i)
-    {
-        double o = 0.0;
-        for (int j = 0; j < K; ++j)
-            if (i != j) o += fabs(V[i][j]);
-        if (V[i][i] < o + eps) dominant = false;
-    }
-    if (dominant) return;
-    sym_eig<K>(V, dg, off);
-    // clamp (HessianProjection.hh:71-91)
+    // ---- clamp (HessianProjection.hh:71-91) and rebuild from the clamped eigenpairs only ----
+    if (counts && count_decomposed) atomicAdd(&counts[0], 1ull);
+    double acc[H];
+#pragma unroll
+    for (int s = 0; s < H; ++s) acc[s] = 0.0;
     bool all_positive = true;
-    for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j)
     {
-        if (eps < 0)
+        const double lam = PD(j);
+        double target = lam;
+        if (eps < 0) { if (lam < 0) target = -lam; }
+        else if (lam < eps) target = eps;
+        if (target != lam)
         {
-            if (dg[i] < 0) { dg[i] = -dg[i]; all_positive = false; }
+            all_positive = false;
+            const double delta = target - lam;
+            double v[K], dv[K];
+#pragma unroll
+            for (int q = 0; q < K; ++q)
+            {
+                v[q] = PV(q, j);
+                dv[q] = delta * v[q];
+            }
+#pragma unroll
+            for (int s = 0; s < H; ++s) acc[s] = fma(dv[hess_seq_rc(K, s).row], v[hess_seq_rc(K, s).col], acc[s]);
         }
-        else if (dg[i] < eps) { dg[i] = eps; all_positive = false; }
     }
-    if (counts) atomicAdd(&counts[0], 1ull);
     // early out 2: nothing clamped -> H stays bit-unchanged (:94-95)
     if (all_positive) return;
     if (counts) atomicAdd(&counts[1], 1ull);
-    // H = V D V^T (:98), lower triangle only
-    for (int s = 0; s < H; ++s)
+#pragma unroll
+    for (int s = 0; s < H; ++s) hp[(int64_t)s * stride] += acc[s];
+#undef PV
+#undef PD
+#undef PE
+}
+
+template <int K>
+__global__ void __launch_bounds__(32) project_kernel_full(double* __restrict__ hess, int64_t n, int64_t stride, double eps,
+                                                          unsigned long long* counts)
+{
+    extern __shared__ double proj_smem[];
+    const int64_t el = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    if (el >= n) return;
+    project_full_one<K>(hess + el, stride, eps, proj_smem + threadIdx.x, 32, counts, true);
+}
+
+// The elements the fast path could not finish (counts[2] of them, normally none or a fraction of a percent): a small
+// fixed grid strides over the list; the work matrix lives in a global scratch buffer ([entry][thread], coalesced) so that
+// the launch needs no shared-memory carve-out switch and costs nothing when the list is empty.
+constexpr int kListBlocks = 296, kListThreads = 64;
+template <int K>
+__global__ void __launch_bounds__(kListThreads) project_kernel_list(double* __restrict__ hess, int64_t stride, double eps,
+                                                                    unsigned long long* counts, const int64_t* __restrict__ list,
+                                                                    double* __restrict__ work)
+{
+    const int64_t count = (int64_t)counts[2];
+    const int nthreads = gridDim.x * blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < count; i += nthreads)
+        project_full_one<K>(hess + list[i], stride, eps, work + tid, nthreads, counts, false);
+}
+
+// Fast path (Detail/Projection.hh), three kernels with different resource profiles, one thread per element:
+//   A  tridiagonalise  -- the packed matrix in registers, fully unrolled (register-heavy, ILP-rich)
+//   B  select vectors  -- eigenvalues of T, eigenvectors of the moved eigenvalues by inverse iteration
+//                         (scalar recurrences on small arrays: few registers, runs at high occupancy)
+//   C  apply           -- back-transform through the reflectors, H += low-rank term (register-heavy)
+// Scratch between them is structure-of-arrays over the elements (coalesced 256-byte rows).
+struct ProjScratch
+{
+    double* R;       // [ProjLayout<K>::nR][stride]
+    double* W;       // [ProjLayout<K>::nW][stride]
+    int32_t* codes;  // [stride] ProjectCode per element
+    int64_t* list;   // elements handed to the full solver
+};
+
+template <int K>
+__global__ void __launch_bounds__(128) project_kernel_a(const double* __restrict__ hess, int64_t n, int64_t stride, double eps, ProjScratch sc)
+{
+    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= n) return;
+    const double* hp = hess + el;
+    double* rp = sc.R + el;
+    sc.codes[el] = TinyAD::detail::proj_tridiagonalize<K>([&](int s) { return hp[(int64_t)s * stride]; },
+                                                          [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
+}
+
+template <int K>
+__global__ void __launch_bounds__(128, 8) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc)
+{
+    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= n) return;
+    if (sc.codes[el] == TinyAD::detail::PROJ_DOMINANT) return;
+    const double* rp = sc.R + el;
+    double* wp = sc.W + el;
+    const int code = TinyAD::detail::proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; },
+                                                            [&](int i, double v) { wp[(int64_t)i * stride] = v; },
+                                                            [&](int i) { return wp[(int64_t)i * stride]; }, eps);
+    sc.codes[el] = code;
+    if (counts) atomicAdd(&counts[0], 1ull);
+    if (code == TinyAD::detail::PROJ_REBUILT && counts) atomicAdd(&counts[1], 1ull);
+    if (code == TinyAD::detail::PROJ_FALLBACK)
     {
-        const TinyAD::detail::HessRC rc = hess_seq_rc(K, s);
-        double acc = 0.0;
-        for (int l = 0; l < K; ++l) acc += V[rc.row][l] * dg[l] * V[rc.col][l];
-        hess[(int64_t)s * stride + el] = acc;
+        const unsigned long long slot = atomicAdd(&counts[2], 1ull);
+        sc.list[slot] = el;
     }
 }
 
 template <int K>
-int launch_project(double* hess, int64_t n, int64_t stride, double eps, int64_t* counts, cudaStream_t st)
+__global__ void __launch_bounds__(128) project_kernel_c(double* __restrict__ hess, int64_t n, int64_t stride, double eps, ProjScratch sc)
 {
-    project_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(hess, n, stride, eps, (unsigned long long*)counts);
+    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= n) return;
+    if (sc.codes[el] != TinyAD::detail::PROJ_REBUILT) return;
+    double* hp = hess + el;
+    const double* rp = sc.R + el;
+    const double* wp = sc.W + el;
+    TinyAD::detail::proj_apply<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
+                                  [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { hp[(int64_t)s * stride] = v; }, eps);
+}
+
+template <int K>
+size_t project_scratch_doubles(int64_t stride)
+{
+    using L = TinyAD::detail::ProjLayout<K>;
+    return (size_t)(L::nR + L::nW) * (size_t)stride + (size_t)(K * K + 2 * K) * kListBlocks * kListThreads;
+}
+
+// counts: device uint64[4] = {#decomposed, #rebuilt, #full solver, unused}.  scratch_d: project_scratch_doubles<K>(stride)
+// doubles, scratch_i: stride int32 + n int64 (see project_scratch_bytes).
+template <int K>
+int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, int32_t* codes,
+                   int64_t* list, bool full_only, cudaStream_t st)
+{
+    using L = TinyAD::detail::ProjLayout<K>;
+    constexpr size_t smem = (size_t)ProjSmem<K>::doubles_per_warp * sizeof(double);
+    static bool configured = false;
+    if (!configured)
+    {
+        if (cudaFuncSetAttribute(project_kernel_full<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel");
+        configured = true;
+    }
+    if (full_only)
+        project_kernel_full<K><<<(unsigned)((n + 31) / 32), 32, smem, st>>>(hess, n, stride, eps, counts);
+    else
+    {
+        ProjScratch sc;
+        sc.R = scratch_d;
+        sc.W = scratch_d + (size_t)L::nR * stride;
+        sc.codes = codes;
+        sc.list = list;
+        const unsigned g = (unsigned)((n + 127) / 128);
+        project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+        project_kernel_b<K><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
+        project_kernel_c<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+        // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
+        project_kernel_list<K><<<kListBlocks, kListThreads, 0, st>>>(hess, stride, eps, counts, list,
+                                                                     scratch_d + (size_t)(L::nR + L::nW) * stride);
+    }
     return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "project kernel launch failed");
 }
 
-int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, int64_t* counts, cudaStream_t st)
+size_t project_scratch_doubles_rt(int k, int64_t stride)
+{
+    switch (k)
+    {
+    case 1: return project_scratch_doubles<1>(stride);
+    case 2: return project_scratch_doubles<2>(stride);
+    case 3: return project_scratch_doubles<3>(stride);
+    case 4: return project_scratch_doubles<4>(stride);
+    case 5: return project_scratch_doubles<5>(stride);
+    case 6: return project_scratch_doubles<6>(stride);
+    case 7: return project_scratch_doubles<7>(stride);
+    case 8: return project_scratch_doubles<8>(stride);
+    case 9: return project_scratch_doubles<9>(stride);
+    case 10: return project_scratch_doubles<10>(stride);
+    case 12: return project_scratch_doubles<12>(stride);
+    case 15: return project_scratch_doubles<15>(stride);
+    case 16: return project_scratch_doubles<16>(stride);
+    case 18: return project_scratch_doubles<18>(stride);
+    default: return 0;
+    }
+}
+
+int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d,
+                     int32_t* codes, int64_t* list, bool full_only, cudaStream_t st)
 {
     if (n <= 0 || k <= 0) return TAD_OK;
     switch (k)
     {
-    case 1: return launch_project<1>(hess, n, stride, eps, counts, st);
-    case 2: return launch_project<2>(hess, n, stride, eps, counts, st);
-    case 3: return launch_project<3>(hess, n, stride, eps, counts, st);
-    case 4: return launch_project<4>(hess, n, stride, eps, counts, st);
-    case 5: return launch_project<5>(hess, n, stride, eps, counts, st);
-    case 6: return launch_project<6>(hess, n, stride, eps, counts, st);
-    case 7: return launch_project<7>(hess, n, stride, eps, counts, st);
-    case 8: return launch_project<8>(hess, n, stride, eps, counts, st);
-    case 9: return launch_project<9>(hess, n, stride, eps, counts, st);
-    case 10: return launch_project<10>(hess, n, stride, eps, counts, st);
-    case 12: return launch_project<12>(hess, n, stride, eps, counts, st);
-    case 15: return launch_project<15>(hess, n, stride, eps, counts, st);
-    case 16: return launch_project<16>(hess, n, stride, eps, counts, st);
-    case 18: return launch_project<18>(hess, n, stride, eps, counts, st);
+    case 1: return launch_project<1>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 2: return launch_project<2>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 3: return launch_project<3>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 4: return launch_project<4>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 5: return launch_project<5>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 6: return launch_project<6>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 7: return launch_project<7>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 8: return launch_project<8>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 9: return launch_project<9>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 10: return launch_project<10>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 12: return launch_project<12>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
     default: return fail(TAD_NOT_SUPPORTED, "Hessian projection is instantiated for k in {1..10,12,15,16,18}");
     }
 }
@@ -1157,7 +1365,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
 {
     if (f->is_vector) return fail(TAD_INVALID_ARGUMENT, "scalar evaluation called on a vector function");
     if (!x && f->n_vars) return fail(TAD_INVALID_ARGUMENT, "x is null");
-    std::lock_guard<std::mutex> lock(f->mtx);
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     cudaStream_t st = f->stream;
     const int n_terms = (int)f->terms.size();
@@ -1170,8 +1378,18 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     if (mode == TAD_MODE_SECOND && !gather && f->nnz) TAD_CUDA(cudaMemsetAsync(Hv, 0, (size_t)f->nnz * sizeof(double), st));
     if (mode == TAD_MODE_SECOND && project)
     {
-        TAD_CUDA(f->proj_counts.ensure(2));
-        TAD_CUDA(cudaMemsetAsync(f->proj_counts.p, 0, 2 * sizeof(int64_t), st));
+        TAD_CUDA(f->proj_counts.ensure(4));
+        TAD_CUDA(cudaMemsetAsync(f->proj_counts.p, 0, 4 * sizeof(unsigned long long), st));
+        int64_t max_n = 0;
+        size_t max_scratch = 1;
+        for (auto& t : f->terms)
+        {
+            max_n = std::max(max_n, t.stride);
+            max_scratch = std::max(max_scratch, project_scratch_doubles_rt(t.k, t.stride));
+        }
+        TAD_CUDA(f->proj_list.ensure((size_t)std::max<int64_t>(max_n, 1)));
+        TAD_CUDA(f->proj_codes.ensure((size_t)std::max<int64_t>(max_n, 1)));
+        if (!f->projection_full) TAD_CUDA(f->proj_scratch.ensure(max_scratch));
     }
     float ms_eval = 0, ms_proj = 0, ms_asm = 0;
     tic(f, 0);
@@ -1191,8 +1409,11 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         }
         if (f->timing) cudaEventRecord(f->ev[2], st);
         TAD_TRY(sum_to(f, a.val, t.n, t.stride, 1, false, f->fterm.p + ti));
+        if (mode == TAD_MODE_SECOND && project && ti > 0)  // the fallback list is per term
+            TAD_CUDA(cudaMemsetAsync(f->proj_counts.p + 2, 0, sizeof(unsigned long long), st));
         if (mode == TAD_MODE_SECOND && project)
-            TAD_TRY(project_dispatch(t.k, a.hess, t.n, t.stride, eps, f->proj_counts.p, st));
+            TAD_TRY(project_dispatch(t.k, a.hess, t.n, t.stride, eps, f->proj_counts.p, f->proj_scratch.p, f->proj_codes.p, f->proj_list.p,
+                                     f->projection_full != 0, st));
         if (f->timing) cudaEventRecord(f->ev[3], st);
         if (mode >= TAD_MODE_FIRST && !gather)
             TAD_TRY(assemble_atomic(f->d, t, a.grad, mode == TAD_MODE_SECOND ? a.hess : nullptr, t.n, g, Hv, f->err.p, st));
@@ -1242,7 +1463,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     if (n_terms)
         TAD_CUDA(cudaMemcpyAsync(fterm.data(), f->fterm.p, (size_t)n_terms * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (mode == TAD_MODE_SECOND && project)
-        TAD_CUDA(cudaMemcpyAsync(f->last_proj, f->proj_counts.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        TAD_CUDA(cudaMemcpyAsync(f->last_proj, f->proj_counts.p, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     TAD_CUDA(cudaStreamSynchronize(st));
     if (f->timing)
     {
@@ -1267,7 +1488,7 @@ int eval_vector(tad_function f, int what, const double* x, double* f_host, doubl
 {
     // what: 0 eval (r), 1 jacobian (r, J), 2 sum of squares (f), 3 sum of squares with derivatives (f, g, r, J)
     if (!f->is_vector) return fail(TAD_INVALID_ARGUMENT, "vector evaluation called on a scalar function");
-    std::lock_guard<std::mutex> lock(f->mtx);
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     cudaStream_t st = f->stream;
     TAD_TRY(ensure_pattern(f));
@@ -1386,6 +1607,7 @@ int tad_function_set_option(tad_function f, int option, int64_t value)
         f->assembly = (int)value;
         return TAD_OK;
     case TAD_OPT_CHUNK_ELEMENTS: f->chunk = value; return TAD_OK;
+    case TAD_OPT_PROJECTION: f->projection_full = value != 0; return TAD_OK;
     default: return fail(TAD_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -1404,7 +1626,7 @@ int tad_function_add_term(tad_function f, int valence, int outputs_per_element, 
     if (!f || !launch) return bail(TAD_INVALID_ARGUMENT, "null function or launcher");
     if (valence < 0 || n_elements < 0) return bail(TAD_INVALID_ARGUMENT, "negative valence or element count");
     if (f->is_vector != (outputs_per_element > 0)) return bail(TAD_INVALID_ARGUMENT, "outputs_per_element must be > 0 exactly for vector functions");
-    std::lock_guard<std::mutex> lock(f->mtx);
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     Term t;
     t.N = valence; t.M = outputs_per_element; t.k = f->d * valence;
@@ -1452,7 +1674,7 @@ int64_t tad_function_n_outputs(tad_function f) { return f ? f->n_outputs : 0; }
 int tad_function_pattern(tad_function f, int64_t* n_outer, int64_t* nnz)
 {
     if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
-    std::lock_guard<std::mutex> lock(f->mtx);
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     TAD_TRY(ensure_pattern(f));
     if (n_outer) *n_outer = f->n_outer;
@@ -1463,7 +1685,7 @@ int tad_function_pattern(tad_function f, int64_t* n_outer, int64_t* nnz)
 int tad_function_pattern_copy(tad_function f, int32_t* outer_host, int32_t* inner_host)
 {
     if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
-    std::lock_guard<std::mutex> lock(f->mtx);
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     TAD_TRY(ensure_pattern(f));
     if (outer_host) TAD_CUDA(cudaMemcpy(outer_host, f->outer.p, ((size_t)f->n_outer + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -1474,7 +1696,7 @@ int tad_function_pattern_copy(tad_function f, int32_t* outer_host, int32_t* inne
 int tad_function_pattern_device(tad_function f, const int32_t** outer_dev, const int32_t** inner_dev)
 {
     if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
-    std::lock_guard<std::mutex> lock(f->mtx);
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     TAD_TRY(ensure_pattern(f));
     if (outer_dev) *outer_dev = f->outer.p;
@@ -1575,10 +1797,30 @@ int tad_veval_sum_of_squares_with_derivatives(tad_function f, const double* x_de
     return eval_vector(f, 3, x_dev, f_host, g_dev, r_dev, J_values_dev);
 }
 
-int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int64_t* counts_dev, void* stream)
+int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int method, int64_t* counts_dev, void* stream)
 {
     if (k < 1 || n < 0 || stride < n || !hess_dev) return fail(TAD_INVALID_ARGUMENT, "bad projection arguments");
-    TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts_dev, static_cast<cudaStream_t>(stream)));
+    // counts_dev: optional device int64[4] {decomposed, rebuilt, fallback, -}, zeroed by the caller
+    DevBuf<unsigned long long> local_counts;
+    DevBuf<int64_t> list;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long* counts = reinterpret_cast<unsigned long long*>(counts_dev);
+    if (!counts)
+    {
+        TAD_CUDA(local_counts.ensure(4));
+        TAD_CUDA(cudaMemsetAsync(local_counts.p, 0, 4 * sizeof(unsigned long long), st));
+        counts = local_counts.p;
+    }
+    DevBuf<double> scratch;
+    DevBuf<int32_t> codes;
+    TAD_CUDA(list.ensure((size_t)std::max<int64_t>(stride, 1)));
+    TAD_CUDA(codes.ensure((size_t)std::max<int64_t>(stride, 1)));
+    if (method != 1) TAD_CUDA(scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(k, stride))));
+    TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts, scratch.p, codes.p, list.p, method == 1, st));
+    unsigned long long h_counts[3] = {0, 0, 0};
+    TAD_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+    TAD_CUDA(cudaStreamSynchronize(st));  // the scratch buffers above are locals
+    (void)h_counts;
     return TAD_OK;
 }
 
@@ -1620,6 +1862,7 @@ int tad_function_projection_stats(tad_function f, int64_t* stats2)
     if (!f || !stats2) return fail(TAD_INVALID_ARGUMENT, "null argument");
     stats2[0] = f->last_proj[0];
     stats2[1] = f->last_proj[1];
+    stats2[2] = f->last_proj[2];
     return TAD_OK;
 }
 

@@ -1,0 +1,577 @@
+// tinyad_b200 -- per-element projection of a packed symmetric K x K Hessian to a positive-definite
+// matrix: project_positive_definite of the reference (Utils/HessianProjection.hh:23-101), i.e.
+//     H  ->  V max(L, eps) V^T        (eps >= 0)        or        V |L| V^T        (eps < 0)
+// with both early-outs (diagonally dominant; nothing clamped) leaving H bit-unchanged.
+//
+// The reference calls Eigen::SelfAdjointEigenSolver (full eigendecomposition) and rebuilds
+// V D V^T.  On the GPU the K x K eigenvector matrix is what hurts: it does not fit in registers
+// (K = 12: 288 registers) and the QL/QR rotations index its columns at run time, so it has to
+// live in shared memory, where rotating it costs ~25 KB of traffic per element.  This
+// implementation never forms it:
+//   1. Householder tridiagonalisation A = Q T Q^T with the packed matrix in REGISTERS (fully
+//      unrolled, compile-time indices); the reflectors stay in the registers A occupied;
+//   2. eigenvalues of T by implicit QL without vectors (EISPACK tql1 scheme) -- O(K^2);
+//   3. the projected matrix differs from H by a low-rank term,
+//          H + sum_{l_j < eps} (eps - l_j) v_j v_j^T       (or the complementary sum if that is shorter),
+//      so only the eigenvectors of the clamped (or the kept) eigenvalues are needed: inverse
+//      iteration on T with re-orthogonalisation inside clusters (the LAPACK dstein scheme),
+//      back-transformed through the reflectors -- O(K^2) per vector.
+// Any backward-stable eigensolver gives the same projected matrix to O(eps_machine |H|), which is
+// what the parity tests check (tolerance 1e-10 relative, BASELINE.json north_star).
+// The function is __host__ __device__ so that the host unit test exercises exactly the device code.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#include <TinyAD/Scalar.hh>
+
+namespace TinyAD
+{
+namespace detail
+{
+
+enum ProjectCode
+{
+    PROJ_DOMINANT = 0,   // early-out 1, H untouched
+    PROJ_UNCHANGED = 1,  // decomposed, nothing clamped, H untouched
+    PROJ_REBUILT = 2,
+    PROJ_FALLBACK = 3    // inverse iteration did not converge: caller must use the full eigensolver (H untouched)
+};
+
+// Scratch layout between the three phases (structure-of-arrays over elements in the kernels):
+//   R[0..K)            d_i = T(i,i)
+//   R[K..2K-1)         e_i = T(i+1,i)
+//   R[2K-1..3K-3)      tau_k of reflector H_k = I - tau_k v_k v_k^T, k < K-2
+//   R[3K-3..)          v_k(2:) for k = 0..K-3, concatenated (v_k(1) = 1 is implicit); last slot: max |H_ij|
+//   W[0] = number of vectors, W[1] = form (0: H + sum, 1: eps I + sum, 2: -H + sum), W[2..2+MAXV) weights,
+//   W[2+MAXV + jv*K + i] = component i of eigenvector jv of T
+template <int K>
+struct ProjLayout
+{
+    static constexpr int H = K * (K + 1) / 2;
+    static constexpr int MAXV = K / 2 + 1;
+    static constexpr int n_refl = K > 2 ? K - 2 : 0;
+    static constexpr int off_d = 0, off_e = K, off_tau = 2 * K - 1, off_v = off_tau + n_refl;
+    static constexpr int n_v = n_refl * (n_refl + 1) / 2;  // sum_{k} (K-k-2)
+    static constexpr int off_amax = off_v + n_v;  // max |H_ij| of the element (scale of the accuracy target)
+    static constexpr int nR = off_amax + 1;
+    static constexpr int off_wgt = 2, off_vec = 2 + MAXV;
+    static constexpr int nW = off_vec + MAXV * K;
+    // offset of v_k(2 + i), i < K-k-2
+    TINYAD_HD static constexpr int v_index(int k, int i)
+    {
+        int o = off_v;
+        for (int q = 0; q < k; ++q) o += K - q - 2;
+        return o + i;
+    }
+};
+
+// Phase A: early-out 1 and Householder tridiagonalisation; the packed matrix lives in registers.
+// Returns PROJ_DOMINANT (nothing stored) or PROJ_UNCHANGED (R stored, continue with phase B).
+template <int K, class LoadFn, class StoreRFn>
+TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, const double eps)
+{
+    using L = ProjLayout<K>;
+    constexpr int H = L::H;
+    double a[H];
+    double amax = 0.0;
+    static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+        constexpr int s = decltype(sc)::value;
+        a[s] = load(s);
+        amax = fmax(amax, fabs(a[s]));
+    });
+#define TAD_A(i, j) a[hess_seq_index(K, (i), (j))]
+
+    // ---- early-out 1: positive diagonally dominant (HessianProjection.hh:23-42, :62-63) ----
+    {
+        double offsum[K];
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { offsum[decltype(ic)::value] = 0.0; });
+        static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+            constexpr int s = decltype(sc)::value;
+            constexpr int r = hess_seq_rc(K, s).row, c = hess_seq_rc(K, s).col;
+            if constexpr (r != c)
+            {
+                const double v = fabs(a[s]);
+                offsum[r] += v;
+                offsum[c] += v;
+            }
+        });
+        bool dominant = true;
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            if (TAD_A(i, i) < offsum[i] + eps) dominant = false;
+        });
+        if (dominant) return PROJ_DOMINANT;
+    }
+
+    double d0[K], e0[K];  // tridiagonal T: d0[i] = T(i,i), e0[i] = T(i+1,i); e0[K-1] = 0
+    double tau[K > 2 ? K - 2 : 1];
+
+    if constexpr (K == 1)
+    {
+        d0[0] = a[0];
+        e0[0] = 0.0;
+    }
+    else
+    {
+        // ---- 1. Householder tridiagonalisation of the lower triangle, column by column ----
+        // After step k: column k of A holds (d_k, e_k, v_k(2:)) with reflector H_k = I - tau_k v_k v_k^T, v_k(1) = 1.
+        static_for<(K > 2 ? K - 2 : 0)>([&](auto kc) TINYAD_LAMBDA_INLINE {
+            constexpr int k = decltype(kc)::value;
+            constexpr int n = K - k - 1;  // order of the trailing block, rows/cols k+1 .. K-1
+            const double alpha = TAD_A(k + 1, k);
+            double xnorm2 = 0.0;
+            static_for<n - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                constexpr int i = decltype(ic)::value;
+                xnorm2 = fma(TAD_A(k + 2 + i, k), TAD_A(k + 2 + i, k), xnorm2);
+            });
+            double t = 0.0;
+            if (xnorm2 > 0.0)
+            {
+                const double nrm = sqrt(fma(alpha, alpha, xnorm2));
+                const double beta = alpha >= 0.0 ? -nrm : nrm;
+                t = (beta - alpha) / beta;
+                const double sc = 1.0 / (alpha - beta);
+                static_for<n - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value;
+                    TAD_A(k + 2 + i, k) *= sc;
+                });
+                TAD_A(k + 1, k) = beta;
+                // p = tau * A22 v,  v = (1, A(k+2.., k))
+                double p[n];
+                static_for<n>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value;
+                    double s = TAD_A(k + 1 + i, k + 1);  // v_0 = 1
+                    static_for<n - 1>([&](auto jc) TINYAD_LAMBDA_INLINE {
+                        constexpr int j = decltype(jc)::value + 1;
+                        s = fma(TAD_A(k + 1 + i, k + 1 + j), TAD_A(k + 1 + j, k), s);
+                    });
+                    p[i] = t * s;
+                });
+                // w = p - (tau/2) (p^T v) v
+                double pv = p[0];
+                static_for<n - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value + 1;
+                    pv = fma(p[i], TAD_A(k + 1 + i, k), pv);
+                });
+                const double hk = -0.5 * t * pv;
+                p[0] += hk;
+                static_for<n - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value + 1;
+                    p[i] = fma(hk, TAD_A(k + 1 + i, k), p[i]);
+                });
+                // A22 -= v w^T + w v^T (lower triangle)
+                static_for<n>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value;
+                    static_for<i + 1>([&](auto jc) TINYAD_LAMBDA_INLINE {
+                        constexpr int j = decltype(jc)::value;
+                        double vi = 1.0, vj = 1.0;
+                        if constexpr (i > 0) vi = TAD_A(k + 1 + i, k);
+                        if constexpr (j > 0) vj = TAD_A(k + 1 + j, k);
+                        TAD_A(k + 1 + i, k + 1 + j) -= vi * p[j] + p[i] * vj;
+                    });
+                });
+            }
+            tau[k] = t;
+        });
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            d0[i] = TAD_A(i, i);
+            if constexpr (i + 1 < K) e0[i] = TAD_A(i + 1, i);
+            else e0[i] = 0.0;
+        });
+    }
+
+    store_r(L::off_amax, amax);
+    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+        constexpr int i = decltype(ic)::value;
+        store_r(L::off_d + i, d0[i]);
+        if constexpr (i + 1 < K) store_r(L::off_e + i, e0[i]);
+    });
+    static_for<L::n_refl>([&](auto kc) TINYAD_LAMBDA_INLINE {
+        constexpr int k = decltype(kc)::value;
+        store_r(L::off_tau + k, tau[k]);
+        static_for<K - k - 2>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            store_r(L::v_index(k, i), TAD_A(k + 2 + i, k));
+        });
+    });
+#undef TAD_A
+    return PROJ_UNCHANGED;
+}
+
+// Phase B: eigenvalues of T, selection of the eigenvalues that move, their eigenvectors (of T) by inverse iteration.
+// Scalar recurrences on small arrays, written as plain loops: nvcc unrolls the fixed-trip-count ones (LU, solves)
+// so those arrays live in registers, while the QL loops with data-dependent bounds index local memory.  Measured on
+// B200 (1M tets): this form 2.7 ms; everything unrolled by hand 16 ms (14k SASS instructions, instruction-cache
+// bound); nothing unrolled (`#pragma unroll 1`) 8 ms.  load_w re-reads vectors already stored through store_w.
+template <int K, class LoadRFn, class StoreWFn, class LoadWFn>
+TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, LoadWFn&& load_w, const double eps)
+{
+    using L = ProjLayout<K>;
+    constexpr double macheps = 2.220446049250313e-16;
+    double d0[K], e0[K];
+    for (int i = 0; i < K; ++i)
+    {
+        d0[i] = load_r(L::off_d + i);
+        e0[i] = (i + 1 < K) ? load_r(L::off_e + i) : 0.0;
+    }
+
+    // ---- 2. eigenvalues of T: implicit QL without vectors (EISPACK tql1 scheme) ----
+    double lam[K];
+    double onenrm = 0.0;
+    {
+        double ee[K];
+        for (int i = 0; i < K; ++i)
+        {
+            lam[i] = d0[i];
+            ee[i] = e0[i];
+            const double rowsum = fabs(d0[i]) + fabs(e0[i]) + (i > 0 ? fabs(e0[i - 1]) : 0.0);
+            onenrm = fmax(onenrm, rowsum);
+        }
+        double f = 0.0, tst1 = 0.0;
+        for (int l = 0; l < K; ++l)
+        {
+            tst1 = fmax(tst1, fabs(lam[l]) + fabs(ee[l]));
+            int m = l;
+            while (m < K - 1)
+            {
+                if (fabs(ee[m]) <= macheps * tst1) break;
+                ++m;
+            }
+            if (m > l)
+            {
+                int iter = 0;
+                double el_abs;
+                do
+                {
+                    ++iter;
+                    const double e_l = ee[l];
+                    double g = lam[l];
+                    double p = (lam[l + 1] - g) / (2.0 * e_l);
+                    double r = (fabs(p) < 1e150) ? sqrt(fma(p, p, 1.0)) : fabs(p);
+                    if (p < 0) r = -r;
+                    const double dl = e_l / (p + r);
+                    const double dl1 = e_l * (p + r);
+                    lam[l] = dl;
+                    lam[l + 1] = dl1;
+                    double h = g - dl;
+                    for (int i = l + 2; i < K; ++i) lam[i] -= h;
+                    f += h;
+                    p = lam[m];
+                    double c = 1.0, c2 = 1.0, c3 = 1.0;
+                    const double el1 = ee[l + 1];
+                    double s = 0.0, s2 = 0.0;
+                    for (int i = m - 1; i >= l; --i)
+                    {
+                        c3 = c2;
+                        c2 = c;
+                        s2 = s;
+                        const double ei = ee[i], di = lam[i];
+                        g = c * ei;
+                        h = c * p;
+                        const double t = fma(p, p, ei * ei);
+                        double rinv;
+                        if (t > 1e-280 && t < 1e280)
+                        {
+#if defined(__CUDA_ARCH__)
+                            rinv = rsqrt(t);
+#else
+                            rinv = 1.0 / sqrt(t);
+#endif
+                            r = t * rinv;
+                        }
+                        else
+                        {
+                            r = hypot(p, ei);
+                            rinv = 1.0 / r;
+                        }
+                        ee[i + 1] = s * r;
+                        s = ei * rinv;
+                        c = p * rinv;
+                        p = c * di - s * g;
+                        lam[i + 1] = h + s * (c * g + s * di);
+                    }
+                    p = -s * s2 * c3 * el1 * e_l / dl1;
+                    ee[l] = s * p;
+                    lam[l] = c * p;
+                    el_abs = fabs(s * p);
+                } while (el_abs > macheps * tst1 && iter < 60);
+                if (iter >= 60) return PROJ_FALLBACK;
+            }
+            lam[l] = lam[l] + f;
+            ee[l] = 0.0;
+        }
+    }
+    // ascending order (insertion sort, K is tiny)
+    for (int i = 1; i < K; ++i)
+    {
+        const double v = lam[i];
+        int j = i - 1;
+        while (j >= 0 && lam[j] > v)
+        {
+            lam[j + 1] = lam[j];
+            --j;
+        }
+        lam[j + 1] = v;
+    }
+    if (!(onenrm == onenrm) || onenrm > 1e300) return PROJ_FALLBACK;  // NaN / Inf input: the caller's finite check reports it
+
+    // ---- 3. which eigenvalues move (HessianProjection.hh:71-91) ----
+    const bool abs_mode = eps < 0.0;
+    const double thresh = abs_mode ? 0.0 : eps;
+    int r = 0;
+    while (r < K && lam[r] < thresh) ++r;
+    if (r == 0) return PROJ_UNCHANGED;  // early-out 2 (:94-95)
+    // form A: H + sum_{j<r} delta_j v_j v_j^T with delta_j = target_j - l_j           (r <= K/2)
+    // form B: base + sum_{j>=r} gamma_j v_j v_j^T, base = eps I (clamp) or -H (abs)     (otherwise: fewer vectors)
+    const bool form_b = 2 * r > K;
+    const int j_begin = form_b ? r : 0, j_end = form_b ? K : r;
+
+    // ---- 4. inverse iteration on T (LAPACK dstein scheme: dlagtf / dlagts, re-orthogonalisation in clusters) ----
+    const double ortol = 1e-3 * onenrm;
+    const double res_limit = 2e-12 * load_r(L::off_amax);
+    double xjm = 0.0;
+    int gpind = j_begin;
+    uint32_t seed = 0x9e3779b9u;
+    for (int j = j_begin; j < j_end; ++j)
+    {
+        const int jv = j - j_begin;
+        const double lj = lam[j];
+        double xj = lj;
+        if (j > j_begin)
+        {
+            const double pertol = 10.0 * fabs(macheps * xj);
+            if (xj - xjm < pertol) xj = xjm + pertol;
+        }
+        // LU factorisation of T - xj I with partial pivoting (dlagtf); the pivot tests |a_k|/scale1 >= |c_k|/scale2
+        // are cross-multiplied, and the pivots are inverted once (with the dlagts perturbation) for all solves.
+        double la[K], lb[K], lc[K], ld[K];
+        uint32_t pivmask = 0;
+        for (int i = 0; i < K; ++i)
+        {
+            la[i] = d0[i] - xj;
+            lb[i] = e0[i];
+            lc[i] = e0[i];
+            ld[i] = 0.0;
+        }
+        double tol = 0.0;
+        {
+            double scale1 = fabs(la[0]) + (K > 1 ? fabs(lb[0]) : 0.0);
+            for (int k = 0; k < K - 1; ++k)
+            {
+                double scale2 = fabs(lc[k]) + fabs(la[k + 1]);
+                if (k < K - 2) scale2 += fabs(lb[k + 1]);
+                if (lc[k] == 0.0) scale1 = scale2;
+                else if (la[k] != 0.0 && fabs(lc[k]) * scale1 <= fabs(la[k]) * scale2)
+                {
+                    scale1 = scale2;
+                    lc[k] = lc[k] / la[k];
+                    la[k + 1] -= lc[k] * lb[k];
+                }
+                else
+                {
+                    pivmask |= (1u << k);
+                    const double mult = la[k] / lc[k];
+                    la[k] = lc[k];
+                    const double temp = la[k + 1];
+                    la[k + 1] = lb[k] - mult * temp;
+                    if (k < K - 2)
+                    {
+                        ld[k] = lb[k + 1];
+                        lb[k + 1] = -mult * ld[k];
+                    }
+                    lb[k] = temp;
+                    lc[k] = mult;
+                }
+            }
+            for (int i = 0; i < K; ++i) tol = fmax(tol, fmax(fabs(la[i]), fmax(fabs(lb[i]), fabs(ld[i]))));
+            tol = (tol == 0.0) ? macheps : tol * macheps;
+        }
+        const double a_last = fabs(la[K - 1]);
+        for (int i = 0; i < K; ++i)
+        {
+            double ak = la[i];
+            if (fabs(ak) < tol) ak = (ak < 0.0) ? -tol : tol;
+            la[i] = 1.0 / ak;
+        }
+
+        double x[K];
+        for (int i = 0; i < K; ++i)
+        {
+            seed = seed * 1664525u + 1013904223u;
+            x[i] = ((double)(seed >> 8) * (1.0 / 8388608.0)) - 1.0;  // deterministic start vector in (-1, 1)
+        }
+        if (j > j_begin && fabs(xj - xjm) > ortol) gpind = j;
+        // With the eigenvalue known to working precision one solve from a random start already gives a residual of a
+        // few eps |T| (more solves do not improve it; for the later members of a cluster they make it worse, because
+        // the re-orthogonalised iterate is fed back into a solve that amplifies the removed directions again).  So,
+        // instead of dstein's growth test plus two extra iterations: solve, re-orthogonalise inside the cluster, and
+        // accept as soon as the residual |(T - l_j) y|_inf of the normalised vector is below res_limit (at most 5 solves,
+        // then the element goes to the full eigensolver).  Because l -> max(l, eps) and l -> |l| are 1-Lipschitz, an
+        // eigenvector error only enters the projected matrix through this residual (the weight ratio
+        // |w_j - w_k| / |l_j - l_k| is <= 2 for every pair), so res_limit = 2e-12 max|H_ij| keeps the projected
+        // matrix within ~1e-11 max|H_ij| of the exact one -- an order below the 1e-10 parity tolerance.  (The last member of an
+        // exactly degenerate cluster typically stalls at ~1e-13 |T|_1; T is not split into blocks here as dstein does.)
+        int its = 0;
+        bool converged = false;
+        double inv = 0.0;
+        while (its < 5)
+        {
+            ++its;
+            // orthogonalise the right-hand side against the earlier vectors of the cluster before the solve: otherwise
+            // the solve amplifies those directions as much as the wanted one and the remainder after removing them
+            // is noisy (residual ~100 eps |T| for the third vector of a triple eigenvalue) ...
+            for (int i = gpind; i < j; ++i)
+            {
+                const int base = L::off_vec + (i - j_begin) * K;
+                double dot = 0.0;
+                for (int q = 0; q < K; ++q) dot = fma(x[q], load_w(base + q), dot);
+                for (int q = 0; q < K; ++q) x[q] = fma(-dot, load_w(base + q), x[q]);
+            }
+            double xabs = 0.0;
+            for (int i = 0; i < K; ++i) xabs += fabs(x[i]);
+            const double scl = (double)K * onenrm * fmax(macheps, fmax(a_last, tol)) / fmax(xabs, 1e-300);
+            // solve (dlagts): forward with L and the interchanges (scaling folded in), back substitution
+            x[0] *= scl;
+            for (int k = 1; k < K; ++k)
+            {
+                const double t1 = x[k] * scl;
+                if (!((pivmask >> (k - 1)) & 1u)) x[k] = t1 - lc[k - 1] * x[k - 1];
+                else
+                {
+                    const double t0 = x[k - 1];
+                    x[k - 1] = t1;
+                    x[k] = t0 - lc[k - 1] * t1;
+                }
+            }
+            for (int k = K - 1; k >= 0; --k)
+            {
+                double temp = x[k];
+                if (k <= K - 2) temp -= lb[k] * x[k + 1];
+                if (k <= K - 3) temp -= ld[k] * x[k + 2];
+                x[k] = temp * la[k];
+            }
+            // ... and once more after it (modified Gram-Schmidt)
+            for (int i = gpind; i < j; ++i)
+            {
+                const int base = L::off_vec + (i - j_begin) * K;
+                double dot = 0.0;
+                for (int q = 0; q < K; ++q) dot = fma(x[q], load_w(base + q), dot);
+                for (int q = 0; q < K; ++q) x[q] = fma(-dot, load_w(base + q), x[q]);
+            }
+            double n2 = 0.0;
+            for (int i = 0; i < K; ++i) n2 = fma(x[i], x[i], n2);
+            if (!(n2 > 0.0) || !(n2 < 1e300)) break;  // NaN, zero or overflow
+            inv = 1.0 / sqrt(n2);
+            double res = 0.0;
+            for (int i = 0; i < K; ++i)
+            {
+                double t = (d0[i] - lj) * x[i];
+                if (i > 0) t = fma(e0[i - 1], x[i - 1], t);
+                if (i + 1 < K) t = fma(e0[i], x[i + 1], t);
+                res = fmax(res, fabs(t));
+            }
+#if defined(TAD_PROJ_DEBUG) && !defined(__CUDA_ARCH__)
+            printf("  j=%d lj=%.3e xj=%.3e its=%d res=%.3e (limit %.3e) gpind=%d a_last=%.3e tol=%.3e\n", j, lj, xj, its, res * inv, res_limit, gpind, a_last, tol);
+#endif
+            if (res * inv <= res_limit)
+            {
+                converged = true;
+                break;
+            }
+        }
+        if (!converged) return PROJ_FALLBACK;
+        for (int i = 0; i < K; ++i) store_w(L::off_vec + jv * K + i, x[i] * inv);
+        // weight of v v^T in the low-rank term
+        double wj;
+        if (!form_b) wj = abs_mode ? -2.0 * lj : eps - lj;
+        else wj = abs_mode ? 2.0 * lj : lj - eps;
+        store_w(L::off_wgt + jv, wj);
+        xjm = xj;
+    }
+    store_w(0, (double)(j_end - j_begin));
+    store_w(1, !form_b ? 0.0 : (abs_mode ? 2.0 : 1.0));
+    return PROJ_REBUILT;
+}
+
+// Phase C: back-transform the selected eigenvectors through the reflectors and add the low-rank term to H.
+template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn>
+TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps)
+{
+    using L = ProjLayout<K>;
+    constexpr int H = L::H;
+    const int nv = (int)load_w(0);
+    const int form = (int)load_w(1);
+    double W[L::MAXV][K];
+    {
+        // reflectors in registers; each vector goes v = H_0 H_1 ... H_{K-3} y
+        double refl[L::n_v > 0 ? L::n_v : 1], tau[L::n_refl > 0 ? L::n_refl : 1];
+        static_for<L::n_v>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; refl[i] = load_r(L::off_v + i); });
+        static_for<L::n_refl>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tau[i] = load_r(L::off_tau + i); });
+        for (int jv = 0; jv < nv; ++jv)
+        {
+            double y[K];
+            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = load_w(L::off_vec + jv * K + i); });
+            static_for<L::n_refl>([&](auto kc) TINYAD_LAMBDA_INLINE {
+                constexpr int k = K - 3 - decltype(kc)::value;
+                constexpr int n = K - k - 1;
+                constexpr int vo = L::v_index(k, 0) - L::off_v;
+                double s = y[k + 1];
+                static_for<n - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value;
+                    s = fma(refl[vo + i], y[k + 2 + i], s);
+                });
+                s *= tau[k];
+                y[k + 1] -= s;
+                static_for<n - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value;
+                    y[k + 2 + i] = fma(-s, refl[vo + i], y[k + 2 + i]);
+                });
+            });
+            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; W[jv][i] = y[i]; });
+        }
+    }
+    double acc[H];
+    static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+        constexpr int s = decltype(sc)::value;
+        constexpr int r_ = hess_seq_rc(K, s).row, c_ = hess_seq_rc(K, s).col;
+        if (form == 0) acc[s] = load(s);
+        else if (form == 2) acc[s] = -load(s);
+        else acc[s] = (r_ == c_) ? eps : 0.0;
+    });
+    for (int jv = 0; jv < nv; ++jv)
+    {
+        const double wj = load_w(L::off_wgt + jv);
+        double v[K], wv[K];
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            v[i] = W[jv][i];
+            wv[i] = wj * v[i];
+        });
+        static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+            constexpr int s = decltype(sc)::value;
+            acc[s] = fma(wv[hess_seq_rc(K, s).row], v[hess_seq_rc(K, s).col], acc[s]);
+        });
+    }
+    static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE { constexpr int s = decltype(sc)::value; store(s, acc[s]); });
+}
+
+// All three phases on one element through local scratch (host tests; the kernels run the phases separately).
+template <int K, class LoadFn, class StoreFn>
+TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const double eps)
+{
+    using L = ProjLayout<K>;
+    double R[L::nR > 0 ? L::nR : 1], Wb[L::nW];
+    int code = proj_tridiagonalize<K>(load, [&](int i, double v) { R[i] = v; }, eps);
+    if (code == PROJ_DOMINANT) return code;
+    code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i, double v) { Wb[i] = v; }, [&](int i) { return Wb[i]; }, eps);
+    if (code != PROJ_REBUILT) return code;
+    proj_apply<K>([&](int i) { return R[i]; }, [&](int i) { return Wb[i]; }, load, store, eps);
+    return PROJ_REBUILT;
+}
+
+
+}  // namespace detail
+}  // namespace TinyAD
