@@ -97,6 +97,10 @@ int tad_function_get_stream(tad_function f, void** stream);
 int tad_function_add_term(tad_function f, int valence, int outputs_per_element, int64_t n_elements,
                           const int64_t* elem_handles_host, tad_launch_fn launch, void* user, void (*user_free)(void*));
 
+/* Multi-GPU: inject structural-only d x d blocks (handle pairs vi, vj) into the Hessian pattern, e.g. the halo-row
+ * blocks other ranks will send to this rank.  They get explicit zero slots; the pattern is rebuilt on next use. */
+int tad_function_add_pattern_blocks(tad_function f, int64_t n_blocks, const int64_t* vi_host, const int64_t* vj_host);
+
 int64_t tad_function_n_vars(tad_function f);
 int64_t tad_function_n_elements(tad_function f);
 int64_t tad_function_n_outputs(tad_function f); /* vector functions: number of residuals */

@@ -31,7 +31,7 @@ SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
 # every symbol include/tinyad_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "tad_last_error", "tad_device_count", "tad_function_create", "tad_function_destroy", "tad_function_set_option",
-    "tad_function_get_stream", "tad_function_add_term", "tad_function_n_vars", "tad_function_n_elements",
+    "tad_function_get_stream", "tad_function_add_term", "tad_function_add_pattern_blocks", "tad_function_n_vars", "tad_function_n_elements",
     "tad_function_n_outputs", "tad_function_pattern", "tad_function_pattern_copy", "tad_function_pattern_device",
     "tad_function_term_table", "tad_eval", "tad_eval_with_gradient", "tad_eval_with_derivatives", "tad_eval_host",
     "tad_eval_with_gradient_host", "tad_eval_with_derivatives_host", "tad_veval", "tad_veval_with_jacobian",
@@ -69,6 +69,7 @@ def runtime():
             fn.restype = i64
             fn.argtypes = [vp]
         L.tad_function_pattern.argtypes = [vp, vp, vp]
+        L.tad_function_add_pattern_blocks.argtypes = [vp, i64, vp, vp]
         L.tad_function_pattern_copy.argtypes = [vp, vp, vp]
         L.tad_function_pattern_device.argtypes = [vp, vp, vp]
         L.tad_function_term_table.argtypes = [vp, ctypes.c_int, vp]
@@ -167,6 +168,13 @@ class Function:
             raise TinyADError(-1, E.tadx_last_error().decode())
         self._pattern = None
         return self
+
+    def add_pattern_blocks(self, vi, vj):
+        """Structural-only d x d blocks (vertex pairs) for halo rows received from other ranks."""
+        vi = np.ascontiguousarray(vi, dtype=np.int64)
+        vj = np.ascontiguousarray(vj, dtype=np.int64)
+        _check(runtime().tad_function_add_pattern_blocks(self.h, len(vi), vi.ctypes.data, vj.ctypes.data))
+        self._pattern = None
 
     def set_option(self, opt, value):
         _check(runtime().tad_function_set_option(self.h, opt, value))

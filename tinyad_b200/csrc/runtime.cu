@@ -144,6 +144,7 @@ struct tad_function_s
     DevBuf<int64_t> block_key;     // [n_blocks]
     DevBuf<int64_t> vrow;          // [n_handles+1] first block of each vertex row
     DevBuf<TermDev> terms_dev;
+    std::vector<int64_t> extra_keys;  // vertex pairs injected by tad_function_add_pattern_blocks (halo rows of other ranks)
     // scratch
     DevBuf<double> stage;          // shared staging (atomic mode)
     DevBuf<double> x_dev, g_dev, H_dev, r_dev;
@@ -752,6 +753,7 @@ __global__ void fill_maps(const int32_t* contrib, const int32_t* pid_incl, int64
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_valid) return;
     const int64_t c = contrib[i];
+    if (c < 0) return;  // structural-only block
     const int64_t p = pid_incl[i] - 1;
     int t = 0;
     while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
@@ -925,6 +927,7 @@ __global__ void __launch_bounds__(128) gather_hessian(const int64_t* __restrict_
     for (int64_t i = block_ptr[p]; i < block_ptr[p + 1]; ++i)
     {
         const int64_t c = contrib[i];
+        if (c < 0) continue;  // structural-only block
         int t = 0;
         while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
         const TermDev& T = terms[t];
@@ -964,6 +967,7 @@ __global__ void __launch_bounds__(128) gather_gradient(const int64_t* __restrict
         for (int64_t i = block_ptr[lo]; i < block_ptr[lo + 1]; ++i)
         {
             const int64_t c = contrib[i];
+            if (c < 0) continue;  // structural-only block
             int t = 0;
             while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
             const TermDev& T = terms[t];
@@ -1178,6 +1182,8 @@ int build_pattern_scalar(tad_function f)
         t.contrib_offset = nC;
         nC += (int64_t)t.N * t.N * t.n;
     }
+    const int64_t n_term_contrib = nC;
+    nC += (int64_t)f->extra_keys.size();
     if (nC >= (int64_t)INT32_MAX) return fail(TAD_NOT_SUPPORTED, "more than 2^31 block contributions");
     f->n_contrib = nC;
     for (auto& t : f->terms)
@@ -1202,6 +1208,13 @@ int build_pattern_scalar(tad_function f)
     {
         const int64_t cnt = (int64_t)td[i].N * td[i].N * td[i].n;
         if (cnt) gen_block_keys<<<blocks_for(cnt, 256), 256, 0, st>>>(td[i], f->n_handles, keys_a.p, pay_a.p);
+    }
+    if (!f->extra_keys.empty())
+    {
+        // structural-only blocks (no local contribution): payload -1
+        const size_t ne = f->extra_keys.size();
+        TAD_CUDA(cudaMemcpyAsync(keys_a.p + n_term_contrib, f->extra_keys.data(), ne * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        fill_i32<<<blocks_for((int64_t)ne, 256), 256, 0, st>>>(pay_a.p + n_term_contrib, (int64_t)ne, -1);
     }
     int64_t n_valid = 0, n_blocks = 0;
     if (nC > 0)
@@ -1663,6 +1676,21 @@ int tad_function_add_term(tad_function f, int valence, int outputs_per_element, 
     f->n_elements += n_elements;
     f->n_outputs += (int64_t)outputs_per_element * n_elements;
     f->terms.push_back(std::move(t));
+    f->pattern_built = false;
+    return TAD_OK;
+}
+
+int tad_function_add_pattern_blocks(tad_function f, int64_t n_blocks, const int64_t* vi_host, const int64_t* vj_host)
+{
+    if (!f || n_blocks < 0 || (n_blocks > 0 && (!vi_host || !vj_host))) return fail(TAD_INVALID_ARGUMENT, "bad pattern blocks");
+    if (f->is_vector) return fail(TAD_INVALID_ARGUMENT, "pattern blocks apply to scalar functions");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
+    for (int64_t i = 0; i < n_blocks; ++i)
+    {
+        if (vi_host[i] < 0 || vi_host[i] >= f->n_handles || vj_host[i] < 0 || vj_host[i] >= f->n_handles)
+            return fail(TAD_INDEX_OUT_OF_RANGE, "pattern block handle out of range");
+        f->extra_keys.push_back(vi_host[i] * f->n_handles + vj_host[i]);
+    }
     f->pattern_built = false;
     return TAD_OK;
 }
