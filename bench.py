@@ -201,7 +201,15 @@ def main():
     t0 = time.perf_counter()
     fn = tad.Function(d, len(V), device=local_rank, assembly=assembly)
     fn.add_term(kind, conn, data)
+    plan = None
+    if world > 1:
+        # vertex ownership + halo rows: the owner's pattern gets slots for the blocks its neighbours send
+        from tinyad_b200.dist import HaloPlan
+        plan = HaloPlan(d, len(V), [conn])
+        fn.add_pattern_blocks(*plan.extra_pattern_blocks())
     nnz = fn.nnz                       # builds the pattern + scatter maps
+    if plan is not None:
+        plan.finalize(*fn.pattern(), device="cuda")
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
 
@@ -215,9 +223,11 @@ def main():
 
     def step():
         f = fn.eval_with_hessian_proj(x_dev, g_dev, H_dev)
-        if world > 1:                   # the only data-path collective of the sharded run: f (g / halo rows: see DESIGN.md)
+        if world > 1:                   # exchange step: halo-row H values to the owners, g and f all-reduced (NCCL)
+            plan.exchange(H_dev, g_dev)
             fsum[0] = f
             dist.all_reduce(fsum)
+            torch.cuda.current_stream().synchronize()   # H_dev / g_dev are reused by the next step
         return f
 
     def barrier():
@@ -225,15 +235,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                   # clocks are sampled under load from the warm-up on (the timed region itself is ~0.1 s)
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream_ptr = tad.ctypes.c_void_p()
     tad.runtime().tad_function_get_stream(fn.h, tad.ctypes.byref(stream_ptr))
-    ext = torch.cuda.ExternalStream(stream_ptr.value)
+    ext = torch.cuda.ExternalStream(stream_ptr.value) if world == 1 else torch.cuda.current_stream()
     t0 = time.perf_counter()
     ev0.record(ext)
     for _ in range(args.steps):
@@ -310,12 +320,15 @@ def main():
             "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong" if args.workload == "c5" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "elements_total": int(n_total), "elements_per_gpu": n_el, "nnz_per_gpu": int(nnz),
-                       "eps": 1e-9, "assembly": args.assembly, "partition": "z-slabs, one per rank" if world > 1 else "none",
+                       "eps": 1e-9, "assembly": args.assembly,
+                       "partition": "z-slabs, one per rank; vertex owner = lowest rank; halo-row H values sent to the owner, g/f all-reduced"
+                       if world > 1 else "none", "halo_bytes_rank0": (plan.halo_bytes if plan else 0),
                        "l2": "no flush: per-step working set (staging + CSR values) exceeds the 126 MB L2" if n_el > 200000 else "small workload, L2-resident",
                        "setup_s_pattern_and_maps": setup_s},
             "e2e": {"value": n_total / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(8 * fn.n_vars), "d2h_bytes_per_step": int(8 * (fn.n_vars + nnz + 1)),
                     "ms_per_step": e2e_t * 1e3},
-            "gpu_launches": 5 * args.steps,
+            # per step: 4 element kernels (one per Hessian part), 2 reduction, 4 projection (A, B, C, fallback list), 1 assembly
+            "gpu_launches": (11 if d == 3 else 8) * args.steps,
             "clocks": clocks, "roofline": roof, "wall_s_timed_region": wall, "f": f,
         }
         if not args.no_cpu_baseline and world == 1:
