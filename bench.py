@@ -68,7 +68,8 @@ def workload_mesh(name, rank, world):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  Started early (nvidia-smi needs a while
+    to come up); stop(t0, t1) keeps the samples taken while the GPU was under load in [t0, t1] (wall clock)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
@@ -85,9 +86,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,7 +98,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.15)]
+        if not rows and self.rows:
+            rows = [self.rows[-1][1]]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nme, v in zip(names, r[3:7]):
@@ -194,6 +198,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     d, kind, V, conn, data, X, desc = workload_mesh(args.workload, rank, world)
     n_el = len(conn)
     assembly = tad.ASSEMBLY_GATHER if args.assembly == "gather" else tad.ASSEMBLY_ATOMIC
@@ -235,8 +241,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()                   # clocks are sampled under load from the warm-up on (the timed region itself is ~0.1 s)
+    load_t0 = time.time()
     for _ in range(args.warmup):
         step()
     barrier()
@@ -252,7 +257,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     dev_s = ev0.elapsed_time(ev1) * 1e-3
-    clocks = sampler.stop()
+    load_t1 = time.time()
     t_step = torch.tensor([dev_s / args.steps], dtype=torch.float64, device="cuda")
     n_total = torch.tensor([float(n_el)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -282,6 +287,7 @@ def main():
         for k, v in fn.last_timings().items():
             phase[k].append(v)
     fn.set_timing(False)
+    clocks = sampler.stop(load_t0, time.time())      # warm-up, timed steps, e2e and the per-kernel pass: all under load
     phase = {k: float(np.median(v)) for k, v in phase.items()}
     stats = fn.projection_stats()
     phi = stats["rebuilt"] / max(1, n_el)
@@ -329,7 +335,7 @@ def main():
                     "ms_per_step": e2e_t * 1e3},
             # per step: 4 element kernels (one per Hessian part), 2 reduction, 4 projection (A, B, C, fallback list), 1 assembly
             "gpu_launches": (11 if d == 3 else 8) * args.steps,
-            "clocks": clocks, "roofline": roof, "wall_s_timed_region": wall, "f": f,
+            "clocks": clocks, "projection_stats": stats, "roofline": roof, "wall_s_timed_region": wall, "f": f,
         }
         if not args.no_cpu_baseline and world == 1:
             import oracle

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -543,8 +544,8 @@ __global__ void __launch_bounds__(128) project_kernel_a(const double* __restrict
                                                           [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
 }
 
-template <int K>
-__global__ void __launch_bounds__(128, 8) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc)
+template <int K, int MINB>
+__global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc)
 {
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
@@ -610,7 +611,11 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         sc.list = list;
         const unsigned g = (unsigned)((n + 127) / 128);
         project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
-        project_kernel_b<K><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
+        static const int occ = getenv("TAD_PROJ_B_OCC") ? atoi(getenv("TAD_PROJ_B_OCC")) : 3;  // tuning knob: min blocks per SM
+        if (occ <= 3) project_kernel_b<K, 3><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
+        else if (occ <= 4) project_kernel_b<K, 4><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
+        else if (occ <= 6) project_kernel_b<K, 6><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
+        else project_kernel_b<K, 8><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         project_kernel_c<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
         // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
         project_kernel_list<K><<<kListBlocks, kListThreads, 0, st>>>(hess, stride, eps, counts, list,

@@ -331,10 +331,14 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
 
     // ---- 4. inverse iteration on T (LAPACK dstein scheme: dlagtf / dlagts, re-orthogonalisation in clusters) ----
     const double ortol = 1e-3 * onenrm;
-    const double res_limit = 2e-12 * load_r(L::off_amax);
+    const double amax = load_r(L::off_amax);
+    const double res_limit = 2e-12 * amax;
     double xjm = 0.0;
     int gpind = j_begin;
     uint32_t seed = 0x9e3779b9u;
+    double la[K], lb[K], lc[K], ld[K];  // LU factors of T - x_j I (kept across the vectors of a cluster, see below)
+    uint32_t pivmask = 0;
+    double tol = 0.0, a_last = 0.0;
     for (int j = j_begin; j < j_end; ++j)
     {
         const int jv = j - j_begin;
@@ -347,17 +351,19 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
         }
         // LU factorisation of T - xj I with partial pivoting (dlagtf); the pivot tests |a_k|/scale1 >= |c_k|/scale2
         // are cross-multiplied, and the pivots are inverted once (with the dlagts perturbation) for all solves.
-        double la[K], lb[K], lc[K], ld[K];
-        uint32_t pivmask = 0;
-        for (int i = 0; i < K; ++i)
+        // Shifts that coincide to working precision (a multiple eigenvalue, e.g. the null space) share one factorisation.
+        const bool reuse_lu = j > j_begin && fabs(xj - xjm) <= 4.0 * macheps * onenrm;
+        if (!reuse_lu)
         {
-            la[i] = d0[i] - xj;
-            lb[i] = e0[i];
-            lc[i] = e0[i];
-            ld[i] = 0.0;
-        }
-        double tol = 0.0;
-        {
+            pivmask = 0;
+            for (int i = 0; i < K; ++i)
+            {
+                la[i] = d0[i] - xj;
+                lb[i] = e0[i];
+                lc[i] = e0[i];
+                ld[i] = 0.0;
+            }
+            tol = 0.0;
             double scale1 = fabs(la[0]) + (K > 1 ? fabs(lb[0]) : 0.0);
             for (int k = 0; k < K - 1; ++k)
             {
@@ -388,14 +394,22 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
             }
             for (int i = 0; i < K; ++i) tol = fmax(tol, fmax(fabs(la[i]), fmax(fabs(lb[i]), fabs(ld[i]))));
             tol = (tol == 0.0) ? macheps : tol * macheps;
+            a_last = fabs(la[K - 1]);
+            for (int i = 0; i < K; ++i)
+            {
+                double ak = la[i];
+                if (fabs(ak) < tol) ak = (ak < 0.0) ? -tol : tol;
+                la[i] = 1.0 / ak;
+            }
         }
-        const double a_last = fabs(la[K - 1]);
-        for (int i = 0; i < K; ++i)
-        {
-            double ak = la[i];
-            if (fabs(ak) < tol) ak = (ak < 0.0) ? -tol : tol;
-            la[i] = 1.0 / ak;
-        }
+
+        // weight of v v^T in the low-rank term, and distance of l_j to the nearest unselected eigenvalue
+        double wj;
+        if (!form_b) wj = abs_mode ? -2.0 * lj : eps - lj;
+        else wj = abs_mode ? 2.0 * lj : lj - eps;
+        double gap = 1e300;
+        if (!form_b) { if (j_end < K) gap = lam[j_end] - lj; }
+        else if (j_begin > 0) gap = lj - lam[j_begin - 1];
 
         double x[K];
         for (int i = 0; i < K; ++i)
@@ -420,10 +434,12 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
         while (its < 5)
         {
             ++its;
-            // orthogonalise the right-hand side against the earlier vectors of the cluster before the solve: otherwise
+            // orthogonalise the right-hand side against the vectors computed so far (all of them, not only the cluster:
+            // the other selected eigenvectors are orthogonal anyway, and removing them confines what is left of the
+            // error to the unselected subspace, see the acceptance test) before the solve: otherwise
             // the solve amplifies those directions as much as the wanted one and the remainder after removing them
             // is noisy (residual ~100 eps |T| for the third vector of a triple eigenvalue) ...
-            for (int i = gpind; i < j; ++i)
+            for (int i = j_begin; i < j; ++i)
             {
                 const int base = L::off_vec + (i - j_begin) * K;
                 double dot = 0.0;
@@ -454,7 +470,7 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
                 x[k] = temp * la[k];
             }
             // ... and once more after it (modified Gram-Schmidt)
-            for (int i = gpind; i < j; ++i)
+            for (int i = j_begin; i < j; ++i)
             {
                 const int base = L::off_vec + (i - j_begin) * K;
                 double dot = 0.0;
@@ -476,7 +492,10 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
 #if defined(TAD_PROJ_DEBUG) && !defined(__CUDA_ARCH__)
             printf("  j=%d lj=%.3e xj=%.3e its=%d res=%.3e (limit %.3e) gpind=%d a_last=%.3e tol=%.3e\n", j, lj, xj, its, res * inv, res_limit, gpind, a_last, tol);
 #endif
-            if (res * inv <= res_limit)
+            // After the orthogonalisation the error of y lies in the unselected eigenspace, at distance >= gap from l_j,
+            // and enters the projected matrix scaled by |w_j| / gap: a vector with a tiny weight (the null space of an
+            // element Hessian has w_j ~ eps) may carry a much larger residual.
+            if (res * inv <= res_limit || res * inv * fabs(wj) <= 1e-12 * amax * gap)
             {
                 converged = true;
                 break;
@@ -484,10 +503,6 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
         }
         if (!converged) return PROJ_FALLBACK;
         for (int i = 0; i < K; ++i) store_w(L::off_vec + jv * K + i, x[i] * inv);
-        // weight of v v^T in the low-rank term
-        double wj;
-        if (!form_b) wj = abs_mode ? -2.0 * lj : eps - lj;
-        else wj = abs_mode ? 2.0 * lj : lj - eps;
         store_w(L::off_wgt + jv, wj);
         xjm = xj;
     }
