@@ -25,7 +25,7 @@ OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION = 1, 2, 3
 
 # term kinds of csrc/energies.cu
 SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
-EDGE_DIRICHLET1D, QUADRATIC2D, REPEATED_HANDLE, TRIG_MIX2D = 5, 6, 7, 8
+EDGE_DIRICHLET1D, QUADRATIC2D, REPEATED_HANDLE, TRIG_MIX2D, SQRT1D = 5, 6, 7, 8, 9
 SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
 
 # every symbol include/tinyad_b200.h declares (checked by tests/test_abi.py)
@@ -110,6 +110,8 @@ def energies():
         L.tadx_handle.argtypes = [vp]
         L.tadx_handle.restype = vp
         L.tadx_add_term.argtypes = [vp, ctypes.c_int, i64, vp, ctypes.c_int, vp, ctypes.c_int]
+        L.tadx_scalar_case.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int]
+        L.tadx_selftest.argtypes = [ctypes.c_int]
         _en = L
     return _en
 
@@ -292,3 +294,37 @@ def fp64_peak_tflops(device=0, seconds=0.5):
     t = ctypes.c_double()
     _check(runtime().tad_bench_fp64_peak(device, seconds, ctypes.byref(t)))
     return t.value
+
+
+# order of enum ScalarCase in csrc/energies.cuh
+SCALAR_CASES = [
+    "neg", "sqrt", "sqr", "fabs", "abs", "exp", "log", "log2", "log10", "sin", "cos", "tan", "asin", "acos", "atan",
+    "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "pow_int", "pow_real",
+    "add", "sub", "mul", "div", "add_s", "s_add", "sub_s", "s_sub", "mul_s", "s_mul", "div_s", "s_div",
+    "iadd", "isub", "imul", "idiv", "iadd_s", "isub_s", "imul_s", "idiv_s", "min", "max", "clamp", "quadratic", "atan2_1",
+    "sqr_pow_mul", "atan2_const", "atan2_2", "hypot", "div2d", "div2d_2", "plus_minus_mult_div_2d", "sphere",
+    "c_mul", "c_mul_d", "c_d_mul", "c_div", "c_div_d", "c_add", "c_sub", "c_sqr", "c_conj", "c_abs", "c_arg", "symm_dirich6",
+]
+
+
+def scalar_case(name, params, k, on_device=False):
+    """Known-answer case of the reference's Scalar tests on the product's Scalar (host build or a 1-thread kernel).
+    Returns a list of (val, grad[k], Hess[k, k])."""
+    p = np.zeros(16)
+    p[:len(params)] = params
+    out = np.zeros(256)
+    n = energies().tadx_scalar_case(SCALAR_CASES.index(name), p.ctypes.data, out.ctypes.data, int(on_device))
+    if n < 0:
+        raise RuntimeError(f"scalar case {name}: code {n}")
+    res, o = [], 0
+    for _ in range(n):
+        res.append((out[o], out[o + 1:o + 1 + k].copy(), out[o + 1 + k:o + 1 + k + k * k].reshape(k, k).copy()))
+        o += 1 + k + k * k
+    return res
+
+
+def selftest(device=0):
+    """C++ facade semantics (default-constructed / moved functions, errors leave the object usable, x_from_data ...)."""
+    code = energies().tadx_selftest(device)
+    if code != 0:
+        raise AssertionError(f"tadx_selftest failed at step {code}: {energies().tadx_last_error().decode()}")

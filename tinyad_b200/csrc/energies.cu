@@ -46,7 +46,7 @@ thread_local std::string g_err;
 enum
 {
     K_SYMDIRICHLET2D = 1, K_PENALTY2D = 2, K_SYMDIRICHLET3D = 3, K_PENALTY3D = 4, K_EDGE_DIRICHLET1D = 5,
-    K_QUADRATIC2D = 6, K_REPEATED_HANDLE = 7, K_TRIG_MIX2D = 8,
+    K_QUADRATIC2D = 6, K_REPEATED_HANDLE = 7, K_TRIG_MIX2D = 8, K_SQRT1D = 9,
     K_SOS_SYMDIRICHLET2D = 101, K_SOS_PENALTY2D = 102, K_SOS_POLYCURL2D = 103,
 };
 
@@ -149,6 +149,7 @@ int tadx_add_term(void* h, int kind, int64_t n_elements, const int32_t* conn, in
         case K_SYMDIRICHLET3D: need(P->s3 && valence == 4 && n_data == 10); P->s3->add_elements<4>(els, SymDirichlet3D{C, D}); break;
         case K_PENALTY3D: need(P->s3 && valence == 1 && n_data == 3); P->s3->add_elements<1>(els, Penalty<3>{C, D}); break;
         case K_EDGE_DIRICHLET1D: need(P->s1 && valence == 2 && n_data == 1); P->s1->add_elements<2>(els, EdgeDirichlet1D{C, D}); break;
+        case K_SQRT1D: need(P->s1 && valence == 1 && n_data == 1); P->s1->add_elements<1>(els, Sqrt1D{C, D}); break;
         case K_QUADRATIC2D: need(P->s2 && valence == 1 && n_data == 1); P->s2->add_elements<1>(els, Quadratic2D{C, D}); break;
         case K_REPEATED_HANDLE: need(P->s2 && valence == 2 && n_data == 1); P->s2->add_elements<2>(els, RepeatedHandle{C, D}); break;
         case K_TRIG_MIX2D: need(P->s2 && valence == 2 && n_data == 1); P->s2->add_elements<2>(els, TrigMix2D{C, D}); break;
@@ -160,4 +161,97 @@ int tadx_add_term(void* h, int kind, int64_t n_elements, const int32_t* conn, in
     });
 }
 
+// ---- known-answer scalar cases on the device (one thread) or on the host ----
+int tadx_scalar_case(int id, const double* params16, double* out, int on_device);
+
+// ---- facade semantics of the reference's tests, exercised in C++ (returns 0 on success, else a failing step) ----
+int tadx_selftest(int device)
+{
+    g_err.clear();
+    try
+    {
+        EvalSettings es;
+        es.device = device;
+        // default-constructed functions evaluate to 0 / empty (tests/ScalarFunctionTest.cc:183-189)
+        ScalarFunction<2> empty;
+        if (empty.eval(std::vector<double>()) != 0.0) return 1;
+        auto [f0, g0, H0] = empty.eval_with_hessian_proj(std::vector<double>());
+        if (f0 != 0.0 || !g0.empty() || H0.nonZeros() != 0) return 2;
+        // a function built in place, then moved: the moved-to object evaluates, the moved-from one is empty (:190-252)
+        DeviceArray dc, dd;
+        const int32_t conn[1] = {0};
+        const double data[1] = {1.0};
+        if (!upload_soa(conn, 1, 1, 32, dc) || !upload_soa(data, 1, 1, 32, dd)) return 3;
+        ConnView C{static_cast<const int32_t*>(dc.p), 32};
+        DataView D{static_cast<const double*>(dd.p), 32};
+        auto func = scalar_function<2>(range(1), es);
+        func.add_elements<1>(range(1), Quadratic2D{C, D});
+        ScalarFunction<2> moved(std::move(func));
+        const std::vector<double> x = {1.0, 2.0};
+        if (moved.eval(x) != 12.0) return 4;                                   // tests/ScalarFunctionTest.cc:72-110
+        auto [f, g, H] = moved.eval_with_derivatives(x);
+        if (f != 12.0 || g[0] != 9.0 || g[1] != 6.0) return 5;
+        if (H.coeff(0, 0) != 4.0 || H.coeff(0, 1) != 2.0 || H.coeff(1, 0) != 2.0 || H.coeff(1, 1) != 2.0) return 6;
+        if (func.n_vars != 0 || func.eval(std::vector<double>()) != 0.0) return 7;
+        ScalarFunction<2> assigned;
+        assigned = std::move(moved);
+        if (assigned(x) != 12.0) return 8;
+        // size mismatch throws (ScalarFunctionImpl.hh:262) and the object stays usable
+        bool threw = false;
+        try { assigned.eval(std::vector<double>(3, 0.0)); } catch (const std::runtime_error&) { threw = true; }
+        if (!threw || assigned.eval(x) != 12.0) return 9;
+        // an error inside the element evaluation is reported to the caller and the function stays usable
+        // (tests/ExceptionTest.cc:8-54; here: non-finite derivative, ScalarObjectiveTerm.hh:210,252-253)
+        auto fs = scalar_function<1>(range(1), es);
+        fs.add_elements<1>(range(1), Sqrt1D{C, D});
+        threw = false;
+        try { fs.eval_with_gradient(std::vector<double>{-1.0}); } catch (const std::runtime_error&) { threw = true; }
+        if (!threw) return 10;
+        auto [fv, gv] = fs.eval_with_gradient(std::vector<double>{4.0});
+        if (fv != 2.0 || gv[0] != 0.25) return 11;
+        // x_from_data / x_to_data (ScalarFunctionImpl.hh:216-254)
+        auto xs = assigned.x_from_data([](int64_t) { return std::vector<double>{3.0, 5.0}; });
+        if (xs.size() != 2 || xs[0] != 3.0 || xs[1] != 5.0) return 12;
+        double seen = 0.0;
+        assigned.x_to_data(xs, [&](int64_t, const Vec<double, 2>& pv) { seen = pv[0] + pv[1]; });
+        if (seen != 8.0) return 13;
+        // non-compact variable indices are rejected (ScalarFunctionImpl.hh:59)
+        threw = false;
+        try { ScalarFunction<2> bad(std::vector<int64_t>{0, 2}, es); } catch (const std::runtime_error&) { threw = true; }
+        if (!threw) return 14;
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 }  // extern "C"
+
+namespace
+{
+__global__ void scalar_case_kernel(int id, const double* p, double* out, int* n) { *n = tadx::scalar_case_run(id, p, out); }
+}  // namespace
+
+extern "C" int tadx_scalar_case(int id, const double* params16, double* out, int on_device)
+{
+    if (!on_device) return tadx::scalar_case_run(id, params16, out);
+    double *dp = nullptr, *dout = nullptr;
+    int* dn = nullptr;
+    int n = -100;
+    if (cudaMalloc(&dp, 16 * sizeof(double)) != cudaSuccess || cudaMalloc(&dout, 256 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&dn, sizeof(int)) != cudaSuccess)
+        return -100;
+    cudaMemcpy(dp, params16, 16 * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(dout, 0, 256 * sizeof(double));
+    scalar_case_kernel<<<1, 1>>>(id, dp, dout, dn);
+    if (cudaDeviceSynchronize() == cudaSuccess)
+    {
+        cudaMemcpy(&n, dn, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(out, dout, 256 * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dp); cudaFree(dout); cudaFree(dn);
+    return n;
+}

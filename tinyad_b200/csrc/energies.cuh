@@ -91,6 +91,18 @@ struct EdgeDirichlet1D  // data: w ; w * (x_a - x_b)^2
     }
 };
 
+struct Sqrt1D  // ExceptionTest analogue: sqrt(x) has a NaN derivative for x < 0 -> TAD_NONFINITE_DERIVATIVE; data unused
+{
+    ConnView C; DataView D;
+    template <class E>
+    TINYAD_HD auto operator()(E& element) const -> TINYAD_SCALAR_TYPE(element)
+    {
+        using T = TINYAD_SCALAR_TYPE(element);
+        T x = element.variable(C(element.handle, 0));
+        return sqrt(x) * D(element.handle, 0);
+    }
+};
+
 struct Quadratic2D  // ScalarFunctionTest.cc:72-146, data: sign
 {
     ConnView C; DataView D;
@@ -195,5 +207,155 @@ struct SosPolycurl2D  // synthetic polycurl-style complex residual (config C4 st
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Known-answer cases of the reference's Scalar tests (tests/ScalarTest*.cc, ComplexTest.cc) on the product's
+// Scalar.  Same case vocabulary as oracle_capi.cc / tests/golden/scalar_cases.json; runs on host and device.
+// out = [val, grad(k), Hess(k*k)] per returned scalar.
+// ---------------------------------------------------------------------------------------------
+enum ScalarCase
+{
+    SC_NEG, SC_SQRT, SC_SQR, SC_FABS, SC_ABS, SC_EXP, SC_LOG, SC_LOG2, SC_LOG10, SC_SIN, SC_COS, SC_TAN, SC_ASIN, SC_ACOS, SC_ATAN,
+    SC_SINH, SC_COSH, SC_TANH, SC_ASINH, SC_ACOSH, SC_ATANH, SC_POW_INT, SC_POW_REAL,
+    SC_ADD, SC_SUB, SC_MUL, SC_DIV, SC_ADD_S, SC_S_ADD, SC_SUB_S, SC_S_SUB, SC_MUL_S, SC_S_MUL, SC_DIV_S, SC_S_DIV,
+    SC_IADD, SC_ISUB, SC_IMUL, SC_IDIV, SC_IADD_S, SC_ISUB_S, SC_IMUL_S, SC_IDIV_S, SC_MIN, SC_MAX, SC_CLAMP, SC_QUADRATIC, SC_ATAN2_1,
+    SC_SQR_POW_MUL, SC_ATAN2_CONST, SC_ATAN2_2, SC_HYPOT, SC_DIV2D, SC_DIV2D_2, SC_PMMD_2D, SC_SPHERE,
+    SC_C_MUL, SC_C_MUL_D, SC_C_D_MUL, SC_C_DIV, SC_C_DIV_D, SC_C_ADD, SC_C_SUB, SC_C_SQR, SC_C_CONJ, SC_C_ABS, SC_C_ARG, SC_SYMM_DIRICH6,
+    SC_COUNT
+};
+
+template <int k>
+TINYAD_HD inline void sc_put(const Scalar<k, true>& s, double*& out)
+{
+    *out++ = s.val;
+    for (int i = 0; i < k; ++i) *out++ = s.grad[i];
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) *out++ = s.Hess(i, j);
+}
+
+TINYAD_HD inline int scalar_case_run(int id, const double* p, double* out)
+{
+    using A1 = Scalar<1, true>;
+    using A2 = Scalar<2, true>;
+    const A1 a = A1::known_derivatives(p[0], p[1], p[2]);
+    const A1 b = A1::known_derivatives(p[3], p[4], p[5]);
+    const double sc = p[6];
+    switch (id)
+    {
+    case SC_NEG: sc_put(-a, out); return 1;
+    case SC_SQRT: sc_put(sqrt(a), out); return 1;
+    case SC_SQR: sc_put(sqr(a), out); return 1;
+    case SC_FABS: sc_put(fabs(a), out); return 1;
+    case SC_ABS: sc_put(abs(a), out); return 1;
+    case SC_EXP: sc_put(exp(a), out); return 1;
+    case SC_LOG: sc_put(log(a), out); return 1;
+    case SC_LOG2: sc_put(log2(a), out); return 1;
+    case SC_LOG10: sc_put(log10(a), out); return 1;
+    case SC_SIN: sc_put(sin(a), out); return 1;
+    case SC_COS: sc_put(cos(a), out); return 1;
+    case SC_TAN: sc_put(tan(a), out); return 1;
+    case SC_ASIN: sc_put(asin(a), out); return 1;
+    case SC_ACOS: sc_put(acos(a), out); return 1;
+    case SC_ATAN: sc_put(atan(a), out); return 1;
+    case SC_SINH: sc_put(sinh(a), out); return 1;
+    case SC_COSH: sc_put(cosh(a), out); return 1;
+    case SC_TANH: sc_put(tanh(a), out); return 1;
+    case SC_ASINH: sc_put(asinh(a), out); return 1;
+    case SC_ACOSH: sc_put(acosh(a), out); return 1;
+    case SC_ATANH: sc_put(atanh(a), out); return 1;
+    case SC_POW_INT: sc_put(pow(a, (int)p[3]), out); return 1;
+    case SC_POW_REAL: sc_put(pow(a, p[3]), out); return 1;
+    case SC_ADD: sc_put(a + b, out); return 1;
+    case SC_SUB: sc_put(a - b, out); return 1;
+    case SC_MUL: sc_put(a * b, out); return 1;
+    case SC_DIV: sc_put(a / b, out); return 1;
+    case SC_ADD_S: sc_put(a + sc, out); return 1;
+    case SC_S_ADD: sc_put(sc + a, out); return 1;
+    case SC_SUB_S: sc_put(a - sc, out); return 1;
+    case SC_S_SUB: sc_put(sc - a, out); return 1;
+    case SC_MUL_S: sc_put(a * sc, out); return 1;
+    case SC_S_MUL: sc_put(sc * a, out); return 1;
+    case SC_DIV_S: sc_put(a / sc, out); return 1;
+    case SC_S_DIV: sc_put(sc / a, out); return 1;
+    case SC_IADD: { A1 t = a; t += b; sc_put(t, out); return 1; }
+    case SC_ISUB: { A1 t = a; t -= b; sc_put(t, out); return 1; }
+    case SC_IMUL: { A1 t = a; t *= b; sc_put(t, out); return 1; }
+    case SC_IDIV: { A1 t = a; t /= b; sc_put(t, out); return 1; }
+    case SC_IADD_S: { A1 t = a; t += sc; sc_put(t, out); return 1; }
+    case SC_ISUB_S: { A1 t = a; t -= sc; sc_put(t, out); return 1; }
+    case SC_IMUL_S: { A1 t = a; t *= sc; sc_put(t, out); return 1; }
+    case SC_IDIV_S: { A1 t = a; t /= sc; sc_put(t, out); return 1; }
+    case SC_MIN: sc_put(min(a, b), out); return 1;
+    case SC_MAX: sc_put(max(a, b), out); return 1;
+    case SC_CLAMP: sc_put(clamp(a, b, A1::known_derivatives(p[6], p[7], p[8])), out); return 1;
+    case SC_QUADRATIC: { A1 x(p[0], 0); sc_put(sqr(x) + x + 2.0, out); return 1; }
+    case SC_ATAN2_1: { A1 x(p[0], 0); A1 y = sqr(x) - x - 1.0; sc_put(atan2(y, x), out); return 1; }
+    default: break;
+    }
+    const A2 x(p[0], 0), y(p[1], 1);
+    switch (id)
+    {
+    case SC_SQR_POW_MUL:
+    {
+        A2 q = x * x + 7.0 * y * y - 3.0 * x * 3.0 + x + 2.0 * y;
+        sc_put(sqr(q), out); sc_put(pow(q, 2), out); sc_put(q * q, out);
+        return 3;
+    }
+    case SC_ATAN2_CONST: sc_put(atan2(y, x), out); return 1;
+    case SC_ATAN2_2:
+    {
+        A2 u = 0.5 * sqr(x) - sqr(y) - y;
+        A2 v = -sqr(x - 2.0) - sqr(y - 3.0) + 1.0;
+        sc_put(atan2(v, u), out); sc_put(atan(v / u), out);
+        return 2;
+    }
+    case SC_HYPOT: sc_put(hypot(x, y), out); return 1;
+    case SC_DIV2D: sc_put(sqr(x) / y, out); return 1;
+    case SC_DIV2D_2:
+    {
+        A2 u = 0.5 * sqr(x) - sqr(y) + 2.0 * x - y;
+        A2 v = -sqr(x - 2.0) - sqr(y - 3.0) + 1.0;
+        sc_put(u / v, out);
+        return 1;
+    }
+    case SC_PMMD_2D: sc_put((sqr(x) + x) * (sqr(y) - y) / (y - 1.0), out); return 1;
+    case SC_SPHERE: sc_put(sin(x) * cos(y), out); sc_put(sin(x) * sin(y), out); sc_put(cos(x), out); return 3;
+    default: break;
+    }
+    {
+        using C = Complex<A2>;
+        const C ca(x, y);
+        const Complex<double> cd(p[2], p[3]);
+        const C cb(A2(p[2]) + 0.5 * x, A2(p[3]) - 0.25 * y);
+        switch (id)
+        {
+        case SC_C_MUL: { auto r = ca * cb; sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_MUL_D: { auto r = ca * cd; sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_D_MUL: { auto r = cd * ca; sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_DIV: { auto r = ca / cb; sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_DIV_D: { auto r = ca / cd; sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_ADD: { auto r = ca + cb; sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_SUB: { auto r = ca - cb; sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_SQR: { auto r = sqr(ca); sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_CONJ: { auto r = conj(ca); sc_put(r.re, out); sc_put(r.im, out); return 2; }
+        case SC_C_ABS: sc_put(abs(ca), out); return 1;
+        case SC_C_ARG: sc_put(arg(ca), out); return 1;
+        default: break;
+        }
+    }
+    if (id == SC_SYMM_DIRICH6)
+    {
+        using A6 = Scalar<6, true>;
+        Vec<double, 2> ar(p[6], p[7]), br(p[8], p[9]), cr(p[10], p[11]);
+        Mat<double, 2, 2> Mr = col_mat(br - ar, cr - ar);
+        Vec<A6, 2> va(A6(p[0], 0), A6(p[1], 1)), vb(A6(p[2], 2), A6(p[3], 3)), vc(A6(p[4], 4), A6(p[5], 5));
+        Mat<A6, 2, 2> M = col_mat(vb - va, vc - va);
+        Mat<A6, 2, 2> J = M * Mr.inverse();
+        A6 E = J.squaredNorm() + J.inverse().squaredNorm();
+        sc_put(E, out);
+        return 1;
+    }
+    return -1;
+}
 
 }  // namespace tadx
