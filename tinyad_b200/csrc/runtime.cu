@@ -503,20 +503,26 @@ __global__ void __launch_bounds__(32) project_kernel_full(double* __restrict__ h
     project_full_one<K>(hess + el, stride, eps, proj_smem + threadIdx.x, 32, counts, true);
 }
 
-// The elements the fast path could not finish (counts[2] of them, normally none or a fraction of a percent): a small
-// fixed grid strides over the list; the work matrix lives in a global scratch buffer ([entry][thread], coalesced) so that
-// the launch needs no shared-memory carve-out switch and costs nothing when the list is empty.
-constexpr int kListBlocks = 296, kListThreads = 64;
+// The elements the fast path could not finish (counts[2] of them: a few per million on the tet workloads): a small fixed
+// grid of single-warp blocks strides over the list.  The cost of this launch is the serial latency of one full solve, so the
+// work matrix is kept in STATIC shared memory when it fits the 48 KB static limit (K <= 12; no opt-in / carve-out switch),
+// else in a global scratch buffer laid out [entry][thread].
+constexpr int kListBlocks = 148, kListThreads = 32;
 template <int K>
 __global__ void __launch_bounds__(kListThreads) project_kernel_list(double* __restrict__ hess, int64_t stride, double eps,
                                                                     unsigned long long* counts, const int64_t* __restrict__ list,
                                                                     double* __restrict__ work)
 {
+    constexpr bool use_smem = (size_t)(K * K + 2 * K) * kListThreads * sizeof(double) <= 48 * 1024;
+    __shared__ double sm[use_smem ? (K * K + 2 * K) * kListThreads : 1];
     const int64_t count = (int64_t)counts[2];
     const int nthreads = gridDim.x * blockDim.x;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = tid; i < count; i += nthreads)
-        project_full_one<K>(hess + list[i], stride, eps, work + tid, nthreads, counts, false);
+    {
+        if (use_smem) project_full_one<K>(hess + list[i], stride, eps, sm + threadIdx.x, kListThreads, counts, false);
+        else project_full_one<K>(hess + list[i], stride, eps, work + tid, nthreads, counts, false);
+    }
 }
 
 // Fast path (Detail/Projection.hh), three kernels with different resource profiles, one thread per element:

@@ -31,6 +31,22 @@ namespace TinyAD
 namespace detail
 {
 
+// 1/sqrt(t) for t in the normal range, without the special-case branches of rsqrt(): hardware approximation plus
+// two Newton steps (host: exact).  Only used on data scaled to O(1).
+TINYAD_HD TINYAD_INLINE double rsqrt_fast(double t)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+    const double ht = 0.5 * t;
+    y = y * fma(-ht * y, y, 1.5);
+    y = y * fma(-ht * y, y, 1.5);
+    return y;
+#else
+    return 1.0 / sqrt(t);
+#endif
+}
+
 enum ProjectCode
 {
     PROJ_DOMINANT = 0,   // early-out 1, H untouched
@@ -219,16 +235,23 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
     }
 
     // ---- 2. eigenvalues of T: implicit QL without vectors (EISPACK tql1 scheme) ----
+    // T is scaled by 1/|T|_1 first: with entries of O(1) the rotations need no overflow / underflow guards
+    // (a sub-diagonal entry inside the active block is > eps * tst1, so p^2 + e^2 >= ~1e-32).
     double lam[K];
     double onenrm = 0.0;
+    for (int i = 0; i < K; ++i)
     {
+        const double rowsum = fabs(d0[i]) + fabs(e0[i]) + (i > 0 ? fabs(e0[i - 1]) : 0.0);
+        onenrm = fmax(onenrm, rowsum);
+    }
+    if (!(onenrm == onenrm) || onenrm > 1e300) return PROJ_FALLBACK;  // NaN / Inf input: the caller's finite check reports it
+    {
+        const double inv_nrm = onenrm > 0.0 ? 1.0 / onenrm : 0.0;
         double ee[K];
         for (int i = 0; i < K; ++i)
         {
-            lam[i] = d0[i];
-            ee[i] = e0[i];
-            const double rowsum = fabs(d0[i]) + fabs(e0[i]) + (i > 0 ? fabs(e0[i - 1]) : 0.0);
-            onenrm = fmax(onenrm, rowsum);
+            lam[i] = d0[i] * inv_nrm;
+            ee[i] = e0[i] * inv_nrm;
         }
         double f = 0.0, tst1 = 0.0;
         for (int l = 0; l < K; ++l)
@@ -272,22 +295,8 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
                         g = c * ei;
                         h = c * p;
                         const double t = fma(p, p, ei * ei);
-                        double rinv;
-                        if (t > 1e-280 && t < 1e280)
-                        {
-#if defined(__CUDA_ARCH__)
-                            rinv = rsqrt(t);
-#else
-                            rinv = 1.0 / sqrt(t);
-#endif
-                            r = t * rinv;
-                        }
-                        else
-                        {
-                            r = hypot(p, ei);
-                            rinv = 1.0 / r;
-                        }
-                        ee[i + 1] = s * r;
+                        const double rinv = rsqrt_fast(t);
+                        ee[i + 1] = s * (t * rinv);
                         s = ei * rinv;
                         c = p * rinv;
                         p = c * di - s * g;
@@ -303,6 +312,7 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
             lam[l] = lam[l] + f;
             ee[l] = 0.0;
         }
+        for (int i = 0; i < K; ++i) lam[i] *= onenrm;
     }
     // ascending order (insertion sort, K is tiny)
     for (int i = 1; i < K; ++i)
@@ -316,7 +326,6 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
         }
         lam[j + 1] = v;
     }
-    if (!(onenrm == onenrm) || onenrm > 1e300) return PROJ_FALLBACK;  // NaN / Inf input: the caller's finite check reports it
 
     // ---- 3. which eigenvalues move (HessianProjection.hh:71-91) ----
     const bool abs_mode = eps < 0.0;
