@@ -333,8 +333,9 @@ def main():
                        "setup_s_pattern_and_maps": setup_s},
             "e2e": {"value": n_total / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(8 * fn.n_vars), "d2h_bytes_per_step": int(8 * (fn.n_vars + nnz + 1)),
                     "ms_per_step": e2e_t * 1e3},
-            # per step: 4 element kernels (one per Hessian part), 2 reduction, 4 projection (A, B, C, fallback list), 1 assembly
-            "gpu_launches": (11 if d == 3 else 8) * args.steps,
+            # per step: 4 element kernels (one per Hessian part; 1 for triangles), 2 reduction, 3 projection (A, B, fallback list),
+            # 1 fused projection-C + assembly
+            "gpu_launches": (10 if d == 3 else 7) * args.steps,
             "clocks": clocks, "projection_stats": stats, "roofline": roof, "wall_s_timed_region": wall, "f": f,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -595,7 +595,7 @@ size_t project_scratch_doubles(int64_t stride)
 // doubles, scratch_i: stride int32 + n int64 (see project_scratch_bytes).
 template <int K>
 int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, int32_t* codes,
-                   int64_t* list, bool full_only, cudaStream_t st)
+                   int64_t* list, bool full_only, ProjScratch* fuse_out, cudaStream_t st)
 {
     using L = TinyAD::detail::ProjLayout<K>;
     constexpr size_t smem = (size_t)ProjSmem<K>::doubles_per_warp * sizeof(double);
@@ -622,10 +622,11 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         else if (occ <= 4) project_kernel_b<K, 4><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         else if (occ <= 6) project_kernel_b<K, 6><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         else project_kernel_b<K, 8><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
-        project_kernel_c<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
         // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
         project_kernel_list<K><<<kListBlocks, kListThreads, 0, st>>>(hess, stride, eps, counts, list,
                                                                      scratch_d + (size_t)(L::nR + L::nW) * stride);
+        if (fuse_out) *fuse_out = sc;  // phase C is fused with the assembly by the caller
+        else project_kernel_c<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
     }
     return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "project kernel launch failed");
 }
@@ -653,25 +654,25 @@ size_t project_scratch_doubles_rt(int k, int64_t stride)
 }
 
 int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d,
-                     int32_t* codes, int64_t* list, bool full_only, cudaStream_t st)
+                     int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, cudaStream_t st)
 {
     if (n <= 0 || k <= 0) return TAD_OK;
     switch (k)
     {
-    case 1: return launch_project<1>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 2: return launch_project<2>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 3: return launch_project<3>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 4: return launch_project<4>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 5: return launch_project<5>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 6: return launch_project<6>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 7: return launch_project<7>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 8: return launch_project<8>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 9: return launch_project<9>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 10: return launch_project<10>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 12: return launch_project<12>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
-    case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, st);
+    case 1: return launch_project<1>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 2: return launch_project<2>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 3: return launch_project<3>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 4: return launch_project<4>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 5: return launch_project<5>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 6: return launch_project<6>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 7: return launch_project<7>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 8: return launch_project<8>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 9: return launch_project<9>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 10: return launch_project<10>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 12: return launch_project<12>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
     default: return fail(TAD_NOT_SUPPORTED, "Hessian projection is instantiated for k in {1..10,12,15,16,18}");
     }
 }
@@ -835,6 +836,104 @@ __global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __r
         }
     }
     if (!finite) atomicOr(err, ERR_NONFINITE);
+}
+
+// Projection phase C fused with the atomic assembly: the projected Hessian of an element is formed in registers
+// (low-rank update of H, Detail/Projection.hh proj_apply) and scattered from there, instead of being written back to
+// the staging buffer and read again by the assembly kernel (saves 1.35 KB of HBM traffic per tet and one launch).
+template <int D, int N>
+__global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* __restrict__ hess, int64_t n, int64_t stride, double eps,
+                                                                 ProjScratch sc, const int32_t* __restrict__ rec,
+                                                                 const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
+                                                                 const double* __restrict__ grad, double* __restrict__ g,
+                                                                 double* __restrict__ Hv, int32_t* err)
+{
+    constexpr int K = D * N;
+    constexpr int H = K * (K + 1) / 2;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double* hp = hess + e;
+    double acc[H];
+    if (sc.codes[e] == TinyAD::detail::PROJ_REBUILT)
+    {
+        const double* rp = sc.R + e;
+        const double* wp = sc.W + e;
+        TinyAD::detail::proj_apply<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
+                                      [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { acc[s] = v; }, eps);
+    }
+    else
+    {
+#pragma unroll
+        for (int s = 0; s < H; ++s) acc[s] = hp[(int64_t)s * stride];
+    }
+    bool finite = true;
+#pragma unroll
+    for (int bi = 0; bi < N; ++bi)
+    {
+        const int32_t vi = rec[(int64_t)bi * stride + e];
+        if (vi < 0) continue;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+        {
+            const double v = grad[(int64_t)(D * bi + a) * stride + e];
+            finite = finite && isfinite(v);
+            atomicAdd(&g[(int64_t)D * vi + a], v);
+        }
+    }
+#pragma unroll
+    for (int bi = 0; bi < N; ++bi)
+    {
+        const int32_t rs = rstride[(int64_t)bi * stride + e];
+#pragma unroll
+        for (int bj = 0; bj < N; ++bj)
+        {
+            const int32_t base = blockbase[(int64_t)(bi * N + bj) * stride + e];
+            if (base < 0) continue;
+#pragma unroll
+            for (int a = 0; a < D; ++a)
+#pragma unroll
+                for (int b = 0; b < D; ++b)
+                {
+                    const double v = acc[hess_seq_index(K, D * bi + a, D * bj + b)];
+                    finite = finite && isfinite(v);
+                    atomicAdd(&Hv[(int64_t)base + (int64_t)a * rs + b], v);
+                }
+        }
+    }
+    if (!finite) atomicOr(err, ERR_NONFINITE);
+}
+
+template <int D, int N>
+void launch_c_assemble(const Term& t, const double* grad, const double* hess, int64_t n, double eps, ProjScratch sc, double* g, double* Hv,
+                       int32_t* err, cudaStream_t st)
+{
+    project_c_assemble_kernel<D, N><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
+                                                                                 t.rstride.p, grad, g, Hv, err);
+}
+
+bool fused_c_assemble_supported(int d, int N) { return d >= 1 && d <= 3 && N >= 1 && N <= 4; }
+
+int c_assemble(int d, const Term& t, const double* grad, const double* hess, int64_t n, double eps, ProjScratch sc, double* g, double* Hv,
+               int32_t* err, cudaStream_t st)
+{
+    if (n <= 0) return TAD_OK;
+    switch (d * 100 + t.N)
+    {
+    case 101: launch_c_assemble<1, 1>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 102: launch_c_assemble<1, 2>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 103: launch_c_assemble<1, 3>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 104: launch_c_assemble<1, 4>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 201: launch_c_assemble<2, 1>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 202: launch_c_assemble<2, 2>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 203: launch_c_assemble<2, 3>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 204: launch_c_assemble<2, 4>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 301: launch_c_assemble<3, 1>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 302: launch_c_assemble<3, 2>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 303: launch_c_assemble<3, 3>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 304: launch_c_assemble<3, 4>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    default: return fail(TAD_NOT_SUPPORTED, "no fused projection/assembly kernel for this (d, N)");
+    }
+    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "fused projection/assembly launch failed");
 }
 
 // generic (runtime d, N) fallback
@@ -1435,11 +1534,16 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         TAD_TRY(sum_to(f, a.val, t.n, t.stride, 1, false, f->fterm.p + ti));
         if (mode == TAD_MODE_SECOND && project && ti > 0)  // the fallback list is per term
             TAD_CUDA(cudaMemsetAsync(f->proj_counts.p + 2, 0, sizeof(unsigned long long), st));
+        // atomic mode + fast projection: the last projection phase (low-rank update) is fused with the scatter
+        const bool fuse = mode == TAD_MODE_SECOND && project && !gather && !f->projection_full && fused_c_assemble_supported(f->d, t.N);
+        ProjScratch fused_sc;
         if (mode == TAD_MODE_SECOND && project)
             TAD_TRY(project_dispatch(t.k, a.hess, t.n, t.stride, eps, f->proj_counts.p, f->proj_scratch.p, f->proj_codes.p, f->proj_list.p,
-                                     f->projection_full != 0, st));
+                                     f->projection_full != 0, fuse ? &fused_sc : nullptr, st));
         if (f->timing) cudaEventRecord(f->ev[3], st);
-        if (mode >= TAD_MODE_FIRST && !gather)
+        if (fuse)
+            TAD_TRY(c_assemble(f->d, t, a.grad, a.hess, t.n, eps, fused_sc, g, Hv, f->err.p, st));
+        else if (mode >= TAD_MODE_FIRST && !gather)
             TAD_TRY(assemble_atomic(f->d, t, a.grad, mode == TAD_MODE_SECOND ? a.hess : nullptr, t.n, g, Hv, f->err.p, st));
         if (f->timing)
         {
@@ -1855,7 +1959,7 @@ int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double
     TAD_CUDA(list.ensure((size_t)std::max<int64_t>(stride, 1)));
     TAD_CUDA(codes.ensure((size_t)std::max<int64_t>(stride, 1)));
     if (method != 1) TAD_CUDA(scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(k, stride))));
-    TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts, scratch.p, codes.p, list.p, method == 1, st));
+    TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts, scratch.p, codes.p, list.p, method == 1, nullptr, st));
     unsigned long long h_counts[3] = {0, 0, 0};
     TAD_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     TAD_CUDA(cudaStreamSynchronize(st));  // the scratch buffers above are locals
