@@ -121,6 +121,14 @@ struct TermDev  // device-visible description used by pattern / gather kernels
     const double* hess;
 };
 
+// Side stream of the fused path: the full solver of the few listed elements runs next to the fused phase C / assembly
+// kernel (its cost is the serial latency of one full eigensolve, ~0.15 ms, not throughput).
+struct ProjSide
+{
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_b = nullptr, ev_list = nullptr;
+};
+
 }  // namespace
 
 struct tad_function_s
@@ -160,6 +168,7 @@ struct tad_function_s
     int64_t last_proj[3] = {0, 0, 0};
     float last_ms[4] = {0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ProjSide proj_side;            // side stream + events of the fused projection / assembly path
     std::recursive_mutex mtx;      // eval* may be called concurrently (ScalarFunctionTest.cc:255-291)
 };
 
@@ -550,17 +559,34 @@ __global__ void __launch_bounds__(128) project_kernel_a(const double* __restrict
                                                           [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
 }
 
+// B1: eigenvalues of T (register-resident QL, Detail/Projection.hh proj_eigenvalues); few registers, high occupancy
+template <int K>
+__global__ void __launch_bounds__(128) project_kernel_b1(int64_t n, int64_t stride, ProjScratch sc)
+{
+    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= n) return;
+    if (sc.codes[el] == TinyAD::detail::PROJ_DOMINANT) return;
+    double* rp = sc.R + el;
+    const int code = TinyAD::detail::proj_eigenvalues<K>([&](int i) { return rp[(int64_t)i * stride]; },
+                                                         [&](int i, double v) { rp[(int64_t)i * stride] = v; });
+    if (code == TinyAD::detail::PROJ_FALLBACK) sc.codes[el] = code;
+}
+
+// B2: selection + inverse iteration
 template <int K, int MINB>
 __global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc)
 {
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
-    if (sc.codes[el] == TinyAD::detail::PROJ_DOMINANT) return;
-    const double* rp = sc.R + el;
+    int code = sc.codes[el];
+    if (code == TinyAD::detail::PROJ_DOMINANT) return;
+    double* rp = sc.R + el;
     double* wp = sc.W + el;
-    const int code = TinyAD::detail::proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; },
-                                                            [&](int i, double v) { wp[(int64_t)i * stride] = v; },
-                                                            [&](int i) { return wp[(int64_t)i * stride]; }, eps);
+    if (code != TinyAD::detail::PROJ_FALLBACK)
+        code = TinyAD::detail::proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; },
+                                                      [&](int i, double v) { rp[(int64_t)i * stride] = v; },
+                                                      [&](int i, double v) { wp[(int64_t)i * stride] = v; },
+                                                      [&](int i) { return wp[(int64_t)i * stride]; }, eps);
     sc.codes[el] = code;
     if (counts) atomicAdd(&counts[0], 1ull);
     if (code == TinyAD::detail::PROJ_REBUILT && counts) atomicAdd(&counts[1], 1ull);
@@ -595,7 +621,7 @@ size_t project_scratch_doubles(int64_t stride)
 // doubles, scratch_i: stride int32 + n int64 (see project_scratch_bytes).
 template <int K>
 int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, int32_t* codes,
-                   int64_t* list, bool full_only, ProjScratch* fuse_out, cudaStream_t st)
+                   int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st)
 {
     using L = TinyAD::detail::ProjLayout<K>;
     constexpr size_t smem = (size_t)ProjSmem<K>::doubles_per_warp * sizeof(double);
@@ -617,14 +643,25 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         sc.list = list;
         const unsigned g = (unsigned)((n + 127) / 128);
         project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+        project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
         static const int occ = getenv("TAD_PROJ_B_OCC") ? atoi(getenv("TAD_PROJ_B_OCC")) : 3;  // tuning knob: min blocks per SM
         if (occ <= 3) project_kernel_b<K, 3><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         else if (occ <= 4) project_kernel_b<K, 4><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         else if (occ <= 6) project_kernel_b<K, 6><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         else project_kernel_b<K, 8><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
-        project_kernel_list<K><<<kListBlocks, kListThreads, 0, st>>>(hess, stride, eps, counts, list,
-                                                                     scratch_d + (size_t)(L::nR + L::nW) * stride);
+        double* work = scratch_d + (size_t)(L::nR + L::nW) * stride;
+        if (fuse_out && side && side->stream)
+        {
+            // fused path: on the side stream, next to the phase C / assembly kernel (which skips the listed elements;
+            // the caller assembles them after ev_list)
+            if (cudaEventRecord(side->ev_b, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->ev_b, 0) != cudaSuccess)
+                return fail(TAD_CUDA_ERROR, "projection side stream");
+            project_kernel_list<K><<<kListBlocks, kListThreads, 0, side->stream>>>(hess, stride, eps, counts, list, work);
+            if (cudaEventRecord(side->ev_list, side->stream) != cudaSuccess) return fail(TAD_CUDA_ERROR, "projection side stream");
+        }
+        else
+            project_kernel_list<K><<<kListBlocks, kListThreads, 0, st>>>(hess, stride, eps, counts, list, work);
         if (fuse_out) *fuse_out = sc;  // phase C is fused with the assembly by the caller
         else project_kernel_c<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
     }
@@ -654,25 +691,25 @@ size_t project_scratch_doubles_rt(int k, int64_t stride)
 }
 
 int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d,
-                     int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, cudaStream_t st)
+                     int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st)
 {
     if (n <= 0 || k <= 0) return TAD_OK;
     switch (k)
     {
-    case 1: return launch_project<1>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 2: return launch_project<2>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 3: return launch_project<3>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 4: return launch_project<4>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 5: return launch_project<5>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 6: return launch_project<6>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 7: return launch_project<7>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 8: return launch_project<8>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 9: return launch_project<9>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 10: return launch_project<10>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 12: return launch_project<12>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
-    case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, st);
+    case 1: return launch_project<1>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 2: return launch_project<2>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 3: return launch_project<3>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 4: return launch_project<4>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 5: return launch_project<5>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 6: return launch_project<6>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 7: return launch_project<7>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 8: return launch_project<8>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 9: return launch_project<9>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 10: return launch_project<10>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 12: return launch_project<12>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
     default: return fail(TAD_NOT_SUPPORTED, "Hessian projection is instantiated for k in {1..10,12,15,16,18}");
     }
 }
@@ -842,19 +879,16 @@ __global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __r
 // (low-rank update of H, Detail/Projection.hh proj_apply) and scattered from there, instead of being written back to
 // the staging buffer and read again by the assembly kernel (saves 1.35 KB of HBM traffic per tet and one launch).
 template <int D, int N>
-__global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* __restrict__ hess, int64_t n, int64_t stride, double eps,
-                                                                 ProjScratch sc, const int32_t* __restrict__ rec,
-                                                                 const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
-                                                                 const double* __restrict__ grad, double* __restrict__ g,
-                                                                 double* __restrict__ Hv, int32_t* err)
+__device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __restrict__ hess, int64_t stride, double eps, const ProjScratch& sc,
+                                               const int32_t* __restrict__ rec, const int32_t* __restrict__ blockbase,
+                                               const int32_t* __restrict__ rstride, const double* __restrict__ grad, double* __restrict__ g,
+                                               double* __restrict__ Hv, int32_t* err, const int code)
 {
     constexpr int K = D * N;
     constexpr int H = K * (K + 1) / 2;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
     const double* hp = hess + e;
     double acc[H];
-    if (sc.codes[e] == TinyAD::detail::PROJ_REBUILT)
+    if (code == TinyAD::detail::PROJ_REBUILT)
     {
         const double* rp = sc.R + e;
         const double* wp = sc.W + e;
@@ -903,34 +937,67 @@ __global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* _
     if (!finite) atomicOr(err, ERR_NONFINITE);
 }
 
+// LIST = false: all elements except those handed to the full solver (code PROJ_FALLBACK) when `skip_listed`;
+// LIST = true: the listed elements (their staged Hessian was projected in place by project_kernel_list).
+template <int D, int N, bool LIST>
+__global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* __restrict__ hess, int64_t n, int64_t stride, double eps,
+                                                                 ProjScratch sc, const int32_t* __restrict__ rec,
+                                                                 const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
+                                                                 const double* __restrict__ grad, double* __restrict__ g,
+                                                                 double* __restrict__ Hv, int32_t* err, const unsigned long long* counts,
+                                                                 bool skip_listed)
+{
+    if constexpr (LIST)
+    {
+        const int64_t count = (int64_t)counts[2];
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+            c_assemble_one<D, N>(sc.list[i], hess, stride, eps, sc, rec, blockbase, rstride, grad, g, Hv, err, TinyAD::detail::PROJ_FALLBACK);
+    }
+    else
+    {
+        const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (e >= n) return;
+        const int code = sc.codes[e];
+        if (skip_listed && code == TinyAD::detail::PROJ_FALLBACK) return;
+        c_assemble_one<D, N>(e, hess, stride, eps, sc, rec, blockbase, rstride, grad, g, Hv, err, code);
+    }
+}
+
 template <int D, int N>
 void launch_c_assemble(const Term& t, const double* grad, const double* hess, int64_t n, double eps, ProjScratch sc, double* g, double* Hv,
-                       int32_t* err, cudaStream_t st)
+                       int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
 {
-    project_c_assemble_kernel<D, N><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
-                                                                                 t.rstride.p, grad, g, Hv, err);
+    const bool split = side && side->stream;
+    project_c_assemble_kernel<D, N, false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
+                                                                                        t.rstride.p, grad, g, Hv, err, counts, split);
+    if (split)
+    {
+        cudaStreamWaitEvent(st, side->ev_list, 0);
+        project_c_assemble_kernel<D, N, true><<<8, 128, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p, t.rstride.p, grad,
+                                                                 g, Hv, err, counts, false);
+    }
 }
 
 bool fused_c_assemble_supported(int d, int N) { return d >= 1 && d <= 3 && N >= 1 && N <= 4; }
 
 int c_assemble(int d, const Term& t, const double* grad, const double* hess, int64_t n, double eps, ProjScratch sc, double* g, double* Hv,
-               int32_t* err, cudaStream_t st)
+               int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
 {
     if (n <= 0) return TAD_OK;
     switch (d * 100 + t.N)
     {
-    case 101: launch_c_assemble<1, 1>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 102: launch_c_assemble<1, 2>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 103: launch_c_assemble<1, 3>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 104: launch_c_assemble<1, 4>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 201: launch_c_assemble<2, 1>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 202: launch_c_assemble<2, 2>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 203: launch_c_assemble<2, 3>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 204: launch_c_assemble<2, 4>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 301: launch_c_assemble<3, 1>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 302: launch_c_assemble<3, 2>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 303: launch_c_assemble<3, 3>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
-    case 304: launch_c_assemble<3, 4>(t, grad, hess, n, eps, sc, g, Hv, err, st); break;
+    case 101: launch_c_assemble<1, 1>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 102: launch_c_assemble<1, 2>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 103: launch_c_assemble<1, 3>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 104: launch_c_assemble<1, 4>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 201: launch_c_assemble<2, 1>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 202: launch_c_assemble<2, 2>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 203: launch_c_assemble<2, 3>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 204: launch_c_assemble<2, 4>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 301: launch_c_assemble<3, 1>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 302: launch_c_assemble<3, 2>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 303: launch_c_assemble<3, 3>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+    case 304: launch_c_assemble<3, 4>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
     default: return fail(TAD_NOT_SUPPORTED, "no fused projection/assembly kernel for this (d, N)");
     }
     return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "fused projection/assembly launch failed");
@@ -1539,10 +1606,10 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         ProjScratch fused_sc;
         if (mode == TAD_MODE_SECOND && project)
             TAD_TRY(project_dispatch(t.k, a.hess, t.n, t.stride, eps, f->proj_counts.p, f->proj_scratch.p, f->proj_codes.p, f->proj_list.p,
-                                     f->projection_full != 0, fuse ? &fused_sc : nullptr, st));
+                                     f->projection_full != 0, fuse ? &fused_sc : nullptr, fuse ? &f->proj_side : nullptr, st));
         if (f->timing) cudaEventRecord(f->ev[3], st);
         if (fuse)
-            TAD_TRY(c_assemble(f->d, t, a.grad, a.hess, t.n, eps, fused_sc, g, Hv, f->err.p, st));
+            TAD_TRY(c_assemble(f->d, t, a.grad, a.hess, t.n, eps, fused_sc, g, Hv, f->err.p, f->proj_counts.p, &f->proj_side, st));
         else if (mode >= TAD_MODE_FIRST && !gather)
             TAD_TRY(assemble_atomic(f->d, t, a.grad, mode == TAD_MODE_SECOND ? a.hess : nullptr, t.n, g, Hv, f->err.p, st));
         if (f->timing)
@@ -1705,6 +1772,10 @@ int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector
         return fail(TAD_CUDA_ERROR, "stream / buffer creation failed");
     }
     for (auto& e : f->ev) cudaEventCreate(&e);
+    if (cudaStreamCreateWithFlags(&f->proj_side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f->proj_side.ev_b, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f->proj_side.ev_list, cudaEventDisableTiming) != cudaSuccess)
+        f->proj_side = ProjSide();  // no side stream: the list kernel stays on the main stream
     *out = f;
     return TAD_OK;
 }
@@ -1719,6 +1790,9 @@ void tad_function_destroy(tad_function f)
             if (t.user_free && t.user) t.user_free(t.user);
         f->terms.clear();
         for (auto& e : f->ev) if (e) cudaEventDestroy(e);
+        if (f->proj_side.ev_b) cudaEventDestroy(f->proj_side.ev_b);
+        if (f->proj_side.ev_list) cudaEventDestroy(f->proj_side.ev_list);
+        if (f->proj_side.stream) cudaStreamDestroy(f->proj_side.stream);
         cudaStreamDestroy(f->stream);
     }
     DeviceGuard guard(f->device);
@@ -1959,7 +2033,7 @@ int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double
     TAD_CUDA(list.ensure((size_t)std::max<int64_t>(stride, 1)));
     TAD_CUDA(codes.ensure((size_t)std::max<int64_t>(stride, 1)));
     if (method != 1) TAD_CUDA(scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(k, stride))));
-    TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts, scratch.p, codes.p, list.p, method == 1, nullptr, st));
+    TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts, scratch.p, codes.p, list.p, method == 1, nullptr, nullptr, st));
     unsigned long long h_counts[3] = {0, 0, 0};
     TAD_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     TAD_CUDA(cudaStreamSynchronize(st));  // the scratch buffers above are locals

@@ -59,7 +59,7 @@ enum ProjectCode
 //   R[0..K)            d_i = T(i,i)
 //   R[K..2K-1)         e_i = T(i+1,i)
 //   R[2K-1..3K-3)      tau_k of reflector H_k = I - tau_k v_k v_k^T, k < K-2
-//   R[3K-3..)          v_k(2:) for k = 0..K-3, concatenated (v_k(1) = 1 is implicit); last slot: max |H_ij|
+//   R[3K-3..)          v_k(2:) for k = 0..K-3, concatenated (v_k(1) = 1 is implicit); then max |H_ij|; then the K eigenvalues
 //   W[0] = number of vectors, W[1] = form (0: H + sum, 1: eps I + sum, 2: -H + sum), W[2..2+MAXV) weights,
 //   W[2+MAXV + jv*K + i] = component i of eigenvector jv of T
 template <int K>
@@ -71,7 +71,8 @@ struct ProjLayout
     static constexpr int off_d = 0, off_e = K, off_tau = 2 * K - 1, off_v = off_tau + n_refl;
     static constexpr int n_v = n_refl * (n_refl + 1) / 2;  // sum_{k} (K-k-2)
     static constexpr int off_amax = off_v + n_v;  // max |H_ij| of the element (scale of the accuracy target)
-    static constexpr int nR = off_amax + 1;
+    static constexpr int off_lam = off_amax + 1;  // eigenvalues of T, ascending (written by proj_eigenvalues)
+    static constexpr int nR = off_lam + K;
     static constexpr int off_wgt = 2, off_vec = 2 + MAXV;
     static constexpr int nW = off_vec + MAXV * K;
     // offset of v_k(2 + i), i < K-k-2
@@ -217,80 +218,116 @@ TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, cons
     return PROJ_UNCHANGED;
 }
 
-// Phase B: eigenvalues of T, selection of the eigenvalues that move, their eigenvectors (of T) by inverse iteration.
-// Scalar recurrences on small arrays, written as plain loops: nvcc unrolls the fixed-trip-count ones (LU, solves)
-// so those arrays live in registers, while the QL loops with data-dependent bounds index local memory.  Measured on
-// B200 (1M tets): this form 2.7 ms; everything unrolled by hand 16 ms (14k SASS instructions, instruction-cache
-// bound); nothing unrolled (`#pragma unroll 1`) 8 ms.  load_w re-reads vectors already stored through store_w.
-template <int K, class LoadRFn, class StoreWFn, class LoadWFn>
-TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, LoadWFn&& load_w, const double eps)
+// Phase B1: eigenvalues of T by QL with explicit shifts and no vectors (EISPACK tql1 scheme), stored UNSORTED to
+// R[off_lam..).  Shaped for the GPU, one thread per matrix:
+//   * d / e live in registers and every array index is a compile-time constant: the unreduced block always starts at
+//     position 0, because a converged eigenvalue is written out and the arrays are shifted down by one (zeros shift into e,
+//     so the block end needs no separate bookkeeping);
+//   * ONE run-time loop whose body is a single QL step (one sweep unrolled over its maximal range K-2 .. 0; the rotations at
+//     and beyond the first negligible sub-diagonal entry m are predicated off) followed by the deflation test.  The body
+//     is ~0.5 k instructions, so it stays in the instruction cache (a version unrolled over the eigenvalue index as well
+//     spent 80 % of its time waiting for instruction fetches), and lanes of a warp that need different numbers of steps for
+//     one eigenvalue do not wait for each other: each lane simply continues with its next eigenvalue;
+//   * no divisions or square roots on the slow paths: reciprocal / reciprocal square root by hardware approximation plus
+//     Newton steps (all arguments are in the normal range because T is scaled by 1/|T|_1 first).
+// Deflation criterion: |e_i| <= macheps * max_i(|d_i| + |e_i|), i.e. absolute accuracy macheps |T| -- what the projection
+// needs (the map l -> max(l, eps) is 1-Lipschitz).
+// 32 fixed pseudo-random numbers in (-1, 1) (start vectors of the inverse iteration)
+TINYAD_HD TINYAD_INLINE double start_table(unsigned i)
+{
+    constexpr double t[32] = {0.4387, -0.7112, 0.2918, 0.9534, -0.1276, 0.6641, -0.8823, 0.3359, -0.5467, 0.7785, 0.1193,
+                              -0.9341, 0.5872, -0.2654, 0.8126, -0.4498, 0.0715, 0.6267, -0.7931, 0.3642, -0.1889, 0.9078,
+                              -0.6013, 0.2471, 0.7356, -0.3927, 0.5189, -0.8564, 0.1632, -0.6745, 0.8891, -0.0458};
+    return t[i & 31u];
+}
+
+TINYAD_HD TINYAD_INLINE double rcp_fast(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    if (!(fabs(y) <= 1.7e308)) y = 1.0 / x;  // denormal / zero / non-finite argument: IEEE division
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+
+template <int K, class LoadRFn, class StoreRFn>
+TINYAD_HD inline int proj_eigenvalues(LoadRFn&& load_r, StoreRFn&& store_r)
 {
     using L = ProjLayout<K>;
     constexpr double macheps = 2.220446049250313e-16;
-    double d0[K], e0[K];
-    for (int i = 0; i < K; ++i)
-    {
-        d0[i] = load_r(L::off_d + i);
-        e0[i] = (i + 1 < K) ? load_r(L::off_e + i) : 0.0;
-    }
-
-    // ---- 2. eigenvalues of T: implicit QL without vectors (EISPACK tql1 scheme) ----
-    // T is scaled by 1/|T|_1 first: with entries of O(1) the rotations need no overflow / underflow guards
-    // (a sub-diagonal entry inside the active block is > eps * tst1, so p^2 + e^2 >= ~1e-32).
-    double lam[K];
+    double lam[K], ee[K];
     double onenrm = 0.0;
-    for (int i = 0; i < K; ++i)
-    {
-        const double rowsum = fabs(d0[i]) + fabs(e0[i]) + (i > 0 ? fabs(e0[i - 1]) : 0.0);
+    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+        constexpr int i = decltype(ic)::value;
+        lam[i] = load_r(L::off_d + i);
+        if constexpr (i + 1 < K) ee[i] = load_r(L::off_e + i);
+        else ee[i] = 0.0;
+    });
+    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+        constexpr int i = decltype(ic)::value;
+        double rowsum = fabs(lam[i]) + fabs(ee[i]);
+        if constexpr (i > 0) rowsum += fabs(ee[i - 1]);
         onenrm = fmax(onenrm, rowsum);
-    }
+    });
     if (!(onenrm == onenrm) || onenrm > 1e300) return PROJ_FALLBACK;  // NaN / Inf input: the caller's finite check reports it
+    const double inv_nrm = onenrm > 0.0 ? 1.0 / onenrm : 0.0;
+    double tn = 0.0;
+    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+        constexpr int i = decltype(ic)::value;
+        lam[i] *= inv_nrm;
+        ee[i] *= inv_nrm;
+        tn = fmax(tn, fabs(lam[i]) + fabs(ee[i]));
+    });
+    const double thr = macheps * tn;
+    double f = 0.0;
+    int done = 0, steps = 0;
+    while (done < K)
     {
-        const double inv_nrm = onenrm > 0.0 ? 1.0 / onenrm : 0.0;
-        double ee[K];
-        for (int i = 0; i < K; ++i)
+        // m = first index with a negligible sub-diagonal entry (e[K-1] = 0 always)
+        int m = K - 1;
+        static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = K - 2 - decltype(ic)::value;  // K-2 down to 0: the smallest index wins
+            if (fabs(ee[i]) <= thr) m = i;
+        });
+        if constexpr (K > 1)
         {
-            lam[i] = d0[i] * inv_nrm;
-            ee[i] = e0[i] * inv_nrm;
-        }
-        double f = 0.0, tst1 = 0.0;
-        for (int l = 0; l < K; ++l)
-        {
-            tst1 = fmax(tst1, fabs(lam[l]) + fabs(ee[l]));
-            int m = l;
-            while (m < K - 1)
+            if (m > 0)
             {
-                if (fabs(ee[m]) <= macheps * tst1) break;
-                ++m;
-            }
-            if (m > l)
-            {
-                int iter = 0;
-                double el_abs;
-                do
-                {
-                    ++iter;
-                    const double e_l = ee[l];
-                    double g = lam[l];
-                    double p = (lam[l + 1] - g) / (2.0 * e_l);
-                    double r = (fabs(p) < 1e150) ? sqrt(fma(p, p, 1.0)) : fabs(p);
-                    if (p < 0) r = -r;
-                    const double dl = e_l / (p + r);
-                    const double dl1 = e_l * (p + r);
-                    lam[l] = dl;
-                    lam[l + 1] = dl1;
-                    double h = g - dl;
-                    for (int i = l + 2; i < K; ++i) lam[i] -= h;
-                    f += h;
-                    p = lam[m];
-                    double c = 1.0, c2 = 1.0, c3 = 1.0;
-                    const double el1 = ee[l + 1];
-                    double s = 0.0, s2 = 0.0;
-                    for (int i = m - 1; i >= l; --i)
+                // one QL step on the block [0, m], shift from the leading 2 x 2 block
+                if (++steps > 40 * K) return PROJ_FALLBACK;
+                const double e_l = ee[0];
+                double g = lam[0];
+                double p = (lam[1] - g) * rcp_fast(2.0 * e_l);
+                const double pp1 = fma(p, p, 1.0);
+                double r = pp1 * rsqrt_fast(pp1);
+                if (p < 0) r = -r;
+                const double q = p + r;  // |q| >= 1
+                const double qinv = rcp_fast(q);
+                const double dl = e_l * qinv;
+                lam[0] = dl;
+                lam[1] = e_l * q;
+                double h = g - dl;
+                static_for<(K > 2 ? K - 2 : 0)>([&](auto ic) TINYAD_LAMBDA_INLINE { lam[2 + decltype(ic)::value] -= h; });
+                f += h;
+                p = lam[K - 1];
+                static_for<(K > 2 ? K - 2 : 0)>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = 1 + decltype(ic)::value;  // 1 .. K-2
+                    if (m == i) p = lam[i];
+                });
+                double c = 1.0, c3 = 1.0;  // c3: c after rotation 2 (1 if it does not run)
+                const double el1 = ee[1];
+                double s = 0.0, s2 = 0.0;  // s2: s after rotation 1 (0 if it does not run)
+                static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = K - 2 - decltype(ic)::value;  // K-2 down to 0
+                    if (i < m)
                     {
-                        c3 = c2;
-                        c2 = c;
-                        s2 = s;
                         const double ei = ee[i], di = lam[i];
                         g = c * ei;
                         h = c * p;
@@ -301,37 +338,87 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
                         c = p * rinv;
                         p = c * di - s * g;
                         lam[i + 1] = h + s * (c * g + s * di);
+                        if constexpr (i == 2) c3 = c;
+                        if constexpr (i == 1) s2 = s;
                     }
-                    p = -s * s2 * c3 * el1 * e_l / dl1;
-                    ee[l] = s * p;
-                    lam[l] = c * p;
-                    el_abs = fabs(s * p);
-                } while (el_abs > macheps * tst1 && iter < 60);
-                if (iter >= 60) return PROJ_FALLBACK;
+                });
+                p = -s * s2 * c3 * el1 * qinv;  // = -s s2 c3 el1 e_l / lam[1]
+                ee[0] = s * p;
+                lam[0] = c * p;
             }
-            lam[l] = lam[l] + f;
-            ee[l] = 0.0;
         }
-        for (int i = 0; i < K; ++i) lam[i] *= onenrm;
-    }
-    // ascending order (insertion sort, K is tiny)
-    for (int i = 1; i < K; ++i)
-    {
-        const double v = lam[i];
-        int j = i - 1;
-        while (j >= 0 && lam[j] > v)
+        if (fabs(ee[0]) <= thr)
         {
-            lam[j + 1] = lam[j];
-            --j;
+            // deflate: eigenvalue found; shift the arrays so that the remaining block starts at 0 again
+            store_r(L::off_lam + done, (lam[0] + f) * onenrm);
+            ++done;
+            static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                constexpr int i = decltype(ic)::value;
+                lam[i] = lam[i + 1];
+                ee[i] = ee[i + 1];
+            });
+            ee[K - 1] = 0.0;
         }
-        lam[j + 1] = v;
+    }
+    return PROJ_UNCHANGED;
+}
+
+// Phase B2: selection of the eigenvalues that move, their eigenvectors (of T) by inverse iteration.
+// Scalar recurrences on small arrays, written as plain loops: nvcc unrolls the fixed-trip-count ones (LU, solves)
+// so those arrays live in registers.  load_w re-reads vectors already stored through store_w; the eigenvalues are read
+// back from R at run-time indices.
+template <int K, class LoadRFn, class StoreLamFn, class StoreWFn, class LoadWFn>
+TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_lam, StoreWFn&& store_w, LoadWFn&& load_w, const double eps)
+{
+    using L = ProjLayout<K>;
+    constexpr double macheps = 2.220446049250313e-16;
+    double d0[K], e0[K];
+    double onenrm = 0.0;
+    for (int i = 0; i < K; ++i)
+    {
+        d0[i] = load_r(L::off_d + i);
+        e0[i] = (i + 1 < K) ? load_r(L::off_e + i) : 0.0;
+    }
+    for (int i = 0; i < K; ++i)
+    {
+        const double rowsum = fabs(d0[i]) + fabs(e0[i]) + (i > 0 ? fabs(e0[i - 1]) : 0.0);
+        onenrm = fmax(onenrm, rowsum);
+    }
+    double emax = 0.0, dmax = 0.0;
+    for (int i = 0; i < K; ++i)
+    {
+        emax = fmax(emax, fabs(e0[i]));
+        dmax = fmax(dmax, fabs(d0[i]));
+    }
+    auto lam_at = [&](int i) { return load_r(L::off_lam + i); };
+    {
+        // B1 leaves the eigenvalues in the order of convergence: sort ascending (odd-even transposition network on
+        // registers), check them, write them back for the run-time indexed reads below
+        double lam[K];
+        double chk = 0.0;
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            lam[i] = load_r(L::off_lam + i);
+            chk += fabs(lam[i]);
+        });
+        if (!(chk <= 1.7e308)) return PROJ_FALLBACK;  // NaN / Inf
+        static_for<K>([&](auto rc) TINYAD_LAMBDA_INLINE {
+            constexpr int round = decltype(rc)::value;
+            static_for<(K - (round & 1)) / 2>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                constexpr int i = (round & 1) + 2 * decltype(ic)::value;
+                const double lo = fmin(lam[i], lam[i + 1]), hi = fmax(lam[i], lam[i + 1]);
+                lam[i] = lo;
+                lam[i + 1] = hi;
+            });
+        });
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; store_lam(L::off_lam + i, lam[i]); });
     }
 
     // ---- 3. which eigenvalues move (HessianProjection.hh:71-91) ----
     const bool abs_mode = eps < 0.0;
     const double thresh = abs_mode ? 0.0 : eps;
-    int r = 0;
-    while (r < K && lam[r] < thresh) ++r;
+    int r = 0;  // the eigenvalues are ascending
+    for (int i = 0; i < K; ++i) r += (lam_at(i) < thresh) ? 1 : 0;
     if (r == 0) return PROJ_UNCHANGED;  // early-out 2 (:94-95)
     // form A: H + sum_{j<r} delta_j v_j v_j^T with delta_j = target_j - l_j           (r <= K/2)
     // form B: base + sum_{j>=r} gamma_j v_j v_j^T, base = eps I (clamp) or -H (abs)     (otherwise: fewer vectors)
@@ -344,14 +431,13 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
     const double res_limit = 2e-12 * amax;
     double xjm = 0.0;
     int gpind = j_begin;
-    uint32_t seed = 0x9e3779b9u;
     double la[K], lb[K], lc[K], ld[K];  // LU factors of T - x_j I (kept across the vectors of a cluster, see below)
     uint32_t pivmask = 0;
     double tol = 0.0, a_last = 0.0;
     for (int j = j_begin; j < j_end; ++j)
     {
         const int jv = j - j_begin;
-        const double lj = lam[j];
+        const double lj = lam_at(j);
         double xj = lj;
         if (j > j_begin)
         {
@@ -372,43 +458,40 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
                 lc[i] = e0[i];
                 ld[i] = 0.0;
             }
-            tol = 0.0;
+            // Branch-free elimination step: "keep" = no row interchange.  One reciprocal per step (hardware approximation
+            // + Newton) instead of a division in each of two divergent branches.
             double scale1 = fabs(la[0]) + (K > 1 ? fabs(lb[0]) : 0.0);
             for (int k = 0; k < K - 1; ++k)
             {
                 double scale2 = fabs(lc[k]) + fabs(la[k + 1]);
                 if (k < K - 2) scale2 += fabs(lb[k + 1]);
-                if (lc[k] == 0.0) scale1 = scale2;
-                else if (la[k] != 0.0 && fabs(lc[k]) * scale1 <= fabs(la[k]) * scale2)
+                const double ak = la[k], ck = lc[k], bk = lb[k], a1 = la[k + 1];
+                const bool czero = ck == 0.0;
+                const bool keep = czero || (ak != 0.0 && fabs(ck) * scale1 <= fabs(ak) * scale2);
+                const double mult = czero ? 0.0 : (keep ? ck : ak) * rcp_fast(keep ? ak : ck);
+                la[k + 1] = fma(-mult, keep ? bk : a1, keep ? a1 : bk);
+                la[k] = keep ? ak : ck;
+                lb[k] = keep ? bk : a1;
+                lc[k] = mult;
+                if (k < K - 2)
                 {
-                    scale1 = scale2;
-                    lc[k] = lc[k] / la[k];
-                    la[k + 1] -= lc[k] * lb[k];
+                    const double b1 = lb[k + 1];
+                    ld[k] = keep ? 0.0 : b1;
+                    lb[k + 1] = keep ? b1 : -mult * b1;
                 }
-                else
-                {
-                    pivmask |= (1u << k);
-                    const double mult = la[k] / lc[k];
-                    la[k] = lc[k];
-                    const double temp = la[k + 1];
-                    la[k + 1] = lb[k] - mult * temp;
-                    if (k < K - 2)
-                    {
-                        ld[k] = lb[k + 1];
-                        lb[k + 1] = -mult * ld[k];
-                    }
-                    lb[k] = temp;
-                    lc[k] = mult;
-                }
+                if (keep) scale1 = scale2;
+                else pivmask |= (1u << k);
             }
-            for (int i = 0; i < K; ++i) tol = fmax(tol, fmax(fabs(la[i]), fmax(fabs(lb[i]), fabs(ld[i]))));
-            tol = (tol == 0.0) ? macheps : tol * macheps;
+            // dlagtf: tol = macheps * max(|a_i|, |b_i|, |d_i|) over the factors.  Their entries are bounded by twice the
+            // largest entry of T - xj I (partial pivoting on a tridiagonal matrix), for which max|e| and max|d| + |xj| are
+            // upper bounds; a tolerance that is a small factor larger only perturbs a negligible pivot a little more.
+            tol = macheps * fmax(emax, dmax + fabs(xj));
             a_last = fabs(la[K - 1]);
             for (int i = 0; i < K; ++i)
             {
                 double ak = la[i];
                 if (fabs(ak) < tol) ak = (ak < 0.0) ? -tol : tol;
-                la[i] = 1.0 / ak;
+                la[i] = rcp_fast(ak);
             }
         }
 
@@ -417,15 +500,13 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
         if (!form_b) wj = abs_mode ? -2.0 * lj : eps - lj;
         else wj = abs_mode ? 2.0 * lj : lj - eps;
         double gap = 1e300;
-        if (!form_b) { if (j_end < K) gap = lam[j_end] - lj; }
-        else if (j_begin > 0) gap = lj - lam[j_begin - 1];
+        if (!form_b) { if (j_end < K) gap = lam_at(j_end) - lj; }
+        else if (j_begin > 0) gap = lj - lam_at(j_begin - 1);
 
+        // deterministic start vector with entries in (-1, 1): a fixed table of pseudo-random numbers, read at an offset that
+        // depends on the vector (dstein draws new random numbers for every vector)
         double x[K];
-        for (int i = 0; i < K; ++i)
-        {
-            seed = seed * 1664525u + 1013904223u;
-            x[i] = ((double)(seed >> 8) * (1.0 / 8388608.0)) - 1.0;  // deterministic start vector in (-1, 1)
-        }
+        for (int i = 0; i < K; ++i) x[i] = start_table((unsigned)(i + 5 * jv));
         if (j > j_begin && fabs(xj - xjm) > ortol) gpind = j;
         // With the eigenvalue known to working precision one solve from a random start already gives a residual of a
         // few eps |T| (more solves do not improve it; for the later members of a cluster they make it worse, because
@@ -443,12 +524,11 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
         while (its < 5)
         {
             ++its;
-            // orthogonalise the right-hand side against the vectors computed so far (all of them, not only the cluster:
-            // the other selected eigenvectors are orthogonal anyway, and removing them confines what is left of the
-            // error to the unselected subspace, see the acceptance test) before the solve: otherwise
-            // the solve amplifies those directions as much as the wanted one and the remainder after removing them
-            // is noisy (residual ~100 eps |T| for the third vector of a triple eigenvalue) ...
-            for (int i = j_begin; i < j; ++i)
+            // orthogonalise the right-hand side against the vectors of the cluster computed so far before the solve:
+            // otherwise the solve amplifies those directions as much as the wanted one and the remainder after removing
+            // them is noisy (residual ~100 eps |T| for the third vector of a triple eigenvalue).  (Vectors outside the
+            // cluster are amplified >= 1e12 times less than the wanted one; they are removed after the solve only.) ...
+            for (int i = gpind; i < j; ++i)
             {
                 const int base = L::off_vec + (i - j_begin) * K;
                 double dot = 0.0;
@@ -478,7 +558,9 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreWFn&& store_w, L
                 if (k <= K - 3) temp -= ld[k] * x[k + 2];
                 x[k] = temp * la[k];
             }
-            // ... and once more after it (modified Gram-Schmidt)
+            // ... and against all selected vectors after it (modified Gram-Schmidt; not only the cluster: the other selected
+            // eigenvectors are orthogonal anyway, and removing them confines what is left of the error to the
+            // unselected subspace, see the acceptance test)
             for (int i = j_begin; i < j; ++i)
             {
                 const int base = L::off_vec + (i - j_begin) * K;
@@ -590,7 +672,10 @@ TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const doubl
     double R[L::nR > 0 ? L::nR : 1], Wb[L::nW];
     int code = proj_tridiagonalize<K>(load, [&](int i, double v) { R[i] = v; }, eps);
     if (code == PROJ_DOMINANT) return code;
-    code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i, double v) { Wb[i] = v; }, [&](int i) { return Wb[i]; }, eps);
+    code = proj_eigenvalues<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; });
+    if (code == PROJ_FALLBACK) return code;
+    code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; }, [&](int i, double v) { Wb[i] = v; },
+                                  [&](int i) { return Wb[i]; }, eps);
     if (code != PROJ_REBUILT) return code;
     proj_apply<K>([&](int i) { return R[i]; }, [&](int i) { return Wb[i]; }, load, store, eps);
     return PROJ_REBUILT;
