@@ -37,9 +37,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c1", "small"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c1", "small", "c3", "c3small"],
                     help="c2: Kuhn cube n=55 (998,250 tets) per GPU [default]; c5: n=119 (10.1M tets) split over the GPUs; "
-                         "c1: 512^2 triangle grid; small: n=16 smoke size")
+                         "c1: 512^2 triangle grid; small: n=16 smoke size; c3: projected-Newton loop on the C2 mesh, timed per phase "
+                         "(--steps = Newton iterations, default 20)")
+    ap.add_argument("--newton-tol", type=float, default=1e-6, help="c3: relative residual of the PCG solve (inexact Newton)")
     ap.add_argument("--assembly", default="atomic", choices=["atomic", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=22, help="cube edge of the CPU-baseline sample (22 -> 63,888 tets)")
@@ -180,10 +182,62 @@ def cpu_baseline_step(n, threads):
     return nt, time.perf_counter() - t0
 
 
+def run_newton(args):
+    """BASELINE.json configs[2]: projected-Newton loop (assembly + linear solve + line search) on the 1M-tet deformation,
+    timed per phase.  The solve is the PCG stand-in of tad_newton_direction (no cuDSS in this image) and is reported apart
+    from the assembly.  Loop shape: tests/NewtonTest.cc:68-75 of the reference."""
+    import torch
+    import tinyad_b200 as tad
+    from tinyad_b200 import meshes
+    n = 55 if args.workload == "c3" else 12
+    V, T = meshes.kuhn_cube(n)
+    x0 = meshes.deform(V, 1.0 / n, seed=0).reshape(-1)
+    pins = np.array([[0], [n], [len(V) - 1], [len(V) - 1 - n]], dtype=np.int32)
+    fn = tad.Function(3, len(V))
+    fn.add_term(tad.SYMDIRICHLET3D, T, meshes.tet_rest_data(V, T))
+    fn.add_term(tad.PENALTY3D, pins, V[pins[:, 0]])
+    nnz = fn.nnz
+    x = torch.from_numpy(x0.copy()).cuda()
+    g = torch.empty(fn.n_vars, dtype=torch.float64, device="cuda")
+    H = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    d = torch.empty_like(g)
+    xn = torch.empty_like(g)
+    iters = args.steps
+    for _ in range(max(1, args.warmup)):   # warm-up (same x)
+        fn.eval_with_hessian_proj(x, g, H)
+    torch.cuda.synchronize()
+    t_asm = t_sol = t_ls = 0.0
+    log = []
+    for it in range(iters):
+        t0 = time.perf_counter()
+        f = fn.eval_with_hessian_proj(x, g, H)
+        t1 = time.perf_counter()
+        cg_iters, rel = fn.newton_direction(g, H, d, w_identity=1e-9, rel_tol=args.newton_tol, max_iters=20000)
+        dec = fn.newton_decrement(d, g)
+        t2 = time.perf_counter()
+        f_new, step, n_evals = fn.line_search(x, d, f, g, xn)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        t_asm += t1 - t0; t_sol += t2 - t1; t_ls += t3 - t2
+        log.append({"f": f, "decrement": dec, "cg_iters": cg_iters, "step": step, "ls_evals": n_evals})
+        x, xn = xn, x
+    total = t_asm + t_sol + t_ls
+    line = {"metric": "projected-Newton iteration time (1M-tet deformation), per phase", "value": total / iters * 1e3, "unit": "ms/iteration",
+            "n_gpus": 1, "steps": iters, "warmup": args.warmup, "higher_is_better": False, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3: {iters} projected-Newton iterations, Kuhn cube n={n} ({len(T):,} tets), 4 pinned vertices, eps=1e-9, "
+                                   f"w_identity=1e-9, PCG rel_tol={args.newton_tol}", "nnz": int(nnz)},
+            "phases_ms_per_iteration": {"assembly_eval_with_hessian_proj": t_asm / iters * 1e3, "solve_pcg_standin_for_cudss": t_sol / iters * 1e3,
+                                        "line_search": t_ls / iters * 1e3},
+            "f_first": log[0]["f"], "f_last": log[-1]["f"], "iterations": log}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload in ("c3", "c3small"):
+        return run_newton(args)
 
     import torch
     import torch.distributed as dist

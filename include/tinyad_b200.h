@@ -33,7 +33,8 @@ typedef enum tad_status
     TAD_TOO_MANY_VARIABLES = 4,    /* "Too many variables requested via element.variables(...)" (Element.hh:237-238) */
     TAD_INDEX_OUT_OF_RANGE = 5,    /* variable handle outside [0, n_handles) (Element.hh:159-170) */
     TAD_NOT_SUPPORTED = 6,
-    TAD_OUT_OF_MEMORY = 7
+    TAD_OUT_OF_MEMORY = 7,
+    TAD_SOLVER_FAILED = 8          /* "Linear solve failed." (Utils/NewtonDirection.hh:43-44) */
 } tad_status;
 
 /* What an element kernel launch computes. */
@@ -83,6 +84,7 @@ typedef struct tad_function_s* tad_function;
 #define TAD_ASSEMBLY_GATHER 1
 
 const char* tad_last_error(void);
+void tad_set_last_error(const char* msg); /* used by the library's own translation units */
 int tad_device_count(int* count);
 
 /* scalar_function<d>(range(n_handles)) / vector_function<d>(...)   ScalarFunctionImpl.hh:418-442, VectorFunctionImpl.hh:303-323 */
@@ -101,6 +103,7 @@ int tad_function_add_term(tad_function f, int valence, int outputs_per_element, 
  * blocks other ranks will send to this rank.  They get explicit zero slots; the pattern is rebuilt on next use. */
 int tad_function_add_pattern_blocks(tad_function f, int64_t n_blocks, const int64_t* vi_host, const int64_t* vj_host);
 
+int tad_function_variable_dimension(tad_function f);
 int64_t tad_function_n_vars(tad_function f);
 int64_t tad_function_n_elements(tad_function f);
 int64_t tad_function_n_outputs(tad_function f); /* vector functions: number of residuals */
@@ -163,6 +166,25 @@ int tad_function_projection_stats(tad_function f, int64_t* stats2);
  * [0] element kernels, [1] projection, [2] assembly, [3] total. */
 int tad_function_last_timings(tad_function f, float* ms4);
 int tad_function_set_timing(tad_function f, int enabled);
+
+/* ---- callers of the hot path: projected-Newton utilities, all vectors device-resident ----
+ * newton_direction   Utils/NewtonDirection.hh:25-48   d = -(H_proj + w_identity I)^-1 g on the function's fixed CSR pattern.
+ *   The reference factorises with Eigen::SimplicialLDLT (Utils/LinearSolver.hh:12-19; BASELINE.json names cuDSS on the GPU);
+ *   no sparse direct solver exists in this image, so the solve is a block-Jacobi preconditioned conjugate gradient
+ *   (tad_pcg_solve) -- a labelled stand-in, timed separately from the assembly.  rel_tol <= 0 -> 1e-10, max_iters <= 0 -> 10000.
+ *   TAD_SOLVER_FAILED ("Linear solve failed.") if H is not positive definite, d is not finite or the tolerance is not reached.
+ * newton_decrement   Utils/NewtonDecrement.hh:20-26    -0.5 d.g
+ * line_search        Utils/LineSearch.hh:26-65         x_new = x0 + s d with the first s in {s_max, s_max*shrink, ...} (and 1.0 when
+ *   s_max > 1) that satisfies the Armijo condition f(x_new) <= f0 + armijo_const * s * d.g (:14-24); each trial is one value-only
+ *   tad_eval; returns x0 (step 0) after max_iters failures like the reference; NaN objective -> TAD_INVALID_ARGUMENT (:53). */
+int tad_pcg_solve(int64_t n, int block_dim, const int32_t* outer_dev, const int32_t* inner_dev, const double* values_dev, double w_identity,
+                  const double* b_dev, double b_scale, double* x_dev, double rel_tol, int max_iters, int* iters_out, double* rel_residual_out,
+                  void* stream);
+int tad_newton_direction(tad_function f, const double* g_dev, const double* H_values_dev, double w_identity, double rel_tol, int max_iters,
+                         double* d_dev, int* iters_out, double* rel_residual_out);
+int tad_newton_decrement(tad_function f, const double* d_dev, const double* g_dev, double* out_host);
+int tad_line_search(tad_function f, const double* x0_dev, const double* d_dev, double f0, const double* g_dev, double s_max, double shrink,
+                    int max_iters, double armijo_const, double* x_new_dev, double* f_new_host, double* step_host, int* n_evals);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 TAD_OK = 0
 STATUS_NAMES = {0: "TAD_OK", 1: "TAD_INVALID_ARGUMENT", 2: "TAD_NONFINITE_DERIVATIVE", 3: "TAD_CUDA_ERROR",
-                4: "TAD_TOO_MANY_VARIABLES", 5: "TAD_INDEX_OUT_OF_RANGE", 6: "TAD_NOT_SUPPORTED", 7: "TAD_OUT_OF_MEMORY"}
+                4: "TAD_TOO_MANY_VARIABLES", 5: "TAD_INDEX_OUT_OF_RANGE", 6: "TAD_NOT_SUPPORTED", 7: "TAD_OUT_OF_MEMORY",
+                8: "TAD_SOLVER_FAILED"}
 ASSEMBLY_ATOMIC, ASSEMBLY_GATHER = 0, 1
 OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION = 1, 2, 3
 
@@ -37,6 +38,8 @@ ABI_SYMBOLS = [
     "tad_eval_with_gradient_host", "tad_eval_with_derivatives_host", "tad_veval", "tad_veval_with_jacobian",
     "tad_veval_sum_of_squares", "tad_veval_sum_of_squares_with_derivatives", "tad_project_batch",
     "tad_function_projection_stats", "tad_function_last_timings", "tad_function_set_timing", "tad_bench_fp64_peak",
+    "tad_set_last_error", "tad_function_variable_dimension",
+    "tad_pcg_solve", "tad_newton_direction", "tad_newton_decrement", "tad_line_search",
 ]
 
 _rt = None
@@ -89,6 +92,11 @@ def runtime():
         L.tad_function_set_timing.argtypes = [vp, ctypes.c_int]
         L.tad_device_count.argtypes = [vp]
         L.tad_bench_fp64_peak.argtypes = [ctypes.c_int, dbl, vp]
+        L.tad_function_variable_dimension.argtypes = [vp]
+        L.tad_pcg_solve.argtypes = [i64, ctypes.c_int, vp, vp, vp, dbl, vp, dbl, vp, dbl, ctypes.c_int, vp, vp, vp]
+        L.tad_newton_direction.argtypes = [vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
+        L.tad_newton_decrement.argtypes = [vp, vp, vp, vp]
+        L.tad_line_search.argtypes = [vp, vp, vp, dbl, vp, dbl, dbl, ctypes.c_int, dbl, vp, vp, vp, vp]
         _rt = L
     return _rt
 
@@ -265,6 +273,26 @@ class Function:
 
     def eval_with_hessian_proj(self, x_dev, g_dev, H_dev, eps=1e-9):
         return self.eval_with_derivatives(x_dev, g_dev, H_dev, True, eps)
+
+    # ---- projected-Newton utilities (Utils/NewtonDirection.hh, NewtonDecrement.hh, LineSearch.hh), device pointers ----
+    def newton_direction(self, g_dev, H_dev, d_dev, w_identity=0.0, rel_tol=1e-10, max_iters=10000):
+        """d = -(H + w_identity I)^-1 g by block-Jacobi PCG on the fixed pattern.  Returns (iterations, relative residual)."""
+        it, rel = ctypes.c_int(), ctypes.c_double()
+        _check(runtime().tad_newton_direction(self.h, _ptr(g_dev), _ptr(H_dev), w_identity, rel_tol, max_iters, _ptr(d_dev),
+                                              ctypes.byref(it), ctypes.byref(rel)))
+        return it.value, rel.value
+
+    def newton_decrement(self, d_dev, g_dev):
+        out = ctypes.c_double()
+        _check(runtime().tad_newton_decrement(self.h, _ptr(d_dev), _ptr(g_dev), ctypes.byref(out)))
+        return out.value
+
+    def line_search(self, x0_dev, d_dev, f0, g_dev, x_new_dev, s_max=1.0, shrink=0.8, max_iters=64, armijo_const=1e-4):
+        """Backtracking Armijo line search; writes x_new_dev, returns (f_new, step, n_evals); step 0 = no improvement found."""
+        f_new, step, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        _check(runtime().tad_line_search(self.h, _ptr(x0_dev), _ptr(d_dev), f0, _ptr(g_dev), s_max, shrink, max_iters, armijo_const,
+                                         _ptr(x_new_dev), ctypes.byref(f_new), ctypes.byref(step), ctypes.byref(n)))
+        return f_new.value, step.value, n.value
 
     # ---- vector functions (device pointers) ----
     def veval(self, x_dev, r_dev):

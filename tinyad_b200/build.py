@@ -54,10 +54,21 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     ptxas = ["-Xptxas", "-v"] if verbose else []
     jobs = []
-    src = os.path.join(HERE, "csrc", "runtime.cu")
-    rebuild_runtime = force or _newer(RUNTIME_SO, [src] + hdrs[:1] + [os.path.join(HERE, "include", "TinyAD", "Detail", "HessLayout.hh")])
-    if rebuild_runtime:
-        jobs.append([NVCC] + FLAGS + ["-shared", "-o", RUNTIME_SO, src])
+    inc = os.path.join(HERE, "include", "TinyAD")
+    api = hdrs[0]
+    # runtime library: one object per translation unit, compiled in parallel, linked into libtinyad_b200.so
+    rt_units = [("runtime.o", "runtime.cu", [os.path.join(inc, "Scalar.hh"), os.path.join(inc, "Detail", "HessLayout.hh"),
+                                             os.path.join(inc, "Detail", "Projection.hh")]),
+                ("newton.o", "newton.cu", [])]
+    rt_objs, relink_runtime = [], not os.path.exists(RUNTIME_SO)
+    for obj, cu, deps in rt_units:
+        o = os.path.join(OBJ_DIR, obj)
+        rt_objs.append(o)
+        src = os.path.join(HERE, "csrc", cu)
+        if force or _newer(o, [src, api, os.path.abspath(__file__)] + deps):
+            jobs.append([NVCC] + FLAGS + ["-c", "-o", o, src])
+            relink_runtime = True
+    hdrs = [h for h in hdrs if not h.endswith("Projection.hh")]   # only the runtime includes the projection routines
     objs = []
     units = [("energies.o", "energies.cu", [])] + [(f"energies_tet_part{p}.o", "energies_tet_part.cu", [f"-DTADX_PART={p}"]) for p in range(TET_PARTS)]
     for obj, cu, defs in units:
@@ -68,6 +79,8 @@ def build(force=False, verbose=False):
             jobs.append([NVCC] + FLAGS + ptxas + [f"-DTADX_TET_PARTS={TET_PARTS}"] + defs + ["-c", "-o", o, src])
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
         list(ex.map(lambda c: _run(c, verbose), jobs))
+    if relink_runtime:
+        _run([NVCC] + FLAGS + ["-shared", "-o", RUNTIME_SO] + rt_objs, verbose)
     if jobs or not os.path.exists(ENERGIES_SO):
         _run([NVCC] + FLAGS + ["-shared", "-o", ENERGIES_SO] + objs + ["-L", HERE, "-ltinyad_b200", "-Xlinker", "-rpath=$ORIGIN"], verbose)
     return RUNTIME_SO, ENERGIES_SO

@@ -17,6 +17,10 @@
 
 #include "energies.cuh"
 
+#include <TinyAD/Utils/LineSearch.hh>
+#include <TinyAD/Utils/NewtonDecrement.hh>
+#include <TinyAD/Utils/NewtonDirection.hh>
+
 using namespace TinyAD;
 using namespace tadx;
 
@@ -219,6 +223,27 @@ int tadx_selftest(int device)
         threw = false;
         try { ScalarFunction<2> bad(std::vector<int64_t>{0, 2}, es); } catch (const std::runtime_error&) { threw = true; }
         if (!threw) return 14;
+        // one projected-Newton step with the solver utilities (loop of tests/NewtonTest.cc:68-75) on the convex quadratic:
+        // H = [[4,2],[2,2]], g = (9,6) at x = (1,2)  ->  d = -H^-1 g = (-1.5,-1.5), decrement 11.25, full step accepted, g(x+d) = 0
+        {
+            auto [fq, gq, Hq] = assigned.eval_with_hessian_proj(x);
+            LinearSolver<double> solver;
+            solver.block_dim = 2;
+            solver.rel_tol = 1e-14;
+            const std::vector<double> dq = newton_direction(gq, Hq, solver);
+            if (std::fabs(dq[0] + 1.5) > 1e-12 || std::fabs(dq[1] + 1.5) > 1e-12) return 15;
+            if (std::fabs(newton_decrement(dq, gq) - 11.25) > 1e-11) return 16;
+            const std::vector<double> xn = line_search(x, dq, fq, gq, assigned);
+            if (std::fabs(xn[0] + 0.5) > 1e-12 || std::fabs(xn[1] - 0.5) > 1e-12) return 17;
+            auto [fn2, gn2] = assigned.eval_with_gradient(xn);
+            if (std::fabs(gn2[0]) > 1e-11 || std::fabs(gn2[1]) > 1e-11 || !(fn2 < fq)) return 18;
+            // an indefinite matrix is reported like the reference's "Linear solve failed." (NewtonDirection.hh:43-44)
+            SparseMatrix Hneg = Hq;
+            for (double& v : Hneg.values) v = -v;
+            threw = false;
+            try { newton_direction(gq, Hneg, solver); } catch (const std::runtime_error&) { threw = true; }
+            if (!threw) return 19;
+        }
         return 0;
     }
     catch (const std::exception& e)

@@ -644,11 +644,7 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         const unsigned g = (unsigned)((n + 127) / 128);
         project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
         project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
-        static const int occ = getenv("TAD_PROJ_B_OCC") ? atoi(getenv("TAD_PROJ_B_OCC")) : 3;  // tuning knob: min blocks per SM
-        if (occ <= 3) project_kernel_b<K, 3><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
-        else if (occ <= 4) project_kernel_b<K, 4><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
-        else if (occ <= 6) project_kernel_b<K, 6><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
-        else project_kernel_b<K, 8><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
+        project_kernel_b<K, 3><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
         // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
         double* work = scratch_d + (size_t)(L::nR + L::nW) * stride;
         if (fuse_out && side && side->stream)
@@ -1740,6 +1736,8 @@ int eval_vector(tad_function f, int what, const double* x, double* f_host, doubl
 extern "C" {
 
 const char* tad_last_error(void) { return g_last_error.c_str(); }
+void tad_set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }  // for the other translation units of this library
+int tad_function_variable_dimension(tad_function f) { return f ? f->d : 0; }
 
 int tad_device_count(int* count)
 {

@@ -235,7 +235,7 @@ TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, cons
 // 32 fixed pseudo-random numbers in (-1, 1) (start vectors of the inverse iteration)
 TINYAD_HD TINYAD_INLINE double start_table(unsigned i)
 {
-    constexpr double t[32] = {0.4387, -0.7112, 0.2918, 0.9534, -0.1276, 0.6641, -0.8823, 0.3359, -0.5467, 0.7785, 0.1193,
+    static constexpr double t[32] = {0.4387, -0.7112, 0.2918, 0.9534, -0.1276, 0.6641, -0.8823, 0.3359, -0.5467, 0.7785, 0.1193,
                               -0.9341, 0.5872, -0.2654, 0.8126, -0.4498, 0.0715, 0.6267, -0.7931, 0.3642, -0.1889, 0.9078,
                               -0.6013, 0.2471, 0.7356, -0.3927, 0.5189, -0.8564, 0.1632, -0.6745, 0.8891, -0.0458};
     return t[i & 31u];
