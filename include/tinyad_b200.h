@@ -176,12 +176,18 @@ int tad_function_set_timing(tad_function f, int enabled);
  * newton_decrement   Utils/NewtonDecrement.hh:20-26    -0.5 d.g
  * line_search        Utils/LineSearch.hh:26-65         x_new = x0 + s d with the first s in {s_max, s_max*shrink, ...} (and 1.0 when
  *   s_max > 1) that satisfies the Armijo condition f(x_new) <= f0 + armijo_const * s * d.g (:14-24); each trial is one value-only
- *   tad_eval; returns x0 (step 0) after max_iters failures like the reference; NaN objective -> TAD_INVALID_ARGUMENT (:53). */
+ *   tad_eval (tad_veval_sum_of_squares for a vector function, GaussNewtonTest.cc:142-145); returns x0 (step 0) after max_iters failures like the reference; NaN objective -> TAD_INVALID_ARGUMENT (:53). */
 int tad_pcg_solve(int64_t n, int block_dim, const int32_t* outer_dev, const int32_t* inner_dev, const double* values_dev, double w_identity,
                   const double* b_dev, double b_scale, double* x_dev, double rel_tol, int max_iters, int* iters_out, double* rel_residual_out,
                   void* stream);
 int tad_newton_direction(tad_function f, const double* g_dev, const double* H_values_dev, double w_identity, double rel_tol, int max_iters,
                          double* d_dev, int* iters_out, double* rel_residual_out);
+/* gauss_newton_direction  Utils/GaussNewtonDirection.hh:24-47: d = -(J^T J + w_identity I)^-1 J^T r for a
+ * vector function, from its residuals r and the values of its fixed-pattern CSC Jacobian.  The reference forms J^T J with a sparse
+ * product and factorises it; here the normal-equations operator is applied matrix-free (y = J p scattered, J^T y gathered) inside
+ * the same PCG, Jacobi preconditioner = 1 / (column norms^2 + w). */
+int tad_gauss_newton_direction(tad_function f, const double* r_dev, const double* J_values_dev, double w_identity, double rel_tol,
+                               int max_iters, double* d_dev, int* iters_out, double* rel_residual_out);
 int tad_newton_decrement(tad_function f, const double* d_dev, const double* g_dev, double* out_host);
 int tad_line_search(tad_function f, const double* x0_dev, const double* d_dev, double f0, const double* g_dev, double s_max, double shrink,
                     int max_iters, double armijo_const, double* x_new_dev, double* f_new_host, double* step_host, int* n_evals);

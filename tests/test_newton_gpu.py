@@ -130,3 +130,55 @@ def test_line_search_matches_reference_loop(torch_cuda, s_max):
     with pytest.raises(tad.TinyADError):
         fn.line_search(xd, d, f, g, xn, s_max=0.0)
     fn.close()
+
+
+def _gn_buffers(torch, fn):
+    g = torch.empty(fn.n_vars, dtype=torch.float64, device="cuda")
+    r = torch.empty(fn.n_outputs, dtype=torch.float64, device="cuda")
+    J = torch.empty(fn.nnz, dtype=torch.float64, device="cuda")
+    return g, r, J
+
+
+def test_gauss_newton_direction_matches_normal_equations(torch_cuda):
+    """gauss_newton_direction (Utils/GaussNewtonDirection.hh:24-47): d = -(J^T J + w I)^-1 J^T r, against scipy on the same J."""
+    torch = torch_cuda
+    from test_vector_gpu import sos_problem
+    p, x = sos_problem(12)
+    fn = p.gpu()
+    xd = torch.from_numpy(x).cuda()
+    g, r, J = _gn_buffers(torch, fn)
+    d = torch.empty_like(g)
+    fn.veval_sum_of_squares_with_derivatives(xd, g, r, J)
+    w = 1e-8
+    its, rel = fn.gauss_newton_direction(r, J, d, w_identity=w, rel_tol=1e-13, max_iters=20000)
+    outer, inner = fn.pattern()
+    Jm = sp.csc_matrix((J.cpu().numpy(), inner, outer), shape=(fn.n_outputs, fn.n_vars))
+    A = (Jm.T @ Jm + w * sp.identity(fn.n_vars)).tocsc()
+    ref = spla.spsolve(A, -(Jm.T @ r.cpu().numpy()))
+    err = np.abs(d.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 1e-6, (err, its, rel)
+    # g = 2 J^T r  =>  the Gauss-Newton direction is a descent direction with decrement -0.5 d.g = d.(J^T J + w) d
+    assert fn.newton_decrement(d, g) > 0.0
+    fn.close()
+
+
+def test_gauss_newton_fixture_on_device(torch_cuda):
+    """tests/GaussNewtonTest.cc:140-160: Gauss-Newton iterations (w_identity = 1e-12) + line search on eval_sum_of_squares
+    reach the distortion minimum f = 4 (within 0.1) with a small gradient."""
+    torch = torch_cuda
+    from test_vector_gpu import sos_problem
+    p, x = sos_problem()
+    fn = p.gpu()
+    xd = torch.from_numpy(x).cuda()
+    g, r, J = _gn_buffers(torch, fn)
+    d = torch.empty_like(g)
+    xn = torch.empty_like(g)
+    for _ in range(20):                                              # GaussNewtonTest.cc:113
+        f = fn.veval_sum_of_squares_with_derivatives(xd, g, r, J)
+        fn.gauss_newton_direction(r, J, d, w_identity=1e-12, rel_tol=1e-12)
+        f_new, step, n = fn.line_search(xd, d, f, g, xn)
+        assert f_new <= f
+        xd, xn = xn, xd
+    f = fn.veval_sum_of_squares_with_derivatives(xd, g, r, J)
+    assert abs(f - 4.0) < 0.1 and float(g.abs().max()) < 0.1           # :152-159
+    fn.close()

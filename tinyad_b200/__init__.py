@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "tad_veval_sum_of_squares", "tad_veval_sum_of_squares_with_derivatives", "tad_project_batch",
     "tad_function_projection_stats", "tad_function_last_timings", "tad_function_set_timing", "tad_bench_fp64_peak",
     "tad_set_last_error", "tad_function_variable_dimension",
-    "tad_pcg_solve", "tad_newton_direction", "tad_newton_decrement", "tad_line_search",
+    "tad_pcg_solve", "tad_newton_direction", "tad_gauss_newton_direction", "tad_newton_decrement", "tad_line_search",
 ]
 
 _rt = None
@@ -95,6 +95,7 @@ def runtime():
         L.tad_function_variable_dimension.argtypes = [vp]
         L.tad_pcg_solve.argtypes = [i64, ctypes.c_int, vp, vp, vp, dbl, vp, dbl, vp, dbl, ctypes.c_int, vp, vp, vp]
         L.tad_newton_direction.argtypes = [vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
+        L.tad_gauss_newton_direction.argtypes = [vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
         L.tad_newton_decrement.argtypes = [vp, vp, vp, vp]
         L.tad_line_search.argtypes = [vp, vp, vp, dbl, vp, dbl, dbl, ctypes.c_int, dbl, vp, vp, vp, vp]
         _rt = L
@@ -280,6 +281,13 @@ class Function:
         it, rel = ctypes.c_int(), ctypes.c_double()
         _check(runtime().tad_newton_direction(self.h, _ptr(g_dev), _ptr(H_dev), w_identity, rel_tol, max_iters, _ptr(d_dev),
                                               ctypes.byref(it), ctypes.byref(rel)))
+        return it.value, rel.value
+
+    def gauss_newton_direction(self, r_dev, J_dev, d_dev, w_identity=0.0, rel_tol=1e-10, max_iters=10000):
+        """d = -(J^T J + w_identity I)^-1 J^T r (Utils/GaussNewtonDirection.hh:24-47), matrix-free PCG.  Returns (iterations, rel. residual)."""
+        it, rel = ctypes.c_int(), ctypes.c_double()
+        _check(runtime().tad_gauss_newton_direction(self.h, _ptr(r_dev), _ptr(J_dev), w_identity, rel_tol, max_iters, _ptr(d_dev),
+                                                    ctypes.byref(it), ctypes.byref(rel)))
         return it.value, rel.value
 
     def newton_decrement(self, d_dev, g_dev):

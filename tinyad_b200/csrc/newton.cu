@@ -3,6 +3,7 @@
 //   tad_newton_direction   <- Utils/NewtonDirection.hh:25-48   d = -(H_proj + w_identity I)^-1 g
 //   tad_newton_decrement   <- Utils/NewtonDecrement.hh:20-26    -0.5 d.g
 //   tad_line_search        <- Utils/LineSearch.hh:14-65         backtracking Armijo search, value-only evaluations
+//   tad_gauss_newton_direction <- Utils/GaussNewtonDirection.hh:24-47  d = -(J^T J + w_identity I)^-1 J^T r, matrix-free
 //   tad_pcg_solve                                               the linear solver behind tad_newton_direction
 //
 // The reference factorises H with Eigen::SimplicialLDLT (Utils/LinearSolver.hh:12-19), BASELINE.json names cuDSS for
@@ -278,10 +279,108 @@ int device_dot(int64_t n, const double* a, const double* b, double* out_host, cu
     return TAD_OK;
 }
 
-template <int D>
-int pcg_run(int64_t n, const int32_t* outer, const int32_t* inner, const double* vals, double w, const double* b, double scale, double* x,
-            double rel_tol, int max_iters, int* iters_out, double* rel_res_out, cudaStream_t st)
+// ---- operators ----------------------------------------------------------------------------------------------------
+// A + w I, A symmetric in CSR (== CSC)
+struct SymCsrOp
 {
+    int64_t n;
+    const int32_t *outer, *inner;
+    const double* vals;
+    double w;
+    int apply(const double* p, double* y, double* pAp, cudaStream_t st) const
+    {
+        spmv_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, w, p, y, pAp);
+        return TAD_OK;
+    }
+    template <int D>
+    int preconditioner(double* minv, cudaStream_t st) const
+    {
+        block_jacobi<D><<<blocks_for(n / D, 128), 128, 0, st>>>(n / D, outer, inner, vals, w, minv);
+        return TAD_OK;
+    }
+};
+
+// y_out = J p (column-compressed J: scatter with atomics, 8 lanes per column)
+__global__ void __launch_bounds__(256) csc_scatter(int64_t n_cols, const int32_t* __restrict__ outer, const int32_t* __restrict__ inner,
+                                                   const double* __restrict__ vals, const double* __restrict__ p, double* __restrict__ y_out)
+{
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (c >= n_cols) return;
+    const double pc = p[c];
+    for (int q = outer[c] + (threadIdx.x & 7); q < outer[c + 1]; q += 8) atomicAdd(&y_out[inner[q]], vals[q] * pc);
+}
+
+// z = J^T y_out + w p, pAp += p.z   (8 lanes per column); p == nullptr: plain z = J^T y_out
+__global__ void __launch_bounds__(256) csc_gather_dot(int64_t n_cols, const int32_t* __restrict__ outer, const int32_t* __restrict__ inner,
+                                                      const double* __restrict__ vals, const double* __restrict__ y_out, double w,
+                                                      const double* __restrict__ p, double* __restrict__ z, double* pAp)
+{
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    double acc = 0.0;
+    if (c < n_cols)
+        for (int q = outer[c] + sub; q < outer[c + 1]; q += 8) acc = fma(vals[q], y_out[inner[q]], acc);
+    acc += __shfl_down_sync(0xffffffffu, acc, 4, 8);
+    acc += __shfl_down_sync(0xffffffffu, acc, 2, 8);
+    acc += __shfl_down_sync(0xffffffffu, acc, 1, 8);
+    double contrib = 0.0;
+    if (c < n_cols && sub == 0)
+    {
+        if (p)
+        {
+            const double pc = p[c];
+            acc = fma(w, pc, acc);
+            contrib = pc * acc;
+        }
+        z[c] = acc;
+    }
+    if (pAp)
+    {
+        const double s = block_sum(contrib);
+        if (threadIdx.x == 0) atomicAdd(pAp, s);
+    }
+}
+
+// 1 / (|J e_c|^2 + w): Jacobi preconditioner of J^T J + w I
+__global__ void __launch_bounds__(256) csc_colnorm_inv(int64_t n_cols, const int32_t* __restrict__ outer, const double* __restrict__ vals, double w,
+                                                       double* __restrict__ minv)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    double s = w;
+    for (int q = outer[c]; q < outer[c + 1]; ++q) s = fma(vals[q], vals[q], s);
+    minv[c] = s > 0.0 ? 1.0 / s : 1.0;
+}
+
+// J^T J + w I without forming the product (the reference multiplies the sparse matrices, GaussNewtonDirection.hh:31)
+struct NormalOp
+{
+    int64_t n, n_out;  // n = columns of J (variables)
+    const int32_t *outer, *inner;
+    const double* vals;
+    double w;
+    double* y_out;  // n_out doubles of scratch
+    int apply(const double* p, double* y, double* pAp, cudaStream_t st) const
+    {
+        if (cudaMemsetAsync(y_out, 0, (size_t)n_out * sizeof(double), st) != cudaSuccess) return fail(TAD_CUDA_ERROR, "memset failed");
+        csc_scatter<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, p, y_out);
+        csc_gather_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, y_out, w, p, y, pAp);
+        return TAD_OK;
+    }
+    template <int D>
+    int preconditioner(double* minv, cudaStream_t st) const
+    {
+        static_assert(D == 1, "scalar Jacobi only");
+        csc_colnorm_inv<<<blocks_for(n, 256), 256, 0, st>>>(n, outer, vals, w, minv);
+        return TAD_OK;
+    }
+};
+
+template <int D, class Op>
+int pcg_run(const Op& op, const double* b, double scale, double* x, double rel_tol, int max_iters, int* iters_out, double* rel_res_out,
+            cudaStream_t st)
+{
+    const int64_t n = op.n;
     const int64_t nb = n / D;
     Buf minv, r, z, p, y, scal, flag;
     NT_CUDA(minv.alloc((size_t)nb * D * D * sizeof(double)));
@@ -298,7 +397,8 @@ int pcg_run(int64_t n, const int32_t* outer, const int32_t* inner, const double*
     double* rz = scal.as<double>();
     double* rr = rz + slots;
     double* pAp = rr + slots;
-    block_jacobi<D><<<blocks_for(nb, 128), 128, 0, st>>>(nb, outer, inner, vals, w, minv.as<double>());
+    int s_ = op.template preconditioner<D>(minv.as<double>(), st);
+    if (s_ != TAD_OK) return s_;
     pcg_init<D><<<blocks_for(nb, 256), 256, 0, st>>>(nb, b, scale, minv.as<double>(), x, r.as<double>(), z.as<double>(), p.as<double>(), rz, rr);
     double rr0 = 0.0;
     NT_CUDA(cudaMemcpyAsync(&rr0, rr, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -312,7 +412,8 @@ int pcg_run(int64_t n, const int32_t* outer, const int32_t* inner, const double*
         const int check_every = 8;
         while (k < max_iters)
         {
-            spmv_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, w, p.as<double>(), y.as<double>(), pAp + k);
+            s_ = op.apply(p.as<double>(), y.as<double>(), pAp + k, st);
+            if (s_ != TAD_OK) return s_;
             pcg_update_xr<D><<<blocks_for(nb, 256), 256, 0, st>>>(nb, minv.as<double>(), p.as<double>(), y.as<double>(), x, r.as<double>(),
                                                                   z.as<double>(), rz + k, pAp + k, rz + k + 1, rr + k + 1, flag.as<int>());
             pcg_update_p<<<blocks_for(n, 256), 256, 0, st>>>(n, z.as<double>(), p.as<double>(), rz + k, rz + k + 1);
@@ -352,11 +453,41 @@ int tad_pcg_solve(int64_t n, int block_dim, const int32_t* outer_dev, const int3
     if (!(rel_tol > 0.0)) rel_tol = 1e-10;
     if (n == 0) { if (iters_out) *iters_out = 0; if (rel_residual_out) *rel_residual_out = 0.0; return TAD_OK; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (block_dim == 3 && n % 3 == 0)
-        return pcg_run<3>(n, outer_dev, inner_dev, values_dev, w_identity, b_dev, b_scale, x_dev, rel_tol, max_iters, iters_out, rel_residual_out, st);
-    if (block_dim == 2 && n % 2 == 0)
-        return pcg_run<2>(n, outer_dev, inner_dev, values_dev, w_identity, b_dev, b_scale, x_dev, rel_tol, max_iters, iters_out, rel_residual_out, st);
-    return pcg_run<1>(n, outer_dev, inner_dev, values_dev, w_identity, b_dev, b_scale, x_dev, rel_tol, max_iters, iters_out, rel_residual_out, st);
+    const SymCsrOp op{n, outer_dev, inner_dev, values_dev, w_identity};
+    if (block_dim == 3 && n % 3 == 0) return pcg_run<3>(op, b_dev, b_scale, x_dev, rel_tol, max_iters, iters_out, rel_residual_out, st);
+    if (block_dim == 2 && n % 2 == 0) return pcg_run<2>(op, b_dev, b_scale, x_dev, rel_tol, max_iters, iters_out, rel_residual_out, st);
+    return pcg_run<1>(op, b_dev, b_scale, x_dev, rel_tol, max_iters, iters_out, rel_residual_out, st);
+}
+
+int tad_gauss_newton_direction(tad_function f, const double* r_dev, const double* J_values_dev, double w_identity, double rel_tol,
+                               int max_iters, double* d_dev, int* iters_out, double* rel_residual_out)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "tad_gauss_newton_direction: null function");
+    const int64_t n_out = tad_function_n_outputs(f);
+    const int64_t n = tad_function_n_vars(f);
+    if (n_out <= 0) return fail(TAD_INVALID_ARGUMENT, "tad_gauss_newton_direction needs a vector function with residuals");
+    const int32_t *outer = nullptr, *inner = nullptr;
+    int s = tad_function_pattern_device(f, &outer, &inner);
+    if (s != TAD_OK) return s;
+    void* stv = nullptr;
+    s = tad_function_get_stream(f, &stv);
+    if (s != TAD_OK) return s;
+    cudaStream_t st = (cudaStream_t)stv;
+    if (max_iters <= 0) max_iters = 10000;
+    if (!(rel_tol > 0.0)) rel_tol = 1e-10;
+    Buf y_out, rhs;
+    NT_CUDA(y_out.alloc((size_t)n_out * sizeof(double)));
+    NT_CUDA(rhs.alloc((size_t)n * sizeof(double)));
+    // b = J^T r; solve (J^T J + w I) d = -b
+    csc_gather_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, J_values_dev, r_dev, 0.0, nullptr, rhs.as<double>(), nullptr);
+    const NormalOp op{n, n_out, outer, inner, J_values_dev, w_identity, y_out.as<double>()};
+    s = pcg_run<1>(op, rhs.as<double>(), -1.0, d_dev, rel_tol, max_iters, iters_out, rel_residual_out, st);
+    if (s != TAD_OK) return s;
+    double dd = 0.0;
+    s = device_dot(n, d_dev, d_dev, &dd, st);
+    if (s != TAD_OK) return s;
+    if (!std::isfinite(dd)) return fail(TAD_SOLVER_FAILED, "Linear solve failed: direction is not finite.");
+    return TAD_OK;
 }
 
 int tad_newton_direction(tad_function f, const double* g_dev, const double* H_values_dev, double w_identity, double rel_tol, int max_iters,
@@ -408,13 +539,14 @@ int tad_line_search(tad_function f, const double* x0_dev, const double* d_dev, d
     st_ = device_dot(n, d_dev, g_dev, &dg, st);
     if (st_ != TAD_OK) return st_;
     const bool try_one = s_max > 1.0;  // also try a step size of 1.0 (LineSearch.hh:44-45)
+    const bool is_vector = tad_function_n_outputs(f) > 0;  // objective of a vector function: eval_sum_of_squares (GaussNewtonTest.cc:142-145)
     double s = s_max;
     int evals = 0;
     for (int i = 0; i < max_iters; ++i)
     {
         axpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, x0_dev, s, d_dev, x_new_dev);
         double f_new = 0.0;
-        st_ = tad_eval(f, x_new_dev, &f_new);
+        st_ = is_vector ? tad_veval_sum_of_squares(f, x_new_dev, &f_new) : tad_eval(f, x_new_dev, &f_new);
         ++evals;
         if (st_ != TAD_OK) return st_;
         if (f_new != f_new) return fail(TAD_INVALID_ARGUMENT, "line_search: objective is NaN");  // TINYAD_ASSERT_EQ(f_new, f_new), :53

@@ -586,7 +586,11 @@ __global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t
         code = TinyAD::detail::proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; },
                                                       [&](int i, double v) { rp[(int64_t)i * stride] = v; },
                                                       [&](int i, double v) { wp[(int64_t)i * stride] = v; },
-                                                      [&](int i) { return wp[(int64_t)i * stride]; }, eps);
+                                                      [&](int jv, double (&v)[K]) {
+                                                          const double* p = wp + (int64_t)(TinyAD::detail::ProjLayout<K>::off_vec + jv * K) * stride;
+#pragma unroll
+                                                          for (int q = 0; q < K; ++q) { v[q] = *p; p += stride; }
+                                                      }, eps);
     sc.codes[el] = code;
     if (counts) atomicAdd(&counts[0], 1ull);
     if (code == TinyAD::detail::PROJ_REBUILT && counts) atomicAdd(&counts[1], 1ull);

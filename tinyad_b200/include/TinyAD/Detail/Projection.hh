@@ -241,6 +241,8 @@ TINYAD_HD TINYAD_INLINE double start_table(unsigned i)
     return t[i & 31u];
 }
 
+// 1/x for x in the normal range (callers guarantee it, see the uses): hardware approximation + two Newton steps,
+// without the slow-path branches of an IEEE division.  x = 0 gives NaN, which the callers select away.
 TINYAD_HD TINYAD_INLINE double rcp_fast(double x)
 {
 #if defined(__CUDA_ARCH__)
@@ -250,7 +252,6 @@ TINYAD_HD TINYAD_INLINE double rcp_fast(double x)
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
-    if (!(fabs(y) <= 1.7e308)) y = 1.0 / x;  // denormal / zero / non-finite argument: IEEE division
     return y;
 #else
     return 1.0 / x;
@@ -363,12 +364,48 @@ TINYAD_HD inline int proj_eigenvalues(LoadRFn&& load_r, StoreRFn&& store_r)
     return PROJ_UNCHANGED;
 }
 
+// Ascending sort of K doubles held in registers: compare-exchange network with compile-time indices (an optimal
+// 39-comparator network for K = 12, odd-even transposition otherwise).  No NaNs (checked by the caller).
+TINYAD_HD TINYAD_INLINE void cswap(double& a, double& b)
+{
+    const bool sw = b < a;
+    const double lo = sw ? b : a, hi = sw ? a : b;
+    a = lo;
+    b = hi;
+}
+template <int K>
+TINYAD_HD TINYAD_INLINE void sort_ascending(double (&v)[K])
+{
+    if constexpr (K == 12)
+    {
+        constexpr int net[39][2] = {{0, 8},  {1, 7},  {2, 6},  {3, 11}, {4, 10}, {5, 9},  {0, 1},  {2, 5},  {3, 4},  {6, 9},
+                                    {7, 8},  {10, 11}, {0, 2},  {1, 6},  {5, 10}, {9, 11}, {0, 3},  {1, 2},  {4, 6},  {5, 7},
+                                    {8, 11}, {9, 10}, {1, 4},  {3, 5},  {6, 8},  {7, 10}, {1, 3},  {2, 5},  {6, 9},  {8, 10},
+                                    {2, 3},  {4, 5},  {6, 7},  {8, 9},  {4, 6},  {5, 7},  {3, 4},  {5, 6},  {7, 8}};
+        static_for<39>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int c = decltype(ic)::value;
+            cswap(v[net[c][0]], v[net[c][1]]);
+        });
+    }
+    else
+    {
+        static_for<K>([&](auto rc) TINYAD_LAMBDA_INLINE {
+            constexpr int round = decltype(rc)::value;
+            static_for<(K - (round & 1)) / 2>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                constexpr int i = (round & 1) + 2 * decltype(ic)::value;
+                cswap(v[i], v[i + 1]);
+            });
+        });
+    }
+}
+
 // Phase B2: selection of the eigenvalues that move, their eigenvectors (of T) by inverse iteration.
 // Scalar recurrences on small arrays, written as plain loops: nvcc unrolls the fixed-trip-count ones (LU, solves)
 // so those arrays live in registers.  load_w re-reads vectors already stored through store_w; the eigenvalues are read
 // back from R at run-time indices.
-template <int K, class LoadRFn, class StoreLamFn, class StoreWFn, class LoadWFn>
-TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_lam, StoreWFn&& store_w, LoadWFn&& load_w, const double eps)
+// load_vec(jv, v) reads back vector jv (K entries, W[off_vec + jv K ..)) already stored through store_w.
+template <int K, class LoadRFn, class StoreLamFn, class StoreWFn, class LoadVecFn>
+TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_lam, StoreWFn&& store_w, LoadVecFn&& load_vec, const double eps)
 {
     using L = ProjLayout<K>;
     constexpr double macheps = 2.220446049250313e-16;
@@ -402,15 +439,7 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
             chk += fabs(lam[i]);
         });
         if (!(chk <= 1.7e308)) return PROJ_FALLBACK;  // NaN / Inf
-        static_for<K>([&](auto rc) TINYAD_LAMBDA_INLINE {
-            constexpr int round = decltype(rc)::value;
-            static_for<(K - (round & 1)) / 2>([&](auto ic) TINYAD_LAMBDA_INLINE {
-                constexpr int i = (round & 1) + 2 * decltype(ic)::value;
-                const double lo = fmin(lam[i], lam[i + 1]), hi = fmax(lam[i], lam[i + 1]);
-                lam[i] = lo;
-                lam[i + 1] = hi;
-            });
-        });
+        sort_ascending<K>(lam);
         static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; store_lam(L::off_lam + i, lam[i]); });
     }
 
@@ -530,10 +559,11 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
             // cluster are amplified >= 1e12 times less than the wanted one; they are removed after the solve only.) ...
             for (int i = gpind; i < j; ++i)
             {
-                const int base = L::off_vec + (i - j_begin) * K;
+                double v[K];
+                load_vec(i - j_begin, v);
                 double dot = 0.0;
-                for (int q = 0; q < K; ++q) dot = fma(x[q], load_w(base + q), dot);
-                for (int q = 0; q < K; ++q) x[q] = fma(-dot, load_w(base + q), x[q]);
+                for (int q = 0; q < K; ++q) dot = fma(x[q], v[q], dot);
+                for (int q = 0; q < K; ++q) x[q] = fma(-dot, v[q], x[q]);
             }
             double xabs = 0.0;
             for (int i = 0; i < K; ++i) xabs += fabs(x[i]);
@@ -563,10 +593,11 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
             // unselected subspace, see the acceptance test)
             for (int i = j_begin; i < j; ++i)
             {
-                const int base = L::off_vec + (i - j_begin) * K;
+                double v[K];
+                load_vec(i - j_begin, v);
                 double dot = 0.0;
-                for (int q = 0; q < K; ++q) dot = fma(x[q], load_w(base + q), dot);
-                for (int q = 0; q < K; ++q) x[q] = fma(-dot, load_w(base + q), x[q]);
+                for (int q = 0; q < K; ++q) dot = fma(x[q], v[q], dot);
+                for (int q = 0; q < K; ++q) x[q] = fma(-dot, v[q], x[q]);
             }
             double n2 = 0.0;
             for (int i = 0; i < K; ++i) n2 = fma(x[i], x[i], n2);
@@ -578,7 +609,7 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
                 double t = (d0[i] - lj) * x[i];
                 if (i > 0) t = fma(e0[i - 1], x[i - 1], t);
                 if (i + 1 < K) t = fma(e0[i], x[i + 1], t);
-                res = fmax(res, fabs(t));
+                if (fabs(t) > res) res = fabs(t);
             }
 #if defined(TAD_PROJ_DEBUG) && !defined(__CUDA_ARCH__)
             printf("  j=%d lj=%.3e xj=%.3e its=%d res=%.3e (limit %.3e) gpind=%d a_last=%.3e tol=%.3e\n", j, lj, xj, its, res * inv, res_limit, gpind, a_last, tol);
@@ -675,7 +706,7 @@ TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const doubl
     code = proj_eigenvalues<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; });
     if (code == PROJ_FALLBACK) return code;
     code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; }, [&](int i, double v) { Wb[i] = v; },
-                                  [&](int i) { return Wb[i]; }, eps);
+                                  [&](int jv, double (&v)[K]) { for (int q = 0; q < K; ++q) v[q] = Wb[L::off_vec + jv * K + q]; }, eps);
     if (code != PROJ_REBUILT) return code;
     proj_apply<K>([&](int i) { return R[i]; }, [&](int i) { return Wb[i]; }, load, store, eps);
     return PROJ_REBUILT;
