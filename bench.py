@@ -368,8 +368,9 @@ def main():
         else:
             achieved = dom_flops * n_el / dom_s / 1e12
             roof = {"bound": "fp64", "kernel": dominant, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak}
-        # dram__bytes_read + dram__bytes_write of the projection kernels (A + B) from the ncu --set full capture in profiles/
-        roof["traffic"] = 2.38e9 if (args.workload == "c2" and dominant == "projection") else None
+        # dram__bytes_read + dram__bytes_write of the projection kernels (A + B1 + B2) from the ncu --set full capture in
+        # profiles/r01_v2_ncu_full_hot_kernels.csv (C2 workload; per step = per launch of each of the three kernels)
+        roof["traffic"] = 2.70e9 if (args.workload == "c2" and dominant == "projection") else None
         roof["peak_source"] = "FP64: DFMA-chain microbenchmark run in this process (measured); HBM: MEASURED_PEAKS.json" if peaks else "HBM fallback 6650 GB/s"
         step_tflops = flops_el * n_el / t_step / 1e12
         roof["whole_step"] = {"fp64_tflops": step_tflops, "frac_of_fp64_peak": step_tflops / fp64_peak,
@@ -388,9 +389,9 @@ def main():
                        "setup_s_pattern_and_maps": setup_s},
             "e2e": {"value": n_total / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(8 * fn.n_vars), "d2h_bytes_per_step": int(8 * (fn.n_vars + nnz + 1)),
                     "ms_per_step": e2e_t * 1e3},
-            # per step: 4 element kernels (one per Hessian part; 1 for triangles), 2 reduction, 3 projection (A, B, fallback list),
-            # 1 fused projection-C + assembly
-            "gpu_launches": (10 if d == 3 else 7) * args.steps,
+            # per step: 4 element kernels (one per Hessian part; 1 for triangles), 2 reduction, 4 projection (A, B1, B2, fallback list),
+            # 2 fused projection-C + assembly (all elements / the listed ones)
+            "gpu_launches": (12 if d == 3 else 9) * args.steps,
             "clocks": clocks, "projection_stats": stats, "roofline": roof, "wall_s_timed_region": wall, "f": f,
         }
         if not args.no_cpu_baseline and world == 1:
