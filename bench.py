@@ -37,10 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c1", "small", "c3", "c3small"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c1", "small", "c3", "c3small", "c4", "c4small"],
                     help="c2: Kuhn cube n=55 (998,250 tets) per GPU [default]; c5: n=119 (10.1M tets) split over the GPUs; "
                          "c1: 512^2 triangle grid; small: n=16 smoke size; c3: projected-Newton loop on the C2 mesh, timed per phase "
-                         "(--steps = Newton iterations, default 20)")
+                         "(--steps = Newton iterations, default 20); c4: VectorFunction residual Jacobians + Gauss-Newton on a 2M-face grid")
     ap.add_argument("--newton-tol", type=float, default=1e-6, help="c3: relative residual of the PCG solve (inexact Newton)")
     ap.add_argument("--assembly", default="atomic", choices=["atomic", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -232,12 +232,75 @@ def run_newton(args):
     print(json.dumps(line))
 
 
+def run_gauss_newton(args):
+    """BASELINE.json configs[3]: frame-field style Gauss-Newton via VectorFunction per-element residual Jacobians on a 2M-face
+    synthetic triangle grid.  The real polycurl functor lives in TinyAD-Examples (not in the reference tree); the stand-in is the
+    complex-arithmetic per-edge residual of csrc/energies.cuh (SOS_POLYCURL2D, 2 residuals x 4 variables per element,
+    std::complex<Scalar> operators of Scalar.hh:1151-1320).  Timed: eval_sum_of_squares_with_derivatives (r, J values in the fixed
+    CSC pattern, f, g = 2 J^T r), and apart from it the matrix-free Gauss-Newton direction and the line search."""
+    import torch
+    import tinyad_b200 as tad
+    from test_vector_gpu import polycurl_problem
+    N = 1000 if args.workload == "c4" else 64
+    p, x0 = polycurl_problem(N)
+    n_el = len(p.terms[0][1])
+    t0 = time.perf_counter()
+    fn = p.gpu()
+    nnz = fn.nnz
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    x = torch.from_numpy(x0.copy()).cuda()
+    g = torch.empty(fn.n_vars, dtype=torch.float64, device="cuda")
+    r = torch.empty(fn.n_outputs, dtype=torch.float64, device="cuda")
+    J = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    d = torch.empty_like(g)
+    xn = torch.empty_like(g)
+    for _ in range(max(3, args.warmup)):
+        fn.veval_sum_of_squares_with_derivatives(x, g, r, J)
+    torch.cuda.synchronize()
+    stream_ptr = tad.ctypes.c_void_p()
+    tad.runtime().tad_function_get_stream(fn.h, tad.ctypes.byref(stream_ptr))
+    ext = torch.cuda.ExternalStream(stream_ptr.value)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    for _ in range(args.steps):
+        f = fn.veval_sum_of_squares_with_derivatives(x, g, r, J)
+    ev1.record(ext)
+    torch.cuda.synchronize()
+    t_eval = ev0.elapsed_time(ev1) * 1e-3 / args.steps
+    # a few Gauss-Newton iterations, phases timed with the host clock around the synchronous C calls
+    t_dir = t_ls = 0.0
+    log = []
+    gn_iters = 3
+    for _ in range(gn_iters):
+        f = fn.veval_sum_of_squares_with_derivatives(x, g, r, J)
+        t1 = time.perf_counter()
+        cg, rel = fn.gauss_newton_direction(r, J, d, w_identity=1e-6, rel_tol=1e-6, max_iters=5000)
+        t2 = time.perf_counter()
+        f_new, step, n_evals = fn.line_search(x, d, f, g, xn)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        t_dir += t2 - t1; t_ls += t3 - t2
+        log.append({"f": f, "f_new": f_new, "cg_iters": cg, "step": step, "ls_evals": n_evals})
+        x, xn = xn, x
+    line = {"metric": "VectorFunction residual-Jacobian elements/s (eval_sum_of_squares_with_derivatives)", "value": n_el / t_eval,
+            "unit": "elements/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_eval * 1e3, "higher_is_better": True,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4: {N}x{N} grid ({2 * N * N:,} faces, {n_el:,} edge elements, 2 residuals x 4 variables each), polycurl-style "
+                                   f"complex residual stand-in", "n_outputs": int(fn.n_outputs), "nnz_jacobian": int(nnz), "setup_s_pattern": setup_s},
+            "gauss_newton_ms_per_iteration": {"direction_matrix_free_pcg": t_dir / gn_iters * 1e3, "line_search": t_ls / gn_iters * 1e3},
+            "iterations": log}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload in ("c3", "c3small"):
         return run_newton(args)
+    if args.workload in ("c4", "c4small"):
+        return run_gauss_newton(args)
 
     import torch
     import torch.distributed as dist

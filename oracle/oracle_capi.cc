@@ -39,6 +39,9 @@ enum
     ORC_QUADRATIC2D = 6,         // d=2 N=1 data: sign     sign*(2x0^2+2x0x1+x1^2+x0+1)   (ScalarFunctionTest.cc:72-146)
     ORC_REPEATED_HANDLE = 7,     // d=2 N=2 accesses conn[0] twice then conn[1]             (ScalarFunctionTest.cc:153-179)
     ORC_TRIG_MIX2D = 8,          // d=2 N=2 exercises sin/cos/exp/log/sqrt/atan2/pow/hypot/tanh on 4 variables
+    ORC_DYN_SUM_SQR2D = 10,      // d=2 dynamic <3,1>: element e accesses handles 0..e-1, |sum|^2   (DynamicElementsTest.cc:9-33)
+    ORC_DYN_ONERING1D = 11,      // d=1 dynamic <4,6,7,10>: conn = padded neighbour table (n_data columns, -1 = none)
+                                 //     0.25 * sum_n (x_v - x_n)^2                                (DynamicElementsTest.cc:92-141)
     ORC_SOS_SYMDIRICHLET2D = 101,  // d=2 N=3 M=8 data: Mr (4) scale
     ORC_SOS_PENALTY2D = 102,       // d=2 N=1 M=2 data: tx ty
     ORC_SOS_POLYCURL2D = 103,      // d=2 N=2 M=2 data: ex ey w   complex residual, see below
@@ -158,6 +161,30 @@ void add_scalar_term(FuncT& func, const oracle_term& t)
                 T u = log(r) + sqrt(r + sqr(s)) + atan2(p[1] + 2.0, q[0] + 3.0);
                 T v = pow(r, 3) - pow(r, 1.5) + tanh(s) * data[e * nd];
                 return u * v + fabs(s - 0.1) + 2.0 / r - (1.0 - s) / 3.0;
+            });
+        break;
+    case ORC_DYN_SUM_SQR2D:
+        if constexpr (std::is_same_v<FuncT, ScalarFunction<2>>)
+            func.template add_elements_dynamic<3, 1>(handles(t.n_elements), [=](auto& element) -> ORACLE_SCALAR_TYPE(element) {
+                using T = ORACLE_SCALAR_TYPE(element);
+                const int e = (int)element.handle;
+                Vec<T, 2> sum;
+                for (int i = 0; i < 2; ++i) sum[i] = T(0.0);
+                for (int v = 0; v < e; ++v) sum = sum + element.variables(v);
+                return sum.squaredNorm();
+            });
+        break;
+    case ORC_DYN_ONERING1D:
+        if constexpr (std::is_same_v<FuncT, ScalarFunction<1>>)
+            func.template add_elements_dynamic<4, 6, 7, 10>(handles(t.n_elements), [=](auto& element) -> ORACLE_SCALAR_TYPE(element) {
+                using T = ORACLE_SCALAR_TYPE(element);
+                const Index v = element.handle;
+                T v_val = element.variable(v);
+                std::vector<T> neigh_vals;
+                for (int i = 0; i < nd && conn[v * nd + i] >= 0; ++i) neigh_vals.push_back(element.variable(conn[v * nd + i]));
+                T dirichlet = 0.0;
+                for (size_t i = 0; i < neigh_vals.size(); ++i) dirichlet = dirichlet + 0.25 * sqr(v_val - neigh_vals[i]);
+                return dirichlet;
             });
         break;
     default:

@@ -45,6 +45,7 @@
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <map>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -1001,6 +1002,25 @@ struct ScalarObjectiveTerm : ScalarObjectiveTermBase
 // ---------------------------------------------------------------------------
 // ScalarFunction (ScalarFunction.hh:36-236, Detail/ScalarFunctionImpl.hh)
 // ---------------------------------------------------------------------------
+// RecorderElement (ScalarFunctionImpl.hh:106-129): records which variable handles the functor accesses
+template <int d>
+struct RecorderElement
+{
+    using ScalarType = double;
+    static constexpr bool active_mode = false;
+    Index handle;
+    std::vector<Index> accessed;
+    explicit RecorderElement(Index h) : handle(h) {}
+    Vec<double, d> variables(Index vh)
+    {
+        if (std::find(accessed.begin(), accessed.end(), vh) == accessed.end()) accessed.push_back(vh);
+        return Vec<double, d>();
+    }
+    double variable(Index vh) { return variables(vh)[0]; }
+    Vec<double, d> variables_passive(Index) { return Vec<double, d>(); }
+    double variable_passive(Index) { return 0.0; }
+};
+
 inline std::vector<Index> range(Index n)  // Utils/Helpers.hh:17-27
 {
     std::vector<Index> r(n);
@@ -1022,6 +1042,30 @@ struct ScalarFunction
     {
         objective_terms.push_back(std::make_unique<ScalarObjectiveTerm<d, N, F>>(handles, std::move(f), n_vars, *settings));
         n_elements += (Index)handles.size();
+    }
+
+    // add_elements_dynamic (ScalarFunction.hh:80-108, ScalarFunctionImpl.hh:134-214): record how many variable handles each
+    // element accesses (RecorderElement, :106-129), group the elements by the exact or next larger static valence, add one
+    // term per non-empty group in the ORDER OF THE TEMPLATE ARGUMENTS (:190-213).
+    template <int... ElementValences, typename F>
+    void add_elements_dynamic(const std::vector<Index>& handles, F f)
+    {
+        std::vector<int> static_valences_sorted = {ElementValences...};
+        std::sort(static_valences_sorted.begin(), static_valences_sorted.end());
+        if (std::unique(static_valences_sorted.begin(), static_valences_sorted.end()) != static_valences_sorted.end())
+            error_throw("Element valences passed to add_elements<..>(..) are not unique. Please pass unique element valences.");  // :158-160
+        std::map<int, std::vector<Index>> groups;
+        for (const Index e : handles)
+        {
+            RecorderElement<d> rec(e);
+            f(rec);
+            const int element_valence = (int)rec.accessed.size();
+            auto it = std::lower_bound(static_valences_sorted.begin(), static_valences_sorted.end(), element_valence);
+            if (it == static_valences_sorted.end())
+                error_throw("Element valence exceeds maximum static valence passed to add_elements<..>(..).");  // :175-180
+            groups[*it].push_back(e);
+        }
+        (add_dynamic_group<ElementValences>(groups, f), ...);
     }
 
     double eval(const std::vector<double>& x) const  // :256-273
@@ -1058,6 +1102,13 @@ struct ScalarFunction
     std::vector<std::unique_ptr<ScalarObjectiveTermBase>> objective_terms;
 
 private:
+    template <int N, typename F>
+    void add_dynamic_group(const std::map<int, std::vector<Index>>& groups, const F& f)
+    {
+        const auto it = groups.find(N);
+        if (it != groups.end()) add_elements<N>(it->second, f);
+    }
+
     void check(const std::vector<double>& x) const
     {
         if ((Index)x.size() != n_vars) error_throw("x.size() != n_vars");

@@ -50,3 +50,40 @@ def tet_problem(n, seed=0, with_penalty=False, nz=None):
         terms.append((tad.PENALTY3D, b, V[b[:, 0]] + 0.01))
     x = meshes.deform(V, 1.0 / n, seed=seed).reshape(-1)
     return Problem(3, len(V), terms), x
+
+
+def icosphere(subdivisions=1):
+    """Closed triangle mesh with vertex valences 5 and 6 (consistently oriented): icosahedron, each face split in four."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    V = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    F = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    V = [np.array(v, dtype=float) / np.linalg.norm(v) for v in V]
+    for _ in range(subdivisions):
+        mid, F2 = {}, []
+
+        def m(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in mid:
+                p = V[a] + V[b]
+                V.append(p / np.linalg.norm(p))
+                mid[key] = len(V) - 1
+            return mid[key]
+        for a, b, c in F:
+            ab, bc, ca = m(a, b), m(b, c), m(c, a)
+            F2 += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        F = F2
+    return np.array(V), np.array(F, dtype=np.int32)
+
+
+def one_ring_table(n_vertices, F, width=9):
+    """DynamicElementsTest.cc:96-105: vertex -> neighbours from the DIRECTED face edges (v_i -> v_{i+1}), padded with -1."""
+    nbrs = [[] for _ in range(n_vertices)]
+    for f in F:
+        for i in range(3):
+            nbrs[int(f[i])].append(int(f[(i + 1) % 3]))
+    tab = -np.ones((n_vertices, width), dtype=np.int32)
+    for v, lst in enumerate(nbrs):
+        assert len(lst) <= width
+        tab[v, :len(lst)] = lst
+    return tab

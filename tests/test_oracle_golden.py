@@ -8,8 +8,9 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import oracle
-from problems import planar_newton_problem, Problem
+from problems import planar_newton_problem, Problem, icosphere, one_ring_table
 import tinyad_b200 as tad
+from tinyad_b200 import meshes
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = json.load(open(os.path.join(HERE, "golden", "scalar_cases.json")))
@@ -193,3 +194,45 @@ def test_inverted_element_returns_infinity():
     assert oracle.scalar_eval(2, 6, p.oracle_terms(), oracle.EVAL, x).f == np.inf
     r = oracle.scalar_eval(2, 6, p.oracle_terms(), oracle.HESSIAN_PROJ, x)   # val = inf is not an error
     assert r.f == np.inf and np.all(np.isfinite(r.g)) and np.all(np.isfinite(r.values))
+
+
+def reference_laplace(n_vertices, F):
+    """DynamicElementsTest.cc:38-56."""
+    L = sp.lil_matrix((n_vertices, n_vertices))
+    for f in F:
+        for i in range(3):
+            v1, v2 = int(f[i]), int(f[(i + 1) % 3])
+            L[v1, v1] += 1.0
+            L[v1, v2] -= 1.0
+    return L.tocsc()
+
+
+def test_dynamic_elements_fixture():
+    """tests/DynamicElementsTest.cc:9-33: add_elements_dynamic<3, 1>, element e accesses e variables; x = ones.
+    Groups: valence 3 <- elements {2, 3}, valence 1 <- elements {0, 1}.  f = sum_e |e * (1,1)|^2 = 2 (0 + 1 + 4 + 9) = 28."""
+    dummy = np.zeros((4, 1), dtype=np.int32)
+    t = [oracle.Term(oracle.DYN_SUM_SQR2D, dummy, np.zeros((4, 1)))]
+    x = np.ones(8)
+    r = oracle.scalar_eval(2, 4, t, oracle.HESSIAN_PROJ, x)
+    assert r.f == 28.0
+    # gradient of |s|^2 w.r.t. every accessed variable is 2 s: vertex v is accessed by the elements e > v
+    g = np.zeros(8)
+    for e in range(4):
+        for v in range(e):
+            g[2 * v:2 * v + 2] += 2.0 * e
+    assert np.array_equal(r.g, g)
+    H = to_csc(r).toarray()
+    assert np.allclose(H, H.T) and np.linalg.eigvalsh(H).min() > -1e-12      # PSD energy: projection leaves it PSD
+
+
+def test_dynamic_one_ring_laplacian():
+    """tests/DynamicElementsTest.cc:92-141: Hessian of the one-ring Dirichlet energy (dynamic vertex elements) == Laplacian to 1e-12;
+    the nnz differ because padded elements add explicit zeros (comment at :140)."""
+    V, F = icosphere(1)                     # closed mesh, 12 vertices of valence 5 and 30 of valence 6 -> two groups (6 and 7)
+    tab = one_ring_table(len(V), F)
+    assert sorted(set((tab >= 0).sum(axis=1))) == [5, 6]
+    t = [oracle.Term(oracle.DYN_ONERING1D, tab, np.zeros(tab.shape))]
+    r = oracle.scalar_eval(1, len(V), t, oracle.DERIVATIVES, np.zeros(len(V)))
+    L = reference_laplace(len(V), F)
+    assert abs(to_csc(r) - L).max() < 1e-12
+    assert spla.norm(to_csc(r) - L) < 1e-12

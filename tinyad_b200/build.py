@@ -8,6 +8,7 @@
 import os
 import subprocess
 import sys
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -42,11 +43,17 @@ def _headers():
 
 
 def _run(cmd, verbose):
+    t0 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    # stamp the output with the START time of the compilation: a source edited while nvcc was running is then newer than
+    # the object and gets rebuilt next time (nvcc reads its inputs at the start)
+    out = cmd[cmd.index("-o") + 1]
+    if os.path.exists(out):
+        os.utime(out, (t0, t0))
 
 
 def build(force=False, verbose=False):

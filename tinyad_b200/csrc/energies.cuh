@@ -53,6 +53,44 @@ struct Penalty  // data: target (d)
     }
 };
 
+// ---- dynamic-valence elements (add_elements_dynamic, tests/DynamicElementsTest.cc) ----
+struct DynSumSqr2D  // DynamicElementsTest.cc:9-33: element e accesses the handles 0 .. e-1
+{
+    ConnView C; DataView D;  // unused
+    template <class E>
+    TINYAD_HD auto operator()(E& element) const -> TINYAD_SCALAR_TYPE(element)
+    {
+        using T = TINYAD_SCALAR_TYPE(element);
+        const int e = (int)element.handle;
+        Vec<T, 2> sum;
+        sum[0] = T(0.0);
+        sum[1] = T(0.0);
+        for (int v = 0; v < e; ++v) sum = sum + element.variables(v);
+        return sum.squaredNorm();
+    }
+};
+
+struct OneRingDirichlet1D  // DynamicElementsTest.cc:112-131: conn = padded neighbour table (W columns, -1 = none)
+{
+    ConnView Nb; DataView D;  // D unused
+    int W;
+    template <class E>
+    TINYAD_HD auto operator()(E& element) const -> TINYAD_SCALAR_TYPE(element)
+    {
+        using T = TINYAD_SCALAR_TYPE(element);
+        const int64_t v = element.handle;
+        T v_val = element.variable(v);
+        T dirichlet = 0.0;
+        for (int i = 0; i < W; ++i)
+        {
+            const int32_t nb = Nb(v, i);
+            if (nb < 0) break;
+            dirichlet = dirichlet + 0.25 * sqr(v_val - element.variable(nb));
+        }
+        return dirichlet;
+    }
+};
+
 struct SymDirichlet3D  // data: Mr^-1 row-major (9), vol
 {
     static constexpr int tinyad_parts = TADX_TET_PARTS;      // Hessian parts (one kernel each)

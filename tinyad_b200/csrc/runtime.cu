@@ -968,8 +968,12 @@ void launch_c_assemble(const Term& t, const double* grad, const double* hess, in
                        int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
 {
     const bool split = side && side->stream;
-    project_c_assemble_kernel<D, N, false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
-                                                                                        t.rstride.p, grad, g, Hv, err, counts, split);
+    // ~200 registers per thread: single-warp blocks fit 10 per SM (10 warps) where 128-thread blocks fit 2 (8 warps); the kernel is
+    // bound by the latency of its load phases, so the extra warps pay (C2: 1.18 -> 1.08 ms; capping the registers at 170 for 12 warps: 1.21 ms).
+    // TAD_CASM_BLOCK overrides (tuning knob).
+    static const int bs = [] { const char* e = getenv("TAD_CASM_BLOCK"); const int v = e ? atoi(e) : 32; return (v == 32 || v == 64 || v == 128) ? v : 32; }();
+    project_c_assemble_kernel<D, N, false><<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
+                                                                                         t.rstride.p, grad, g, Hv, err, counts, split);
     if (split)
     {
         cudaStreamWaitEvent(st, side->ev_list, 0);

@@ -165,7 +165,9 @@ struct functor_unique_handles<Functor, std::void_t<decltype(Functor::tinyad_uniq
 
 // One objective term = functor + its launch function (the type-erased LambdaImpl of
 // ScalarObjectiveTerm.hh:78-115, with the three deferred instantiations done eagerly by nvcc).
-template <class Functor, int d, int N, int M>
+// ForceDense: always use the run-time-indexed element (add_elements_dynamic: the number of handles an element touches, and
+// with it the slot of each variables() call, is a run-time quantity).
+template <class Functor, int d, int N, int M, bool ForceDense = false>
 struct TermLauncher
 {
     static constexpr int k = d * N;
@@ -219,9 +221,13 @@ struct TermLauncher
             detail::record_kernel<Functor, d, N, M><<<(unsigned)((a->n_elements + 127) / 128), 128, 0, st>>>(self->f, *a);
             return detail::check_launch();
         }
-        if (!a->dedup) return launch_eval<false>(self, a);
-        if constexpr (detail::functor_unique_handles<Functor>::value) return TAD_NOT_SUPPORTED;
-        else return launch_eval<true>(self, a);
+        if constexpr (ForceDense) return launch_eval<true>(self, a);
+        else
+        {
+            if (!a->dedup) return launch_eval<false>(self, a);
+            if constexpr (detail::functor_unique_handles<Functor>::value) return TAD_NOT_SUPPORTED;
+            else return launch_eval<true>(self, a);
+        }
     }
 };
 

@@ -20,6 +20,8 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
+#include <map>
 #include <tuple>
 #include <utility>
 #include <vector>
@@ -135,11 +137,54 @@ struct ScalarFunction
         require_handle();
         std::vector<int64_t> handles;
         const bool identity = detail::is_identity_range(_element_range, handles);
-        using L = TermLauncher<EvalElementFunction, variable_dimension, element_valence, 0>;
-        L* launcher = new L{std::move(_eval_element)};
-        detail::check(tad_function_add_term(h, element_valence, 0, (int64_t)handles.size(),
-                                            identity ? nullptr : handles.data(), &L::launch, launcher, &L::destroy));
-        n_elements += (int64_t)handles.size();
+        add_term_impl<element_valence, false>(handles, identity, std::move(_eval_element));
+    }
+
+    // ScalarFunction.hh:80-108 / ScalarFunctionImpl.hh:134-214: each element may touch a different number of variable handles.
+    // The functor is run once on a recorder element (on the device, with the largest static valence) to find each element's
+    // valence; elements are grouped by the exact or next larger static valence and one term per non-empty group is added, in
+    // the order of the template arguments -- exactly the reference's grouping.  Within a group the slot of a variables() call
+    // is a run-time quantity, so these terms use the run-time-indexed element (dense derivative masks).  As in the reference,
+    // the projection acts on the padded k x k block while only the accessed variables are assembled.
+    template <int... ElementValences, typename ElementHandleRangeT, typename EvalElementFunction>
+    void add_elements_dynamic(const ElementHandleRangeT& _element_range, EvalElementFunction _eval_element)
+    {
+        static_assert(sizeof...(ElementValences) >= 1, "At least one element valence has to be passed.");
+        static_assert(((ElementValences >= 0) && ...), "Element valences need to be non-negative.");
+        require_handle();
+        std::vector<int> static_valences_sorted = {ElementValences...};
+        std::sort(static_valences_sorted.begin(), static_valences_sorted.end());
+        if (std::unique(static_valences_sorted.begin(), static_valences_sorted.end()) != static_valences_sorted.end())
+            throw std::runtime_error("[TinyAD-B200] Element valences passed to add_elements<..>(..) are not unique. Please pass unique element valences.");
+        constexpr int max_valence = std::max({ElementValences...});
+        std::vector<int64_t> handles;
+        const bool identity = detail::is_identity_range(_element_range, handles);
+        const int64_t n = (int64_t)handles.size();
+
+        // record: a scratch function with one term of the largest valence; its element -> handle table gives the valences
+        std::vector<int32_t> table((size_t)std::max<int64_t>(1, max_valence * n), -1);
+        {
+            tad_function rec = nullptr;
+            detail::check(tad_function_create(variable_dimension, (int64_t)variable_handles.size(), 0, settings.device, &rec));
+            using R = TermLauncher<EvalElementFunction, variable_dimension, max_valence, 0, true>;
+            R* launcher = new R{_eval_element};
+            const int s = tad_function_add_term(rec, max_valence, 0, n, identity ? nullptr : handles.data(), &R::launch, launcher, &R::destroy);
+            if (s == TAD_OK && n > 0) detail::check(tad_function_term_table(rec, 0, table.data()));
+            tad_function_destroy(rec);
+            if (s == TAD_TOO_MANY_VARIABLES)
+                throw std::runtime_error("[TinyAD-B200] Element valence exceeds maximum static valence passed to add_elements<..>(..). "
+                                         "Please pass a large-enough static valence as template argument.");
+            detail::check(s);
+        }
+        std::map<int, std::vector<int64_t>> groups;
+        for (int64_t e = 0; e < n; ++e)
+        {
+            int valence = 0;
+            for (int j = 0; j < max_valence; ++j) valence += table[(size_t)(j * n + e)] >= 0 ? 1 : 0;
+            const auto it = std::lower_bound(static_valences_sorted.begin(), static_valences_sorted.end(), valence);
+            groups[*it].push_back(handles[(size_t)e]);  // it != end(): valence <= max_valence was checked by the record pass
+        }
+        (add_dynamic_group<ElementValences>(groups, _eval_element), ...);
     }
 
     // ScalarFunctionImpl.hh:216-254
@@ -280,6 +325,22 @@ struct ScalarFunction
     std::vector<VariableHandleT> variable_handles;  // :230
 
 private:
+    template <int element_valence, bool force_dense, typename EvalElementFunction>
+    void add_term_impl(const std::vector<int64_t>& handles, bool identity, EvalElementFunction _eval_element)
+    {
+        using L = TermLauncher<EvalElementFunction, variable_dimension, element_valence, 0, force_dense>;
+        L* launcher = new L{std::move(_eval_element)};
+        detail::check(tad_function_add_term(h, element_valence, 0, (int64_t)handles.size(), identity ? nullptr : handles.data(), &L::launch,
+                                            launcher, &L::destroy));
+        n_elements += (int64_t)handles.size();
+    }
+    template <int element_valence, typename EvalElementFunction>
+    void add_dynamic_group(const std::map<int, std::vector<int64_t>>& groups, const EvalElementFunction& _eval_element)
+    {
+        const auto it = groups.find(element_valence);
+        if (it == groups.end()) return;
+        add_term_impl<element_valence, true>(it->second, false, _eval_element);
+    }
     void require_handle() const
     {
         if (!h) throw std::runtime_error("[TinyAD-B200] function has no variables (default-constructed or moved-from)");
