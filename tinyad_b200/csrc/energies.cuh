@@ -4,6 +4,7 @@
 
 #include <TinyAD/ScalarFunction.hh>
 #include <TinyAD/VectorFunction.hh>
+#include <TinyAD/Operations/SVD.hh>
 
 #ifndef TADX_TET_PARTS
 #define TADX_TET_PARTS 4
@@ -259,6 +260,7 @@ enum ScalarCase
     SC_IADD, SC_ISUB, SC_IMUL, SC_IDIV, SC_IADD_S, SC_ISUB_S, SC_IMUL_S, SC_IDIV_S, SC_MIN, SC_MAX, SC_CLAMP, SC_QUADRATIC, SC_ATAN2_1,
     SC_SQR_POW_MUL, SC_ATAN2_CONST, SC_ATAN2_2, SC_HYPOT, SC_DIV2D, SC_DIV2D_2, SC_PMMD_2D, SC_SPHERE,
     SC_C_MUL, SC_C_MUL_D, SC_C_D_MUL, SC_C_DIV, SC_C_DIV_D, SC_C_ADD, SC_C_SUB, SC_C_SQR, SC_C_CONJ, SC_C_ABS, SC_C_ARG, SC_SYMM_DIRICH6,
+    SC_SVD2, SC_CLOSEST_ORTHOGONAL2,
     SC_COUNT
 };
 
@@ -392,6 +394,28 @@ TINYAD_HD inline int scalar_case_run(int id, const double* p, double* out)
         A6 E = J.squaredNorm() + J.inverse().squaredNorm();
         sc_put(E, out);
         return 1;
+    }
+    if (id == SC_SVD2 || id == SC_CLOSEST_ORTHOGONAL2)  // tests/SVDTest.cc:9-97, Scalar<4>: A = [[p0, p1], [p2, p3]]
+    {
+        using A4 = Scalar<4, true>;
+        Mat<A4, 2, 2> A;
+        A(0, 0) = A4(p[0], 0); A(0, 1) = A4(p[1], 1); A(1, 0) = A4(p[2], 2); A(1, 1) = A4(p[3], 3);
+        Mat<A4, 2, 2> R;
+        if (id == SC_SVD2)
+        {
+            Mat<A4, 2, 2> U, V;
+            Vec<A4, 2> S;
+            svd(A, U, S, V);
+            Mat<A4, 2, 2> US;
+            US(0, 0) = U(0, 0) * S[0]; US(0, 1) = U(0, 1) * S[1]; US(1, 0) = U(1, 0) * S[0]; US(1, 1) = U(1, 1) * S[1];
+            R = US * V.transpose();  // U * S.asDiagonal() * V^T
+            sc_put(R(0, 0), out); sc_put(R(0, 1), out); sc_put(R(1, 0), out); sc_put(R(1, 1), out);
+            sc_put(S[0], out); sc_put(S[1], out);
+            return 6;
+        }
+        R = closest_orthogonal(A);
+        sc_put(R(0, 0), out); sc_put(R(0, 1), out); sc_put(R(1, 0), out); sc_put(R(1, 1), out);
+        return 4;
     }
     return -1;
 }
