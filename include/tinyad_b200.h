@@ -78,7 +78,7 @@ typedef struct tad_function_s* tad_function;
 
 /* Options (tad_function_set_option). */
 #define TAD_OPT_ASSEMBLY 1      /* 0 = FP64 atomics (default), 1 = deterministic gather in element order */
-#define TAD_OPT_CHUNK_ELEMENTS 2 /* max elements per element-kernel launch (staging size); 0 = whole term */
+#define TAD_OPT_CHUNK_ELEMENTS 2 /* reserved: max elements per element-kernel launch; the whole term is staged today (7.4 GB at 10M tets) */
 #define TAD_OPT_PROJECTION 3    /* 0 = low-rank update via selected eigenvectors (default), 1 = full eigendecomposition */
 #define TAD_ASSEMBLY_ATOMIC 0
 #define TAD_ASSEMBLY_GATHER 1
