@@ -892,8 +892,13 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
     {
         const double* rp = sc.R + e;
         const double* wp = sc.W + e;
+        // scratch of proj_apply in shared memory: [slot][thread of the block], conflict-free
+        extern __shared__ double casm_tmp[];
+        double* tp = casm_tmp + threadIdx.x;
+        const int bd = blockDim.x;
         TinyAD::detail::proj_apply<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
-                                      [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { acc[s] = v; }, eps);
+                                      [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { acc[s] = v; }, eps,
+                                      [&](int i, double v) { tp[i * bd] = v; }, [&](int i) { return tp[i * bd]; });
     }
     else
     {
@@ -972,13 +977,23 @@ void launch_c_assemble(const Term& t, const double* grad, const double* hess, in
     // bound by the latency of its load phases, so the extra warps pay (C2: 1.18 -> 1.08 ms; capping the registers at 170 for 12 warps: 1.21 ms).
     // TAD_CASM_BLOCK overrides (tuning knob).
     static const int bs = [] { const char* e = getenv("TAD_CASM_BLOCK"); const int v = e ? atoi(e) : 32; return (v == 32 || v == 64 || v == 128) ? v : 32; }();
-    project_c_assemble_kernel<D, N, false><<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
-                                                                                         t.rstride.p, grad, g, Hv, err, counts, split);
+    constexpr int K = D * N;
+    constexpr size_t tmp_thread = (size_t)TinyAD::detail::ProjLayout<K>::MAXV * (K + 1) * sizeof(double);  // 728 B at K = 12
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread));
+        cudaFuncSetAttribute(project_c_assemble_kernel<D, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread));
+        cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    project_c_assemble_kernel<D, N, false><<<(unsigned)((n + bs - 1) / bs), bs, bs * tmp_thread, st>>>(
+        hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p, t.rstride.p, grad, g, Hv, err, counts, split);
     if (split)
     {
         cudaStreamWaitEvent(st, side->ev_list, 0);
-        project_c_assemble_kernel<D, N, true><<<8, 128, 0, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p, t.rstride.p, grad,
-                                                                 g, Hv, err, counts, false);
+        project_c_assemble_kernel<D, N, true><<<8, 128, 128 * tmp_thread, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
+                                                                                 t.rstride.p, grad, g, Hv, err, counts, false);
     }
 }
 

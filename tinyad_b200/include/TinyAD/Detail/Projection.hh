@@ -634,23 +634,42 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
 }
 
 // Phase C: back-transform the selected eigenvectors through the reflectors and add the low-rank term to H.
-template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn>
-TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps)
+// tmp_store(slot, v) / tmp_load(slot): per-thread scratch of MAXV * (K + 1) doubles for the back-transformed vectors and their
+// weights between the two halves (the reflectors and the accumulator do not fit in registers together).  The kernels keep it
+// in SHARED memory: as a run-time indexed local array it missed L1 92 % of the time and every vector iteration waited for L2.
+// The global loads of vector jv + 1 are issued before vector jv is processed (software prefetch), for the same reason.
+template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn, class TmpStoreFn, class TmpLoadFn>
+TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps, TmpStoreFn&& tmp_store,
+                                 TmpLoadFn&& tmp_load)
 {
     using L = ProjLayout<K>;
     constexpr int H = L::H;
     const int nv = (int)load_w(0);
     const int form = (int)load_w(1);
-    double W[L::MAXV][K];
     {
         // reflectors in registers; each vector goes v = H_0 H_1 ... H_{K-3} y
         double refl[L::n_v > 0 ? L::n_v : 1], tau[L::n_refl > 0 ? L::n_refl : 1];
         static_for<L::n_v>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; refl[i] = load_r(L::off_v + i); });
         static_for<L::n_refl>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tau[i] = load_r(L::off_tau + i); });
+        double ynext[K], wnext = 0.0;
+        if (nv > 0)
+        {
+            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; ynext[i] = load_w(L::off_vec + i); });
+            wnext = load_w(L::off_wgt);
+        }
         for (int jv = 0; jv < nv; ++jv)
         {
             double y[K];
-            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = load_w(L::off_vec + jv * K + i); });
+            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = ynext[i]; });
+            const double wj = wnext;
+            if (jv + 1 < nv)
+            {
+                static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value;
+                    ynext[i] = load_w(L::off_vec + (jv + 1) * K + i);
+                });
+                wnext = load_w(L::off_wgt + jv + 1);
+            }
             static_for<L::n_refl>([&](auto kc) TINYAD_LAMBDA_INLINE {
                 constexpr int k = K - 3 - decltype(kc)::value;
                 constexpr int n = K - k - 1;
@@ -667,7 +686,8 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
                     y[k + 2 + i] = fma(-s, refl[vo + i], y[k + 2 + i]);
                 });
             });
-            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; W[jv][i] = y[i]; });
+            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tmp_store(jv * (K + 1) + i, y[i]); });
+            tmp_store(jv * (K + 1) + K, wj);
         }
     }
     double acc[H];
@@ -680,11 +700,11 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
     });
     for (int jv = 0; jv < nv; ++jv)
     {
-        const double wj = load_w(L::off_wgt + jv);
+        const double wj = tmp_load(jv * (K + 1) + K);
         double v[K], wv[K];
         static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
-            v[i] = W[jv][i];
+            v[i] = tmp_load(jv * (K + 1) + i);
             wv[i] = wj * v[i];
         });
         static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
@@ -693,6 +713,14 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
         });
     }
     static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE { constexpr int s = decltype(sc)::value; store(s, acc[s]); });
+}
+
+// with a thread-local scratch array (host; kernels without shared memory)
+template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn>
+TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps)
+{
+    double tmp[ProjLayout<K>::MAXV * (K + 1)];
+    proj_apply<K>(load_r, load_w, load, store, eps, [&](int i, double v) { tmp[i] = v; }, [&](int i) { return tmp[i]; });
 }
 
 // All three phases on one element through local scratch (host tests; the kernels run the phases separately).
