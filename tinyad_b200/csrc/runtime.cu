@@ -898,7 +898,25 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
         const int bd = blockDim.x;
         TinyAD::detail::proj_apply<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
                                       [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { acc[s] = v; }, eps,
-                                      [&](int i, double v) { tp[i * bd] = v; }, [&](int i) { return tp[i * bd]; });
+                                      [&](int i, double v) { tp[i * bd] = v; }, [&](int i) { return tp[i * bd]; },
+                                      [&](int nv) {
+                                          // asynchronous global -> shared copies of the nv vectors and their weights (cp.async, 8 bytes
+                                          // each): no registers, and they overlap the reflector loads that follow
+                                          using L = TinyAD::detail::ProjLayout<K>;
+                                          const unsigned dst0 = (unsigned)__cvta_generic_to_shared(tp);
+                                          for (int jv = 0; jv < nv; ++jv)
+                                          {
+#pragma unroll
+                                              for (int i = 0; i <= K; ++i)
+                                              {
+                                                  const double* src = wp + (int64_t)(i < K ? L::off_vec + jv * K + i : L::off_wgt + jv) * stride;
+                                                  const unsigned dst = dst0 + (unsigned)((jv * (K + 1) + i) * bd) * 8u;
+                                                  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                                              }
+                                          }
+                                          return true;
+                                      },
+                                      [&] { asm volatile("cp.async.wait_all;" ::: "memory"); });
     }
     else
     {

@@ -638,21 +638,26 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
 // weights between the two halves (the reflectors and the accumulator do not fit in registers together).  The kernels keep it
 // in SHARED memory: as a run-time indexed local array it missed L1 92 % of the time and every vector iteration waited for L2.
 // The global loads of vector jv + 1 are issued before vector jv is processed (software prefetch), for the same reason.
-template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn, class TmpStoreFn, class TmpLoadFn>
+// preload(nv): optional asynchronous copy of the nv vectors and weights from W straight into the scratch (slot jv (K+1) + i <-
+// W[off_vec + jv K + i], slot jv (K+1) + K <- W[off_wgt + jv]); returns true if it did so.  preload_wait() completes it.  The
+// fused kernel uses cp.async here, so these loads overlap the reflector loads and cost no registers.
+template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn, class TmpStoreFn, class TmpLoadFn, class PreloadFn, class PreloadWaitFn>
 TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps, TmpStoreFn&& tmp_store,
-                                 TmpLoadFn&& tmp_load)
+                                 TmpLoadFn&& tmp_load, PreloadFn&& preload, PreloadWaitFn&& preload_wait)
 {
     using L = ProjLayout<K>;
     constexpr int H = L::H;
     const int nv = (int)load_w(0);
     const int form = (int)load_w(1);
+    const bool preloaded = preload(nv);
     {
         // reflectors in registers; each vector goes v = H_0 H_1 ... H_{K-3} y
         double refl[L::n_v > 0 ? L::n_v : 1], tau[L::n_refl > 0 ? L::n_refl : 1];
         static_for<L::n_v>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; refl[i] = load_r(L::off_v + i); });
         static_for<L::n_refl>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tau[i] = load_r(L::off_tau + i); });
         double ynext[K], wnext = 0.0;
-        if (nv > 0)
+        if (preloaded) preload_wait();
+        else if (nv > 0)
         {
             static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; ynext[i] = load_w(L::off_vec + i); });
             wnext = load_w(L::off_wgt);
@@ -660,15 +665,20 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
         for (int jv = 0; jv < nv; ++jv)
         {
             double y[K];
-            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = ynext[i]; });
-            const double wj = wnext;
-            if (jv + 1 < nv)
+            double wj = wnext;
+            if (preloaded)
+                static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = tmp_load(jv * (K + 1) + i); });
+            else
             {
-                static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
-                    constexpr int i = decltype(ic)::value;
-                    ynext[i] = load_w(L::off_vec + (jv + 1) * K + i);
-                });
-                wnext = load_w(L::off_wgt + jv + 1);
+                static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = ynext[i]; });
+                if (jv + 1 < nv)
+                {
+                    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                        constexpr int i = decltype(ic)::value;
+                        ynext[i] = load_w(L::off_vec + (jv + 1) * K + i);
+                    });
+                    wnext = load_w(L::off_wgt + jv + 1);
+                }
             }
             static_for<L::n_refl>([&](auto kc) TINYAD_LAMBDA_INLINE {
                 constexpr int k = K - 3 - decltype(kc)::value;
@@ -687,7 +697,7 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
                 });
             });
             static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tmp_store(jv * (K + 1) + i, y[i]); });
-            tmp_store(jv * (K + 1) + K, wj);
+            if (!preloaded) tmp_store(jv * (K + 1) + K, wj);
         }
     }
     double acc[H];
@@ -720,7 +730,8 @@ template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn>
 TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps)
 {
     double tmp[ProjLayout<K>::MAXV * (K + 1)];
-    proj_apply<K>(load_r, load_w, load, store, eps, [&](int i, double v) { tmp[i] = v; }, [&](int i) { return tmp[i]; });
+    proj_apply<K>(load_r, load_w, load, store, eps, [&](int i, double v) { tmp[i] = v; }, [&](int i) { return tmp[i]; },
+                  [](int) { return false; }, [] {});
 }
 
 // All three phases on one element through local scratch (host tests; the kernels run the phases separately).
