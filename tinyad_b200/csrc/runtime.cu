@@ -572,25 +572,50 @@ __global__ void __launch_bounds__(128) project_kernel_b1(int64_t n, int64_t stri
     if (code == TinyAD::detail::PROJ_FALLBACK) sc.codes[el] = code;
 }
 
-// B2: selection + inverse iteration
+// B2: selection + inverse iteration.  The sorted eigenvalues and the first B2_SMEM_VECS eigenvectors of every thread live in
+// shared memory ([slot][thread], conflict-free): they are re-read at run-time indices / by every later vector's two
+// orthogonalisation passes, and as global re-reads (L2 round trips of data the thread has just written) those loads were
+// ~25 % of the kernel's stall samples.
+constexpr int B2_SMEM_VECS = 4;
+template <int K>
+constexpr size_t b2_smem_bytes(int threads) { return (size_t)(K + B2_SMEM_VECS * K) * threads * sizeof(double); }
+
 template <int K, int MINB>
 __global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc)
 {
+    using L = TinyAD::detail::ProjLayout<K>;
+    extern __shared__ double b2_smem[];
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
     int code = sc.codes[el];
     if (code == TinyAD::detail::PROJ_DOMINANT) return;
     double* rp = sc.R + el;
     double* wp = sc.W + el;
+    const int bd = blockDim.x;
+    double* sl = b2_smem + threadIdx.x;        // eigenvalues: slot i
+    double* sv = sl + (size_t)K * bd;          // vectors: slot jv * K + q, jv < B2_SMEM_VECS
     if (code != TinyAD::detail::PROJ_FALLBACK)
-        code = TinyAD::detail::proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; },
-                                                      [&](int i, double v) { rp[(int64_t)i * stride] = v; },
-                                                      [&](int i, double v) { wp[(int64_t)i * stride] = v; },
-                                                      [&](int jv, double (&v)[K]) {
-                                                          const double* p = wp + (int64_t)(TinyAD::detail::ProjLayout<K>::off_vec + jv * K) * stride;
+        code = TinyAD::detail::proj_select_vectors<K>(
+            [&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return sl[i * bd]; }, [&](int i, double v) { sl[i * bd] = v; },
+            [&](int i, double v) { wp[(int64_t)i * stride] = v; },
+            [&](int jv, int q, double v) {
+                wp[(int64_t)(L::off_vec + jv * K + q) * stride] = v;
+                if (jv < B2_SMEM_VECS) sv[(jv * K + q) * bd] = v;
+            },
+            [&](int jv, double (&v)[K]) {
+                if (jv < B2_SMEM_VECS)
+                {
 #pragma unroll
-                                                          for (int q = 0; q < K; ++q) { v[q] = *p; p += stride; }
-                                                      }, eps);
+                    for (int q = 0; q < K; ++q) v[q] = sv[(jv * K + q) * bd];
+                }
+                else
+                {
+                    const double* p = wp + (int64_t)(L::off_vec + jv * K) * stride;
+#pragma unroll
+                    for (int q = 0; q < K; ++q) { v[q] = *p; p += stride; }
+                }
+            },
+            eps);
     sc.codes[el] = code;
     if (counts) atomicAdd(&counts[0], 1ull);
     if (code == TinyAD::detail::PROJ_REBUILT && counts) atomicAdd(&counts[1], 1ull);
@@ -648,7 +673,18 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         const unsigned g = (unsigned)((n + 127) / 128);
         project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
         project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
-        project_kernel_b<K, 3><<<g, 128, 0, st>>>(n, stride, eps, counts, sc);
+        {
+            static bool b2_configured = false;
+            if (!b2_configured)
+            {
+                cudaFuncSetAttribute(project_kernel_b<K, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128));
+                cudaFuncSetAttribute(project_kernel_b<K, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                b2_configured = true;
+            }
+            // K <= 12: 3 blocks of 128 threads fit (61 KB each at K = 12); larger K: smaller blocks keep the footprint per SM
+            const int bt = K <= 12 ? 128 : 64;
+            project_kernel_b<K, 3><<<(unsigned)((n + bt - 1) / bt), bt, b2_smem_bytes<K>(bt), st>>>(n, stride, eps, counts, sc);
+        }
         // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
         double* work = scratch_d + (size_t)(L::nR + L::nW) * stride;
         if (fuse_out && side && side->stream)

@@ -403,9 +403,13 @@ TINYAD_HD TINYAD_INLINE void sort_ascending(double (&v)[K])
 // Scalar recurrences on small arrays, written as plain loops: nvcc unrolls the fixed-trip-count ones (LU, solves)
 // so those arrays live in registers.  load_w re-reads vectors already stored through store_w; the eigenvalues are read
 // back from R at run-time indices.
-// load_vec(jv, v) reads back vector jv (K entries, W[off_vec + jv K ..)) already stored through store_w.
-template <int K, class LoadRFn, class StoreLamFn, class StoreWFn, class LoadVecFn>
-TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_lam, StoreWFn&& store_w, LoadVecFn&& load_vec, const double eps)
+// Functors: load_r(i) reads R; load_lam(i) / store_lam(i, v), i < K: the eigenvalues (read unsorted from R[off_lam + i] by the
+// first load_lam calls, then rewritten sorted -- the kernel keeps the sorted copy in shared memory, they are read at run-time
+// indices); store_w(i, v) writes W; store_vec(jv, q, v) writes component q of vector jv (W[off_vec + jv K + q]) and load_vec(jv, v)
+// reads vector jv back (the kernel serves the first few vectors, the ones re-read most often, from shared memory).
+template <int K, class LoadRFn, class LoadLamFn, class StoreLamFn, class StoreWFn, class StoreVecFn, class LoadVecFn>
+TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam, StoreLamFn&& store_lam, StoreWFn&& store_w,
+                                         StoreVecFn&& store_vec, LoadVecFn&& load_vec, const double eps)
 {
     using L = ProjLayout<K>;
     constexpr double macheps = 2.220446049250313e-16;
@@ -427,7 +431,7 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
         emax = fmax(emax, fabs(e0[i]));
         dmax = fmax(dmax, fabs(d0[i]));
     }
-    auto lam_at = [&](int i) { return load_r(L::off_lam + i); };
+    auto lam_at = [&](int i) { return load_lam(i); };
     {
         // B1 leaves the eigenvalues in the order of convergence: sort ascending (odd-even transposition network on
         // registers), check them, write them back for the run-time indexed reads below
@@ -435,12 +439,12 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
         double chk = 0.0;
         static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
             constexpr int i = decltype(ic)::value;
-            lam[i] = load_r(L::off_lam + i);
+            lam[i] = load_r(L::off_lam + i);  // unsorted, from B1
             chk += fabs(lam[i]);
         });
         if (!(chk <= 1.7e308)) return PROJ_FALLBACK;  // NaN / Inf
         sort_ascending<K>(lam);
-        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; store_lam(L::off_lam + i, lam[i]); });
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; store_lam(i, lam[i]); });
     }
 
     // ---- 3. which eigenvalues move (HessianProjection.hh:71-91) ----
@@ -624,7 +628,7 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, StoreLamFn&& store_la
             }
         }
         if (!converged) return PROJ_FALLBACK;
-        for (int i = 0; i < K; ++i) store_w(L::off_vec + jv * K + i, x[i] * inv);
+        for (int i = 0; i < K; ++i) store_vec(jv, i, x[i] * inv);
         store_w(L::off_wgt + jv, wj);
         xjm = xj;
     }
@@ -744,7 +748,8 @@ TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const doubl
     if (code == PROJ_DOMINANT) return code;
     code = proj_eigenvalues<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; });
     if (code == PROJ_FALLBACK) return code;
-    code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; }, [&](int i, double v) { Wb[i] = v; },
+    code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i) { return R[L::off_lam + i]; }, [&](int i, double v) { R[L::off_lam + i] = v; },
+                                  [&](int i, double v) { Wb[i] = v; }, [&](int jv, int q, double v) { Wb[L::off_vec + jv * K + q] = v; },
                                   [&](int jv, double (&v)[K]) { for (int q = 0; q < K; ++q) v[q] = Wb[L::off_vec + jv * K + q]; }, eps);
     if (code != PROJ_REBUILT) return code;
     proj_apply<K>([&](int i) { return R[i]; }, [&](int i) { return Wb[i]; }, load, store, eps);

@@ -71,12 +71,15 @@ __global__ void __launch_bounds__(128, MINB) kb2(int64_t n, int64_t stride, doub
     if (el >= n) return;
     double* rp = R + el;
     double* wp = W + el;
-    const int code = proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i, double v) { rp[(int64_t)i * stride] = v; },
-                                            [&](int i, double v) { wp[(int64_t)i * stride] = v; }, [&](int jv, double (&v)[K]) {
-                                                          const double* p = wp + (int64_t)(TinyAD::detail::ProjLayout<K>::off_vec + jv * K) * stride;
+    const int code = proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return rp[(int64_t)(L::off_lam + i) * stride]; },
+                                            [&](int i, double v) { rp[(int64_t)(L::off_lam + i) * stride] = v; },
+                                            [&](int i, double v) { wp[(int64_t)i * stride] = v; },
+                                            [&](int jv, int q, double v) { wp[(int64_t)(L::off_vec + jv * K + q) * stride] = v; },
+                                            [&](int jv, double (&v)[K]) {
+                                                const double* p = wp + (int64_t)(L::off_vec + jv * K) * stride;
 #pragma unroll
-                                                          for (int q = 0; q < K; ++q) { v[q] = *p; p += stride; }
-                                                      }, eps);
+                                                for (int q = 0; q < K; ++q) { v[q] = *p; p += stride; }
+                                            }, eps);
     codes[el] = code;
     atomicAdd(&counts[code], 1ull);
     if (code == PROJ_REBUILT) atomicAdd(&counts[4], (unsigned long long)wp[0]);
