@@ -19,25 +19,36 @@ inline bool armijo_condition(const double _f_curr, const double _f_new, const do
     return _f_new <= _f_curr + _armijo_const * _s * dg;
 }
 
-// Host vectors; _eval is any callable double(const std::vector<double>&), e.g. the function object itself.  :26-65
+namespace detail
+{
+// Step schedule of the reference (LineSearch.hh:44-60): s_max, s_max * shrink, ... and, when s_max > 1, the value 1.0 is visited
+// exactly once at the point where the geometric sequence would jump over it.
+inline double next_line_search_step(const double s, const double shrink, const bool visit_one)
+{
+    return (visit_one && s > 1.0 && s * shrink < 1.0) ? 1.0 : s * shrink;
+}
+}  // namespace detail
+
+// Host vectors; _eval is any callable double(const std::vector<double>&), e.g. the function object itself (LineSearch.hh:26-65).
+// The directional derivative d.g is formed once (the reference re-evaluates the same dot product in every Armijo test).
 template <typename EvalFunctionT>
 std::vector<double> line_search(const std::vector<double>& _x0, const std::vector<double>& _d, const double _f, const std::vector<double>& _g,
                                 const EvalFunctionT& _eval, const double _s_max = 1.0, const double _shrink = 0.8, const int _max_iters = 64,
                                 const double _armijo_const = 1e-4)
 {
-    if (_x0.size() != _g.size()) throw std::runtime_error("[TinyAD-B200] line_search: size mismatch");
-    if (_s_max <= 0.0) throw std::runtime_error("[TinyAD-B200] Max step size not positive.");
-    const bool try_one = _s_max > 1.0;  // also try a step size of 1.0 (if valid)
-    std::vector<double> x_new = _x0;
-    double s = _s_max;
-    for (int i = 0; i < _max_iters; ++i)
+    const size_t n = _x0.size();
+    if (n != _g.size() || n != _d.size()) throw std::runtime_error("[TinyAD-B200] line_search: size mismatch");
+    if (!(_s_max > 0.0)) throw std::runtime_error("[TinyAD-B200] Max step size not positive.");
+    double slope = 0.0;
+    for (size_t q = 0; q < n; ++q) slope += _d[q] * _g[q];
+    std::vector<double> trial(n);
+    double step = _s_max;
+    for (int it = 0; it < _max_iters; ++it, step = detail::next_line_search_step(step, _shrink, _s_max > 1.0))
     {
-        for (size_t q = 0; q < _x0.size(); ++q) x_new[q] = _x0[q] + s * _d[q];
-        const double f_new = _eval(x_new);
-        if (f_new != f_new) throw std::runtime_error("[TinyAD-B200] line_search: objective is NaN");
-        if (armijo_condition(_f, f_new, s, _d, _g, _armijo_const)) return x_new;
-        if (try_one && s > 1.0 && s * _shrink < 1.0) s = 1.0;
-        else s *= _shrink;
+        for (size_t q = 0; q < n; ++q) trial[q] = _x0[q] + step * _d[q];
+        const double f_trial = _eval(trial);
+        if (f_trial != f_trial) throw std::runtime_error("[TinyAD-B200] line_search: objective is NaN");  // TINYAD_ASSERT_EQ(f_new, f_new)
+        if (f_trial <= _f + _armijo_const * step * slope) return trial;                                    // Armijo: sufficient decrease
     }
     std::printf("[TinyAD-B200] WARNING: Line search couldn't find improvement.\n");
     return _x0;
