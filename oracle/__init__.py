@@ -16,6 +16,7 @@ _LIB = None
 # term kinds (keep in sync with oracle_capi.cc)
 SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
 EDGE_DIRICHLET1D, QUADRATIC2D, REPEATED_HANDLE, TRIG_MIX2D = 5, 6, 7, 8
+ARAP2D = 12
 DYN_SUM_SQR2D, DYN_ONERING1D = 10, 11   # add_elements_dynamic; ONERING: data must have as many columns as conn
 SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
 

@@ -39,6 +39,7 @@ enum
     ORC_QUADRATIC2D = 6,         // d=2 N=1 data: sign     sign*(2x0^2+2x0x1+x1^2+x0+1)   (ScalarFunctionTest.cc:72-146)
     ORC_REPEATED_HANDLE = 7,     // d=2 N=2 accesses conn[0] twice then conn[1]             (ScalarFunctionTest.cc:153-179)
     ORC_TRIG_MIX2D = 8,          // d=2 N=2 exercises sin/cos/exp/log/sqrt/atan2/pow/hypot/tanh on 4 variables
+    ORC_ARAP2D = 12,             // d=2 N=3 data: Mr (4) w      w * |J - closest_orthogonal(J)|^2, J = M Mr^-1   (Operations/SVD.hh)
     ORC_DYN_SUM_SQR2D = 10,      // d=2 dynamic <3,1>: element e accesses handles 0..e-1, |sum|^2   (DynamicElementsTest.cc:9-33)
     ORC_DYN_ONERING1D = 11,      // d=1 dynamic <4,6,7,10>: conn = padded neighbour table (n_data columns, -1 = none)
                                  //     0.25 * sum_n (x_v - x_n)^2                                (DynamicElementsTest.cc:92-141)
@@ -161,6 +162,22 @@ void add_scalar_term(FuncT& func, const oracle_term& t)
                 T u = log(r) + sqrt(r + sqr(s)) + atan2(p[1] + 2.0, q[0] + 3.0);
                 T v = pow(r, 3) - pow(r, 1.5) + tanh(s) * data[e * nd];
                 return u * v + fabs(s - 0.1) + 2.0 / r - (1.0 - s) / 3.0;
+            });
+        break;
+    case ORC_ARAP2D:
+        if constexpr (std::is_same_v<FuncT, ScalarFunction<2>>)
+            func.template add_elements<3>(handles(t.n_elements), [=](auto& element) -> ORACLE_SCALAR_TYPE(element) {
+                using T = ORACLE_SCALAR_TYPE(element);
+                const Index e = element.handle;
+                const double* dd = data + e * nd;
+                Mat<double, 2, 2> Mr;
+                Mr(0, 0) = dd[0]; Mr(0, 1) = dd[1]; Mr(1, 0) = dd[2]; Mr(1, 1) = dd[3];
+                Vec<T, 2> a = element.variables(conn[3 * e + 0]);
+                Vec<T, 2> b = element.variables(conn[3 * e + 1]);
+                Vec<T, 2> c = element.variables(conn[3 * e + 2]);
+                Mat<T, 2, 2> J = col_mat(b - a, c - a) * Mr.inverse();
+                Mat<T, 2, 2> R = closest_orthogonal(J);
+                return (J - R).squaredNorm() * dd[4];
             });
         break;
     case ORC_DYN_SUM_SQR2D:

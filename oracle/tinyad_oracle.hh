@@ -1002,6 +1002,37 @@ struct ScalarObjectiveTerm : ScalarObjectiveTermBase
 // ---------------------------------------------------------------------------
 // ScalarFunction (ScalarFunction.hh:36-236, Detail/ScalarFunctionImpl.hh)
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Operations/SVD.hh:12-21, :70-99 -- sign() and the closed-form closest orthogonal 2x2 matrix U V^T
+// ---------------------------------------------------------------------------
+template <typename T>
+int svd_sign(const T& x)
+{
+    if (x < T(0.0)) return -1;
+    else if (x > T(0.0)) return 1;
+    else return 0;
+}
+
+template <typename T>
+Mat<T, 2, 2> closest_orthogonal(const Mat<T, 2, 2>& A)
+{
+    Mat<T, 2, 2> Su = A * A.transpose();                                        // :77
+    T phi = 0.5 * atan2(Su(0, 1) + Su(1, 0), Su(0, 0) - Su(1, 1));              // :78
+    T Cphi = cos(phi), Sphi = sin(phi);
+    Mat<T, 2, 2> U;
+    U(0, 0) = Cphi; U(0, 1) = -Sphi; U(1, 0) = Sphi; U(1, 1) = Cphi;            // :81-83
+    Mat<T, 2, 2> Sw = A.transpose() * A;                                        // :86
+    T theta = 0.5 * atan2(Sw(0, 1) + Sw(1, 0), Sw(0, 0) - Sw(1, 1));
+    T Ctheta = cos(theta), Stheta = sin(theta);
+    Mat<T, 2, 2> W;
+    W(0, 0) = Ctheta; W(0, 1) = -Stheta; W(1, 0) = Stheta; W(1, 1) = Ctheta;    // :90-92
+    Mat<T, 2, 2> S = U.transpose() * A * W;                                     // :95
+    const double c0 = (double)svd_sign(S(0, 0)), c1 = (double)svd_sign(S(1, 1));
+    Mat<T, 2, 2> V;                                                             // V = W * C.asDiagonal(), :96-97
+    V(0, 0) = W(0, 0) * c0; V(0, 1) = W(0, 1) * c1; V(1, 0) = W(1, 0) * c0; V(1, 1) = W(1, 1) * c1;
+    return U * V.transpose();                                                   // :99
+}
+
 // RecorderElement (ScalarFunctionImpl.hh:106-129): records which variable handles the functor accesses
 template <int d>
 struct RecorderElement

@@ -129,3 +129,26 @@ def test_quadratic_known_answers(torch_cuda):
     w = np.linalg.eigvalsh(Hp.reshape(2, 2))
     assert w.min() > 0.0  # ScalarFunctionTest.cc:143-146
     fn.close()
+
+
+def test_arap_with_closest_orthogonal(torch_cuda):
+    """Operations/SVD.hh (closest_orthogonal) inside an element functor, Double<6>: the 2-D ARAP energy
+    w |J - R(J)|^2 on a deformed grid; f, g, H and projected H against the oracle's restatement of Operations/SVD.hh:70-99."""
+    from tinyad_b200 import meshes
+    V, F = meshes.grid_2d(10)
+    data = meshes.tri_rest_data(V, F)
+    x = meshes.deform(V, 1.0 / 10, seed=7).reshape(-1)
+    p = Problem(2, len(V), [(tad.ARAP2D, F, data)])
+    for mode, project in ((oracle.DERIVATIVES, False), (oracle.HESSIAN_PROJ, True)):
+        ref = oracle.scalar_eval(2, len(V), p.oracle_terms(), mode, x)
+        fn = p.gpu()
+        xd = torch_cuda.from_numpy(x).cuda()
+        g = torch_cuda.empty(fn.n_vars, dtype=torch_cuda.float64, device="cuda")
+        H = torch_cuda.empty(fn.nnz, dtype=torch_cuda.float64, device="cuda")
+        f = fn.eval_with_derivatives(xd, g, H, project=project)
+        outer, inner = fn.pattern()
+        assert_pattern(outer, inner, ref)
+        assert_f(f, ref.f)
+        assert_vec(g.cpu().numpy(), ref.g)
+        assert_vec(H.cpu().numpy(), ref.values, tol=TOL_H_PROJ if project else 1e-11)
+        fn.close()

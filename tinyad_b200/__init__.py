@@ -27,6 +27,7 @@ OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION = 1, 2, 3
 # term kinds of csrc/energies.cu
 SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
 EDGE_DIRICHLET1D, QUADRATIC2D, REPEATED_HANDLE, TRIG_MIX2D, SQRT1D = 5, 6, 7, 8, 9
+ARAP2D = 12                             # w |J - closest_orthogonal(J)|^2 (Operations/SVD.hh inside an element functor)
 DYN_SUM_SQR2D, DYN_ONERING1D = 10, 11   # add_elements_dynamic (tests/DynamicElementsTest.cc)
 SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
 

@@ -54,6 +54,26 @@ struct Penalty  // data: target (d)
     }
 };
 
+struct Arap2D  // data: Mr(0,0) Mr(0,1) Mr(1,0) Mr(1,1) w;  w |J - closest_orthogonal(J)|^2 with Operations/SVD.hh on active scalars
+{
+    static constexpr bool tinyad_unique_handles = true;
+    ConnView F; DataView D;
+    template <class E>
+    TINYAD_HD auto operator()(E& element) const -> TINYAD_SCALAR_TYPE(element)
+    {
+        using T = TINYAD_SCALAR_TYPE(element);
+        const int64_t e = element.handle;
+        Mat<double, 2, 2> Mr;
+        Mr(0, 0) = D(e, 0); Mr(0, 1) = D(e, 1); Mr(1, 0) = D(e, 2); Mr(1, 1) = D(e, 3);
+        Vec<T, 2> a = element.variables(F(e, 0));
+        Vec<T, 2> b = element.variables(F(e, 1));
+        Vec<T, 2> c = element.variables(F(e, 2));
+        Mat<T, 2, 2> J = col_mat(b - a, c - a) * Mr.inverse();
+        Mat<T, 2, 2> R = closest_orthogonal(J);
+        return (J - R).squaredNorm() * D(e, 4);
+    }
+};
+
 // ---- dynamic-valence elements (add_elements_dynamic, tests/DynamicElementsTest.cc) ----
 struct DynSumSqr2D  // DynamicElementsTest.cc:9-33: element e accesses the handles 0 .. e-1
 {
