@@ -677,13 +677,14 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
             static bool b2_configured = false;
             if (!b2_configured)
             {
-                cudaFuncSetAttribute(project_kernel_b<K, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128));
-                cudaFuncSetAttribute(project_kernel_b<K, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128));
+                cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 b2_configured = true;
             }
-            // K <= 12: 3 blocks of 128 threads fit (61 KB each at K = 12); larger K: smaller blocks keep the footprint per SM
+            // 2 blocks per SM at 255 registers (no spills) beat 3 blocks at 168 registers with ~400 B of spills by 3-6 % (tools/proj_bench.cu);
+            // K <= 12: 128-thread blocks (61 KB of shared memory each at K = 12); larger K: smaller blocks keep the footprint per SM
             const int bt = K <= 12 ? 128 : 64;
-            project_kernel_b<K, 3><<<(unsigned)((n + bt - 1) / bt), bt, b2_smem_bytes<K>(bt), st>>>(n, stride, eps, counts, sc);
+            project_kernel_b<K, 2><<<(unsigned)((n + bt - 1) / bt), bt, b2_smem_bytes<K>(bt), st>>>(n, stride, eps, counts, sc);
         }
         // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
         double* work = scratch_d + (size_t)(L::nR + L::nW) * stride;
