@@ -109,7 +109,7 @@ def energies():
     global _en
     if _en is None:
         runtime()
-        so = _build.ENERGIES_SO
+        so = os.environ.get("TINYAD_ENERGIES_SO", _build.ENERGIES_SO)   # override: experiment builds of the functor library
         if not os.path.exists(so):
             raise ImportError(f"{so} is missing: run `python -m tinyad_b200.build`")
         L = ctypes.CDLL(so)

@@ -38,6 +38,12 @@ TADX_EXTERN_PART(2)
 TADX_EXTERN_PART(3)
 #endif
 #if TADX_TET_PARTS > 4
+TADX_EXTERN_PART(4)
+#endif
+#if TADX_TET_PARTS > 5
+TADX_EXTERN_PART(5)
+#endif
+#if TADX_TET_PARTS > 6
 #error "add more TADX_EXTERN_PART lines"
 #endif
 } }
