@@ -86,6 +86,5 @@ def test_newton_loops_from_four_threads_are_deterministic(torch_cuda):
     f0, x0, g0 = results[0]
     assert abs(f0 - 4.0) < 1e-12 and np.abs(g0).max() < 1e-10          # NewtonTest.cc:82-88
     for f, xx, gg in results[1:]:
-        # the element path (gather assembly) is bitwise deterministic; the PCG accumulates its dot products with atomics, so the
-        # iterates agree to solver accuracy rather than bitwise
-        assert abs(f - f0) < 1e-12 and np.abs(xx - x0).max() < 1e-9
+        # gather assembly and the PCG's fixed-order dot products make the whole loop bitwise reproducible, like the reference's
+        assert f == f0 and np.array_equal(xx, x0) and np.array_equal(gg, g0)

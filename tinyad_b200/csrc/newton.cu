@@ -10,7 +10,8 @@
 // the GPU; neither a sparse direct solver for the device nor Eigen exists in this image.  The stand-in, clearly
 // labelled as such, is a preconditioned conjugate gradient on the fixed CSR pattern: block-Jacobi preconditioner
 // (the d x d diagonal blocks of the vertex-block matrix), CSR SpMV with 8 lanes per row, all CG scalars kept on
-// the device (no host synchronisation inside an iteration; the residual is read back every few iterations).
+// the device (no host synchronisation inside an iteration; the residual is read back every few iterations).  Dot products
+// are reduced in a fixed order (block partials + one finishing block), so the Newton solve is bitwise reproducible.
 // It is written against the public C ABI only (pattern_device / get_stream / eval), so it is independent of runtime.cu.
 #include <cuda_runtime.h>
 
@@ -153,7 +154,24 @@ __global__ void __launch_bounds__(256) spmv_dot(int64_t n, const int32_t* __rest
         contrib = pr * acc;
     }
     const double s = block_sum(contrib);
-    if (threadIdx.x == 0) atomicAdd(pAp, s);
+    if (threadIdx.x == 0) pAp[blockIdx.x] = s;  // block partial; finish_dots adds the partials in a fixed order (deterministic)
+}
+
+// Adds the block partials of up to two dot products in a fixed order: out_a = sum part_a[0..n_a), out_b = sum part_b[0..n_b).
+// One block; every thread accumulates a strided subsequence, then a fixed-shape tree -- the same order in every run, so the whole
+// solve is bitwise reproducible (the reference's direct solve is; tests/NewtonTest.cc:97-111 relies on it).
+__global__ void __launch_bounds__(256) finish_dots(const double* part_a, int n_a, double* out_a, const double* part_b, int n_b, double* out_b)
+{
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n_a; i += blockDim.x) a += part_a[i];
+    for (int i = threadIdx.x; i < n_b; i += blockDim.x) b += part_b[i];
+    const double ta = block_sum(a);
+    const double tb = block_sum(b);
+    if (threadIdx.x == 0)
+    {
+        *out_a = ta;
+        if (out_b) *out_b = tb;
+    }
 }
 
 // z = Minv r for block row v (D rows)
@@ -193,7 +211,7 @@ __global__ void __launch_bounds__(256) pcg_init(int64_t n_blocks, const double* 
     }
     const double t1 = block_sum(s_rz);
     const double t2 = block_sum(s_rr);
-    if (threadIdx.x == 0) { atomicAdd(rz, t1); atomicAdd(rr, t2); }
+    if (threadIdx.x == 0) { rz[blockIdx.x] = t1; rr[blockIdx.x] = t2; }  // block partials, see finish_dots
 }
 
 // alpha = rz_k / pAp_k; x += alpha p; r -= alpha y; z = Minv r; rz_{k+1} += r.z; rr_{k+1} += r.r
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(256) pcg_update_xr(int64_t n_blocks, const dou
     }
     const double t1 = block_sum(s_rz);
     const double t2 = block_sum(s_rr);
-    if (threadIdx.x == 0) { atomicAdd(rz_next, t1); atomicAdd(rr_next, t2); }
+    if (threadIdx.x == 0) { rz_next[blockIdx.x] = t1; rr_next[blockIdx.x] = t2; }  // block partials, see finish_dots
 }
 
 // beta = rz_{k+1} / rz_k; p = z + beta p
@@ -287,9 +305,11 @@ struct SymCsrOp
     const int32_t *outer, *inner;
     const double* vals;
     double w;
-    int apply(const double* p, double* y, double* pAp, cudaStream_t st) const
+    int dot_blocks() const { return (int)blocks_for(n * 8, 256); }
+    // y = (A + w I) p; pAp_part[dot_blocks()] receives the block partials of p.y
+    int apply(const double* p, double* y, double* pAp_part, cudaStream_t st) const
     {
-        spmv_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, w, p, y, pAp);
+        spmv_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, w, p, y, pAp_part);
         return TAD_OK;
     }
     template <int D>
@@ -337,7 +357,7 @@ __global__ void __launch_bounds__(256) csc_gather_dot(int64_t n_cols, const int3
     if (pAp)
     {
         const double s = block_sum(contrib);
-        if (threadIdx.x == 0) atomicAdd(pAp, s);
+        if (threadIdx.x == 0) pAp[blockIdx.x] = s;  // block partial, see finish_dots
     }
 }
 
@@ -360,11 +380,13 @@ struct NormalOp
     const double* vals;
     double w;
     double* y_out;  // n_out doubles of scratch
-    int apply(const double* p, double* y, double* pAp, cudaStream_t st) const
+    int dot_blocks() const { return (int)blocks_for(n * 8, 256); }
+    // (the scatter J p accumulates with atomics: the Gauss-Newton solve is not bitwise reproducible, unlike the Newton solve)
+    int apply(const double* p, double* y, double* pAp_part, cudaStream_t st) const
     {
         if (cudaMemsetAsync(y_out, 0, (size_t)n_out * sizeof(double), st) != cudaSuccess) return fail(TAD_CUDA_ERROR, "memset failed");
         csc_scatter<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, p, y_out);
-        csc_gather_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, y_out, w, p, y, pAp);
+        csc_gather_dot<<<blocks_for(n * 8, 256), 256, 0, st>>>(n, outer, inner, vals, y_out, w, p, y, pAp_part);
         return TAD_OK;
     }
     template <int D>
@@ -397,9 +419,17 @@ int pcg_run(const Op& op, const double* b, double scale, double* x, double rel_t
     double* rz = scal.as<double>();
     double* rr = rz + slots;
     double* pAp = rr + slots;
+    // block partials of the dot products (summed in a fixed order by finish_dots: deterministic)
+    const int nbv = (int)blocks_for(nb, 256), nbs = op.dot_blocks();
+    Buf parts;
+    NT_CUDA(parts.alloc((size_t)(2 * nbv + nbs) * sizeof(double)));
+    double* part_rz = parts.as<double>();
+    double* part_rr = part_rz + nbv;
+    double* part_pAp = part_rr + nbv;
     int s_ = op.template preconditioner<D>(minv.as<double>(), st);
     if (s_ != TAD_OK) return s_;
-    pcg_init<D><<<blocks_for(nb, 256), 256, 0, st>>>(nb, b, scale, minv.as<double>(), x, r.as<double>(), z.as<double>(), p.as<double>(), rz, rr);
+    pcg_init<D><<<nbv, 256, 0, st>>>(nb, b, scale, minv.as<double>(), x, r.as<double>(), z.as<double>(), p.as<double>(), part_rz, part_rr);
+    finish_dots<<<1, 256, 0, st>>>(part_rz, nbv, rz, part_rr, nbv, rr);
     double rr0 = 0.0;
     NT_CUDA(cudaMemcpyAsync(&rr0, rr, sizeof(double), cudaMemcpyDeviceToHost, st));
     NT_CUDA(cudaStreamSynchronize(st));
@@ -412,10 +442,12 @@ int pcg_run(const Op& op, const double* b, double scale, double* x, double rel_t
         const int check_every = 8;
         while (k < max_iters)
         {
-            s_ = op.apply(p.as<double>(), y.as<double>(), pAp + k, st);
+            s_ = op.apply(p.as<double>(), y.as<double>(), part_pAp, st);
             if (s_ != TAD_OK) return s_;
-            pcg_update_xr<D><<<blocks_for(nb, 256), 256, 0, st>>>(nb, minv.as<double>(), p.as<double>(), y.as<double>(), x, r.as<double>(),
-                                                                  z.as<double>(), rz + k, pAp + k, rz + k + 1, rr + k + 1, flag.as<int>());
+            finish_dots<<<1, 256, 0, st>>>(part_pAp, nbs, pAp + k, nullptr, 0, nullptr);
+            pcg_update_xr<D><<<nbv, 256, 0, st>>>(nb, minv.as<double>(), p.as<double>(), y.as<double>(), x, r.as<double>(), z.as<double>(), rz + k,
+                                                  pAp + k, part_rz, part_rr, flag.as<int>());
+            finish_dots<<<1, 256, 0, st>>>(part_rz, nbv, rz + k + 1, part_rr, nbv, rr + k + 1);
             pcg_update_p<<<blocks_for(n, 256), 256, 0, st>>>(n, z.as<double>(), p.as<double>(), rz + k, rz + k + 1);
             ++k;
             if (k % check_every == 0 || k == max_iters || k <= 2)
