@@ -432,8 +432,8 @@ def main():
             achieved = dom_flops * n_el / dom_s / 1e12
             roof = {"bound": "fp64", "kernel": dominant, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak}
         # dram__bytes_read + dram__bytes_write of the projection kernels (A + B1 + B2) from the ncu --set full capture in
-        # profiles/r01_v2_ncu_full_hot_kernels.csv (C2 workload; per step = per launch of each of the three kernels)
-        roof["traffic"] = 2.70e9 if (args.workload == "c2" and dominant == "projection") else None
+        # profiles/r01_v5_ncu_full_hot_kernels.csv (C2 workload; per step = per launch of each of the three kernels)
+        roof["traffic"] = 2.48e9 if (args.workload == "c2" and dominant == "projection") else None
         roof["peak_source"] = "FP64: DFMA-chain microbenchmark run in this process (measured); HBM: MEASURED_PEAKS.json" if peaks else "HBM fallback 6650 GB/s"
         step_tflops = flops_el * n_el / t_step / 1e12
         roof["whole_step"] = {"fp64_tflops": step_tflops, "frac_of_fp64_peak": step_tflops / fp64_peak,
