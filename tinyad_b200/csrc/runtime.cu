@@ -42,6 +42,21 @@ int fail(int status, const std::string& msg)
     return status;
 }
 
+// Function attributes (dynamic shared-memory opt-in, carve-out) are per device: true the first time a call site runs on the
+// current device.  (One flag array per call site; processes normally drive one GPU, but nothing here assumes it.)
+struct PerDeviceOnce
+{
+    bool done[64] = {};
+    bool first()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 #define TAD_CUDA(expr)                                                                                   \
     do                                                                                                   \
     {                                                                                                    \
@@ -654,12 +669,11 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
 {
     using L = TinyAD::detail::ProjLayout<K>;
     constexpr size_t smem = (size_t)ProjSmem<K>::doubles_per_warp * sizeof(double);
-    static bool configured = false;
-    if (!configured)
+    static PerDeviceOnce configured;
+    if (configured.first())
     {
         if (cudaFuncSetAttribute(project_kernel_full<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel");
-        configured = true;
     }
     if (full_only)
         project_kernel_full<K><<<(unsigned)((n + 31) / 32), 32, smem, st>>>(hess, n, stride, eps, counts);
@@ -674,12 +688,11 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
         project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
         {
-            static bool b2_configured = false;
-            if (!b2_configured)
+            static PerDeviceOnce b2_configured;
+            if (b2_configured.first())
             {
                 cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128));
                 cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                b2_configured = true;
             }
             // 2 blocks per SM at 255 registers (no spills) beat 3 blocks at 168 registers with ~400 B of spills by 3-6 % (tools/proj_bench.cu);
             // K <= 12: 128-thread blocks (61 KB of shared memory each at K = 12); larger K: smaller blocks keep the footprint per SM
@@ -1034,13 +1047,12 @@ void launch_c_assemble(const Term& t, const double* grad, const double* hess, in
     static const int bs = [] { const char* e = getenv("TAD_CASM_BLOCK"); const int v = e ? atoi(e) : 32; return (v == 32 || v == 64 || v == 128) ? v : 32; }();
     constexpr int K = D * N;
     constexpr size_t tmp_thread = (size_t)TinyAD::detail::ProjLayout<K>::MAXV * (K + 1) * sizeof(double);  // 728 B at K = 12
-    static bool configured = false;
-    if (!configured)
+    static PerDeviceOnce configured;
+    if (configured.first())
     {
         cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread));
         cudaFuncSetAttribute(project_c_assemble_kernel<D, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread));
         cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     project_c_assemble_kernel<D, N, false><<<(unsigned)((n + bs - 1) / bs), bs, bs * tmp_thread, st>>>(
         hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p, t.rstride.p, grad, g, Hv, err, counts, split);

@@ -111,7 +111,9 @@ int main(int argc, char** argv)
     cudaMalloc(&W, sizeof(double) * L::nW * stride);
     cudaMalloc(&codes, sizeof(int) * stride);
     cudaMalloc(&counts, 8 * sizeof(unsigned long long));
+    const int ba = argc > 3 ? atoi(argv[3]) : 128, bb1 = argc > 4 ? atoi(argv[4]) : 128, bb2 = argc > 5 ? atoi(argv[5]) : 128;  // block sizes
     const unsigned g = (unsigned)((n + 127) / 128);
+    auto grid = [&](int b) { return (unsigned)((n + b - 1) / b); };
     gen<<<g, 128>>>(n, stride, h0, shift);
     cudaEvent_t ev[6];
     for (auto& e : ev) cudaEventCreate(&e);
@@ -122,11 +124,11 @@ int main(int argc, char** argv)
         cudaMemcpy(hess, h0, sizeof(double) * L::H * stride, cudaMemcpyDeviceToDevice);
         cudaMemset(counts, 0, 8 * sizeof(unsigned long long));
         cudaEventRecord(ev[0]);
-        ka<<<g, 128>>>(hess, n, stride, eps, R, codes);
+        ka<<<grid(ba), ba>>>(hess, n, stride, eps, R, codes);
         cudaEventRecord(ev[1]);
-        kb1<<<g, 128>>>(n, stride, R, codes);
+        kb1<<<grid(bb1), bb1>>>(n, stride, R, codes);
         cudaEventRecord(ev[2]);
-        kb2<<<g, 128>>>(n, stride, eps, R, W, codes, counts);
+        kb2<<<grid(bb2), bb2>>>(n, stride, eps, R, W, codes, counts);
         cudaEventRecord(ev[3]);
         kc<<<g, 128>>>(hess, n, stride, eps, R, W, codes);
         cudaEventRecord(ev[4]);
