@@ -81,16 +81,17 @@ def _worker(rank, world, port, kind, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["tri", "tet"])
-def test_halo_exchange_world2(kind):
-    world = 2
+@pytest.mark.parametrize("kind,world", [("tri", 2), ("tet", 2), ("tet", 3)])
+def test_halo_exchange(kind, world):
+    """world 2: one interface; world 3: the middle rank owns one interface and sends the other (two neighbours)."""
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 500) + (7 if kind == "tet" else 0)
+    port = 29500 + (os.getpid() % 500) + (7 if kind == "tet" else 0) + 13 * world
     mp.spawn(_worker, args=(world, port, kind, ret), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         ok, n_owned, halo = ret[r]
         assert ok, f"rank {r}"
         assert n_owned > 0
-    assert ret[1][2] > 0 and ret[0][2] == 0       # rank 1 sends its halo rows to rank 0 (lowest rank owns the interface)
+    # every rank but the first sends its lower interface rows to the rank below (the lowest rank touching a vertex owns it)
+    assert ret[0][2] == 0 and all(ret[r][2] > 0 for r in range(1, world))
