@@ -615,7 +615,11 @@ inline void sym_eig_jacobi(int k, const double* a_in, double* w, double* V)
         for (int i = 0; i < k; ++i)
             for (int j = 0; j < k; ++j)
                 (i == j ? diag : off) += A[i * k + j] * A[i * k + j];
-        if (off == 0.0 || off <= 1e-36 * diag) break;
+        // converged when the off-diagonal Frobenius norm is below machine epsilon times the norm of the matrix (eigenvalue error
+        // <= off^2 / gap).  A stricter test never fires for the element Hessians of the benchmark: their three-dimensional null
+        // space leaves rounding noise of ~1e-17 |A| off the diagonal, and the solver would burn all 100 sweeps on every element
+        // (that made the CPU baseline ~6x slower than the algorithm it stands for).
+        if (off == 0.0 || off <= 4.9e-32 * (diag + off)) break;
         for (int p = 0; p < k - 1; ++p)
             for (int q = p + 1; q < k; ++q)
             {
