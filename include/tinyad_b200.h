@@ -34,7 +34,11 @@ typedef enum tad_status
     TAD_INDEX_OUT_OF_RANGE = 5,    /* variable handle outside [0, n_handles) (Element.hh:159-170) */
     TAD_NOT_SUPPORTED = 6,
     TAD_OUT_OF_MEMORY = 7,
-    TAD_SOLVER_FAILED = 8          /* "Linear solve failed." (Utils/NewtonDirection.hh:43-44) */
+    TAD_SOLVER_FAILED = 8,         /* "Linear solve failed." (Utils/NewtonDirection.hh:43-44) */
+    TAD_PATTERN_MISMATCH = 9,      /* an element requested other variable handles at evaluation time than when it was added: the
+                                      fixed pattern (recorded once; the reference rediscovers it at every evaluation,
+                                      Element.hh:208-260) does not cover this x.  SURVEY.md App. E 3 */
+    TAD_COMM_ERROR = 10            /* NCCL failure in the multi-GPU exchange */
 } tad_status;
 
 /* What an element kernel launch computes. */
@@ -46,12 +50,17 @@ typedef enum tad_mode
     TAD_MODE_SECOND = 3   /* Scalar<k,true>      (ScalarObjectiveTerm.hh:224-278) */
 } tad_mode;
 
-/* Arguments of one element-kernel launch.  All pointers are device pointers.  The per-element
- * outputs are written structure-of-arrays with leading dimension `stride` (>= n_elements):
- *   val [m * stride + e]                       m < max(1, outputs_per_element)
- *   grad[(m * k + i) * stride + e]             i < k = d * valence
- *   hess[s * stride + e]                       s < k(k+1)/2, tile order (Detail/HessLayout.hh), scalar terms only
- *   rec_handles[j * stride + e], rec_counts[e] j < valence, -1 = unused            (TAD_MODE_RECORD)
+/* Arguments of one element-kernel launch.  All pointers are device pointers.  A launch covers the element SLAB
+ * [e_begin, e_begin + n_elements) of its term (TAD_OPT_CHUNK_ELEMENTS); the per-element outputs are written
+ * structure-of-arrays, indexed by the position i = e - e_begin inside the slab, with leading dimension `stride`
+ * (>= n_elements):
+ *   val [m * stride + i]                       m < max(1, outputs_per_element)
+ *   grad[(m * k + i') * stride + i]            i' < k = d * valence
+ *   hess[s * stride + i]                       s < k(k+1)/2, tile order (Detail/HessLayout.hh), scalar terms only
+ * The recorded element -> handle table is indexed by the element itself with leading dimension `rec_stride`:
+ *   rec_handles[j * rec_stride + e], rec_counts[e]   j < valence, -1 = unused
+ * It is written by TAD_MODE_RECORD and read back by the other modes, which check that the functor requests the same
+ * handles in the same order as recorded (else TAD_PATTERN_MISMATCH).
  */
 typedef struct tad_launch_args
 {
@@ -69,6 +78,9 @@ typedef struct tad_launch_args
     int32_t* rec_counts;
     int32_t* error_flags;       /* device int32[8], OR-ed: bit per tad_status */
     void* stream;               /* cudaStream_t */
+    int64_t e_begin;            /* first element of the slab */
+    int64_t rec_stride;         /* leading dimension of rec_handles */
+    int64_t* launch_counter;    /* HOST counter (may be NULL): the launcher adds the number of kernels it launched */
 } tad_launch_args;
 
 /* Launches the element kernel of one term; returns a tad_status (TAD_CUDA_ERROR on launch failure). */
@@ -78,8 +90,13 @@ typedef struct tad_function_s* tad_function;
 
 /* Options (tad_function_set_option). */
 #define TAD_OPT_ASSEMBLY 1      /* 0 = FP64 atomics (default), 1 = deterministic gather in element order */
-#define TAD_OPT_CHUNK_ELEMENTS 2 /* reserved: max elements per element-kernel launch; the whole term is staged today (7.4 GB at 10M tets) */
+#define TAD_OPT_CHUNK_ELEMENTS 2 /* elements per slab (rounded up to a multiple of 256): a term is evaluated, projected and assembled slab
+                                    by slab, so staging + projection scratch are bounded by `lanes` slabs (2.3 KB per tet) instead of the
+                                    whole term, consecutive slabs overlap on different streams, and the host-buffer entry points copy
+                                    finished CSR rows to the host while later slabs are still being assembled.
+                                    0 = default (524288 for the device-pointer entry points, 131072 for the host-buffer ones), < 0 = whole term in one slab.  Gather assembly always stages whole terms. */
 #define TAD_OPT_PROJECTION 3    /* 0 = low-rank update via selected eigenvectors (default), 1 = full eigendecomposition */
+#define TAD_OPT_LANES 4         /* number of slabs in flight (1..4, default 2) */
 #define TAD_ASSEMBLY_ATOMIC 0
 #define TAD_ASSEMBLY_GATHER 1
 
@@ -91,7 +108,15 @@ int tad_device_count(int* count);
 int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector_function, int device, tad_function* out);
 void tad_function_destroy(tad_function f);
 int tad_function_set_option(tad_function f, int option, int64_t value);
+/* Stream contract of the device-pointer entry points (tad_eval*, tad_veval*, tad_newton_direction, tad_line_search ...): the
+ * work runs on the function's own non-blocking streams (tad_function_get_stream returns the main one) and is COMPLETE when
+ * the call returns (the call synchronises), so outputs may be consumed from any stream afterwards.  Inputs (x_dev, g_dev,
+ * H_values_dev ...) must be complete before the call, OR the stream that produces them is registered once with
+ * tad_function_set_caller_stream: every evaluation then first waits (event record + stream wait, no host sync) for the work
+ * queued on that stream at the time of the call.  stream = NULL registers the legacy default stream; call with
+ * enabled = 0 to unregister. */
 int tad_function_get_stream(tad_function f, void** stream);
+int tad_function_set_caller_stream(tad_function f, void* stream, int enabled);
 
 /* add_elements<N>(range, functor) / add_elements<N, M>(...)   ScalarFunctionImpl.hh:63-100, VectorFunctionImpl.hh:64-101
  * elem_handles_host may be NULL (identity).  The term keeps `user` and calls user_free(user) on destroy.
@@ -130,7 +155,9 @@ int tad_eval_with_gradient(tad_function f, const double* x_dev, double* f_host, 
 int tad_eval_with_derivatives(tad_function f, const double* x_dev, double* f_host, double* g_dev, double* H_values_dev,
                               int project_hessian, double projection_eps);
 
-/* Same with HOST buffers (H2D of x, D2H of g and H values inside the call). */
+/* Same with HOST buffers (H2D of x, D2H of g and H values inside the call).  The D2H of the CSR values is pipelined with the
+ * evaluation: after every slab the prefix of the value array whose rows can no longer change is copied on a second stream
+ * (fast for pinned host buffers; pageable buffers work, the copies are then staged by the driver). */
 int tad_eval_host(tad_function f, const double* x_host, double* f_host);
 int tad_eval_with_gradient_host(tad_function f, const double* x_host, double* f_host, double* g_host);
 int tad_eval_with_derivatives_host(tad_function f, const double* x_host, double* f_host, double* g_host,
@@ -166,6 +193,9 @@ int tad_function_projection_stats(tad_function f, int64_t* stats2);
  * [0] element kernels, [1] projection, [2] assembly, [3] total. */
 int tad_function_last_timings(tad_function f, float* ms4);
 int tad_function_set_timing(tad_function f, int enabled);
+/* Number of CUDA kernels launched for this function since it was created (this library's kernels plus the element
+ * kernels reported by the term launchers through tad_launch_args.launch_counter). */
+int tad_function_launch_count(tad_function f, int64_t* count);
 
 /* ---- callers of the hot path: projected-Newton utilities, all vectors device-resident ----
  * newton_direction   Utils/NewtonDirection.hh:25-48   d = -(H_proj + w_identity I)^-1 g on the function's fixed CSR pattern.

@@ -120,6 +120,8 @@ def _collect(L, h, want_matrix):
 
 
 EVAL, GRADIENT, DERIVATIVES, HESSIAN_PROJ = 0, 1, 2, 3
+NORM_SUM = 16  # same, every contribution counted with its element's largest |entry| (element-level rounding scale)
+ABS_SUM = 8   # OR-ed into DERIVATIVES / HESSIAN_PROJ: g and H values come back as sum |contributions| per entry (parity scale)
 
 
 def scalar_eval(d, n_vertices, terms, mode, x, eps=1e-9, n_threads=-1):
@@ -130,7 +132,7 @@ def scalar_eval(d, n_vertices, terms, mode, x, eps=1e-9, n_threads=-1):
     x = np.ascontiguousarray(x, dtype=np.float64)
     assert x.size == d * n_vertices
     h = L.oracle_scalar_eval(d, n_vertices, len(terms), ctypes.addressof(arr), mode, x.ctypes.data, eps, n_threads)
-    return _collect(L, h, mode >= 2)
+    return _collect(L, h, (mode & 7) >= 2)
 
 
 V_EVAL, V_JACOBIAN, V_SOS, V_SOS_DERIVATIVES = 0, 1, 2, 3

@@ -310,6 +310,9 @@ int scalar_eval_impl(std::int64_t n_vertices, int n_terms, const oracle_term* te
 {
     auto func = build_scalar<d>(n_vertices, n_terms, terms, n_threads);
     std::vector<double> x(x_in, x_in + func->n_vars);
+    out.pt.abs_sum = (mode & 8) != 0;    // modes 2|8, 3|8: g / H values = sum of |contributions| (scale of the per-entry parity bound)
+    out.pt.norm_sum = (mode & 16) != 0;  // modes 2|16, 3|16: sum over the contributing elements of the element's max |entry|
+    mode &= 7;
     switch (mode)
     {
     case 0: out.f = func->eval(x); break;

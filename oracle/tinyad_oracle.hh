@@ -895,7 +895,11 @@ bool all_finite(const Scalar<k, wh>& s, bool check_hess)
 
 // Phase timers filled by the second-order path:
 // [0] parallel element evaluation + projection, [1] serial accumulation + triplet push, [2] COO->CSC
-struct PhaseTimes { double eval = 0, accumulate = 0, compress = 0; Index n_projected = 0, n_decomposed = 0; };
+// norm_sum: like abs_sum, but every contribution of an element counts with the element's largest |grad| / |H| entry (the scale of the
+// rounding error of an element-level computation: cancellation inside an element leaves errors relative to its largest intermediates).
+// abs_sum (test metric only, SURVEY 8(c) "per-entry |delta| <= tol * sum |contributions|"): accumulate |grad_i| and |H_ij| instead of the
+// signed values, so that g / H come back as the per-entry scale of the parity bound.
+struct PhaseTimes { double eval = 0, accumulate = 0, compress = 0; Index n_projected = 0, n_decomposed = 0; bool abs_sum = false, norm_sum = false; };
 
 // ---------------------------------------------------------------------------
 // Scalar objective terms (Detail/ScalarObjectiveTerm.hh:22-289)
@@ -983,10 +987,21 @@ struct ScalarObjectiveTerm : ScalarObjectiveTermBase
         {
             f += results[e].val;
             const auto& l2g = elements[e].idx_local_to_global;
-            for (size_t i = 0; i < l2g.size(); ++i) g[l2g[i]] += results[e].grad[i];
+            const bool abs_sum = pt && pt->abs_sum, norm_sum = pt && pt->norm_sum;
+            double gmax = 0.0, hmax = 0.0;
+            if (norm_sum)
+            {
+                for (double v : results[e].grad) gmax = std::max(gmax, std::fabs(v));
+                for (double v : results[e].Hess) hmax = std::max(hmax, std::fabs(v));
+            }
+            for (size_t i = 0; i < l2g.size(); ++i)
+                g[l2g[i]] += norm_sum ? gmax : (abs_sum ? std::fabs(results[e].grad[i]) : results[e].grad[i]);
             for (size_t i = 0; i < l2g.size(); ++i)
                 for (size_t j = 0; j < l2g.size(); ++j)
-                    T.push_back(Triplet{(std::int32_t)l2g[i], (std::int32_t)l2g[j], results[e].H((int)i, (int)j)});
+                {
+                    const double h = results[e].H((int)i, (int)j);
+                    T.push_back(Triplet{(std::int32_t)l2g[i], (std::int32_t)l2g[j], norm_sum ? hmax : (abs_sum ? std::fabs(h) : h)});
+                }
         }
         const double t2 = now_s();
         if (pt)

@@ -62,3 +62,25 @@ def test_invalid_arguments(torch_cuda):
     h = ctypes.c_void_p()
     assert R.tad_function_create(0, 4, 0, 0, ctypes.byref(h)) == 1       # variable dimension must be >= 1
     fn.close()
+
+
+def test_functor_that_changes_its_handles_is_reported(torch_cuda):
+    """the sparsity pattern is recorded once (the reference rediscovers it at every evaluation,
+    Element.hh:208-260).  A functor whose variables() calls depend on x must be reported (TAD_PATTERN_MISMATCH), not silently
+    assembled into the wrong rows; evaluations that stay on the recorded path work, and the object stays usable."""
+    torch = torch_cuda
+    fn = tad.Function(1, 3)
+    # element 0: handles (0, 1), element 1: handles (1, 2); the functor returns before touching its second handle when x_a > 0.5
+    fn.add_term(tad.BRANCH_ON_X1D, np.array([[0, 1], [1, 2]], dtype=np.int32), np.array([[0.5], [0.5]]))
+    g = torch.empty(3, dtype=torch.float64, device="cuda")
+    H = torch.empty(fn.nnz, dtype=torch.float64, device="cuda")
+    ok = torch.tensor([0.2, 0.1, 0.4], dtype=torch.float64, device="cuda")
+    f = fn.eval_with_derivatives(ok, g, H)
+    assert abs(f - (0.1 ** 2 + 0.3 ** 2)) < 1e-15
+    bad = torch.tensor([0.9, 0.1, 0.4], dtype=torch.float64, device="cuda")     # element 0 leaves early
+    for call in (lambda: fn.eval(bad), lambda: fn.eval_with_gradient(bad, g), lambda: fn.eval_with_hessian_proj(bad, g, H)):
+        with pytest.raises(tad.TinyADError) as e:
+            call()
+        assert e.value.status == 9                                              # TAD_PATTERN_MISMATCH
+    assert abs(fn.eval(ok) - f) < 1e-15                                         # still usable
+    fn.close()

@@ -20,13 +20,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 TAD_OK = 0
 STATUS_NAMES = {0: "TAD_OK", 1: "TAD_INVALID_ARGUMENT", 2: "TAD_NONFINITE_DERIVATIVE", 3: "TAD_CUDA_ERROR",
                 4: "TAD_TOO_MANY_VARIABLES", 5: "TAD_INDEX_OUT_OF_RANGE", 6: "TAD_NOT_SUPPORTED", 7: "TAD_OUT_OF_MEMORY",
-                8: "TAD_SOLVER_FAILED"}
+                8: "TAD_SOLVER_FAILED", 9: "TAD_PATTERN_MISMATCH", 10: "TAD_COMM_ERROR"}
 ASSEMBLY_ATOMIC, ASSEMBLY_GATHER = 0, 1
-OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION = 1, 2, 3
+OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION, OPT_LANES = 1, 2, 3, 4
 
 # term kinds of csrc/energies.cu
 SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
 EDGE_DIRICHLET1D, QUADRATIC2D, REPEATED_HANDLE, TRIG_MIX2D, SQRT1D = 5, 6, 7, 8, 9
+BRANCH_ON_X1D = 13                      # variables() calls depend on x -> TAD_PATTERN_MISMATCH
 ARAP2D = 12                             # w |J - closest_orthogonal(J)|^2 (Operations/SVD.hh inside an element functor)
 DYN_SUM_SQR2D, DYN_ONERING1D = 10, 11   # add_elements_dynamic (tests/DynamicElementsTest.cc)
 SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
@@ -34,7 +35,7 @@ SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
 # every symbol include/tinyad_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "tad_last_error", "tad_device_count", "tad_function_create", "tad_function_destroy", "tad_function_set_option",
-    "tad_function_get_stream", "tad_function_add_term", "tad_function_add_pattern_blocks", "tad_function_n_vars", "tad_function_n_elements",
+    "tad_function_get_stream", "tad_function_set_caller_stream", "tad_function_launch_count", "tad_function_add_term", "tad_function_add_pattern_blocks", "tad_function_n_vars", "tad_function_n_elements",
     "tad_function_n_outputs", "tad_function_pattern", "tad_function_pattern_copy", "tad_function_pattern_device",
     "tad_function_term_table", "tad_eval", "tad_eval_with_gradient", "tad_eval_with_derivatives", "tad_eval_host",
     "tad_eval_with_gradient_host", "tad_eval_with_derivatives_host", "tad_veval", "tad_veval_with_jacobian",
@@ -69,6 +70,8 @@ def runtime():
         L.tad_function_destroy.restype = None
         L.tad_function_set_option.argtypes = [vp, ctypes.c_int, i64]
         L.tad_function_get_stream.argtypes = [vp, vp]
+        L.tad_function_set_caller_stream.argtypes = [vp, vp, ctypes.c_int]
+        L.tad_function_launch_count.argtypes = [vp, vp]
         for n in ("n_vars", "n_elements", "n_outputs"):
             fn = getattr(L, "tad_function_" + n)
             fn.restype = i64
@@ -191,6 +194,16 @@ class Function:
 
     def set_option(self, opt, value):
         _check(runtime().tad_function_set_option(self.h, opt, value))
+
+    def launch_count(self):
+        """CUDA kernels launched for this function so far."""
+        n = ctypes.c_int64()
+        _check(runtime().tad_function_launch_count(self.h, ctypes.byref(n)))
+        return n.value
+
+    def set_caller_stream(self, stream_ptr, enabled=True):
+        """Evaluations first wait for the work queued on this CUDA stream (0 / None = legacy default stream)."""
+        _check(runtime().tad_function_set_caller_stream(self.h, stream_ptr, int(enabled)))
 
     def set_timing(self, on=True):
         _check(runtime().tad_function_set_timing(self.h, int(on)))

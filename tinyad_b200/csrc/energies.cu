@@ -56,7 +56,7 @@ thread_local std::string g_err;
 enum
 {
     K_SYMDIRICHLET2D = 1, K_PENALTY2D = 2, K_SYMDIRICHLET3D = 3, K_PENALTY3D = 4, K_EDGE_DIRICHLET1D = 5, K_ARAP2D = 12, K_DYN_SUM_SQR2D = 10, K_DYN_ONERING1D = 11,
-    K_QUADRATIC2D = 6, K_REPEATED_HANDLE = 7, K_TRIG_MIX2D = 8, K_SQRT1D = 9,
+    K_QUADRATIC2D = 6, K_REPEATED_HANDLE = 7, K_TRIG_MIX2D = 8, K_SQRT1D = 9, K_BRANCH_ON_X1D = 13,
     K_SOS_SYMDIRICHLET2D = 101, K_SOS_PENALTY2D = 102, K_SOS_POLYCURL2D = 103,
 };
 
@@ -160,6 +160,7 @@ int tadx_add_term(void* h, int kind, int64_t n_elements, const int32_t* conn, in
         case K_PENALTY3D: need(P->s3 && valence == 1 && n_data == 3); P->s3->add_elements<1>(els, Penalty<3>{C, D}); break;
         case K_EDGE_DIRICHLET1D: need(P->s1 && valence == 2 && n_data == 1); P->s1->add_elements<2>(els, EdgeDirichlet1D{C, D}); break;
         case K_SQRT1D: need(P->s1 && valence == 1 && n_data == 1); P->s1->add_elements<1>(els, Sqrt1D{C, D}); break;
+        case K_BRANCH_ON_X1D: need(P->s1 && valence == 2 && n_data == 1); P->s1->add_elements<2>(els, BranchOnX1D{C, D}); break;
         case K_QUADRATIC2D: need(P->s2 && valence == 1 && n_data == 1); P->s2->add_elements<1>(els, Quadratic2D{C, D}); break;
         case K_REPEATED_HANDLE: need(P->s2 && valence == 2 && n_data == 1); P->s2->add_elements<2>(els, RepeatedHandle{C, D}); break;
         case K_TRIG_MIX2D: need(P->s2 && valence == 2 && n_data == 1); P->s2->add_elements<2>(els, TrigMix2D{C, D}); break;

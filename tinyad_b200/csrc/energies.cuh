@@ -136,6 +136,23 @@ struct SymDirichlet3D  // data: Mr^-1 row-major (9), vol
     }
 };
 
+// A functor whose variables() calls depend on x (it returns before touching its second handle when x_a > data): the recorded
+// pattern (x = 0 at add_elements time) does not cover such an evaluation -> TAD_PATTERN_MISMATCH.
+struct BranchOnX1D  // data: threshold
+{
+    ConnView C; DataView D;
+    template <class E>
+    TINYAD_HD auto operator()(E& element) const -> TINYAD_SCALAR_TYPE(element)
+    {
+        using T = TINYAD_SCALAR_TYPE(element);
+        const int64_t e = element.handle;
+        T a = element.variable(C(e, 0));
+        if (a > D(e, 0)) return sqr(a);
+        T b = element.variable(C(e, 1));
+        return sqr(a - b);
+    }
+};
+
 struct EdgeDirichlet1D  // data: w ; w * (x_a - x_b)^2
 {
     ConnView C; DataView D;

@@ -42,19 +42,29 @@ int fail(int status, const std::string& msg)
     return status;
 }
 
-// Function attributes (dynamic shared-memory opt-in, carve-out) are per device: true the first time a call site runs on the
-// current device.  (One flag array per call site; processes normally drive one GPU, but nothing here assumes it.)
+// Function attributes (dynamic shared-memory opt-in, carve-out) are per device: run(fn) executes fn exactly once per device
+// (std::call_once: a second thread that arrives while the first is still configuring waits for it, so no launch can overtake
+// the opt-in).  One object per call site; processes normally drive one GPU, but nothing here assumes it.
 struct PerDeviceOnce
 {
-    bool done[64] = {};
-    bool first()
+    std::once_flag flags[64];
+    template <class Fn>
+    void run(Fn&& fn)
     {
         int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-        if (done[dev]) return false;
-        done[dev] = true;
-        return true;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { fn(); return; }
+        std::call_once(flags[dev], fn);
     }
+};
+
+// Kernel-launch accounting (tad_function_launch_count): the evaluation entry points point this at the function's counter.
+thread_local int64_t* tl_launch_counter = nullptr;
+inline void count_launch(int n = 1) { if (tl_launch_counter) *tl_launch_counter += n; }
+struct LaunchCounterScope
+{
+    int64_t* prev;
+    explicit LaunchCounterScope(int64_t* c) : prev(tl_launch_counter) { tl_launch_counter = c; }
+    ~LaunchCounterScope() { tl_launch_counter = prev; }
 };
 
 #define TAD_CUDA(expr)                                                                                   \
@@ -76,6 +86,7 @@ struct PerDeviceOnce
 constexpr int ERR_NONFINITE = 1 << TAD_NONFINITE_DERIVATIVE;
 constexpr int ERR_TOO_MANY = 1 << TAD_TOO_MANY_VARIABLES;
 constexpr int ERR_RANGE = 1 << TAD_INDEX_OUT_OF_RANGE;
+constexpr int ERR_PATTERN = 1 << TAD_PATTERN_MISMATCH;
 
 template <class T>
 struct DevBuf
@@ -144,6 +155,36 @@ struct ProjSide
     cudaEvent_t ev_b = nullptr, ev_list = nullptr;
 };
 
+// One element slab in flight: its own stream, staging, projection scratch and counters.  Consecutive slabs of an evaluation
+// alternate between the lanes, so the tail of one slab's kernels overlaps the head of the next slab's, and the memory an
+// evaluation needs is bounded by lanes x slab size instead of the term size.
+struct Lane
+{
+    cudaStream_t stream = nullptr;
+    ProjSide side;
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // timing mode: before element / after element / after projection / after assembly
+    DevBuf<double> stage;                  // val / grad / hess of the slab, SoA with the slab's stride
+    DevBuf<double> proj_scratch;           // R and W of the fast projection path
+    DevBuf<int32_t> proj_codes;
+    DevBuf<int64_t> proj_list;             // elements handed to the full eigensolver
+    DevBuf<unsigned long long> counts;     // [4]: decomposed, rebuilt, listed in this slab, listed in this evaluation
+};
+
+// A slab of the evaluation schedule.
+struct Slab
+{
+    int term;
+    int64_t e_begin, n;
+    int64_t final_values;  // leading CSR values that can no longer change once this slab and all earlier ones are complete
+};
+
+// Destination of the pipelined device -> host copies of the host-buffer entry points.
+struct HostCopy
+{
+    double* g_host = nullptr;
+    double* H_host = nullptr;
+};
+
 }  // namespace
 
 struct tad_function_s
@@ -157,7 +198,8 @@ struct tad_function_s
     int64_t n_elements = 0, n_outputs = 0;
     // options
     int assembly = TAD_ASSEMBLY_ATOMIC;
-    int64_t chunk = 0;
+    int64_t chunk = 0;             // TAD_OPT_CHUNK_ELEMENTS: 0 default, < 0 whole term
+    int n_lanes = 2;               // TAD_OPT_LANES
     bool timing = false;
     // pattern
     bool pattern_built = false;
@@ -167,24 +209,39 @@ struct tad_function_s
     DevBuf<int32_t> contrib;       // sorted contribution ids
     DevBuf<int64_t> block_key;     // [n_blocks]
     DevBuf<int64_t> vrow;          // [n_handles+1] first block of each vertex row
+    std::vector<int64_t> vrow_host;   // host copy (row finality of the slab schedule)
     DevBuf<TermDev> terms_dev;
+    std::vector<TermDev> terms_dev_host;  // what terms_dev holds
+    DevBuf<unsigned char> seqs_dev;   // SeqTable per term (gather assembly), built with the pattern
     std::vector<int64_t> extra_keys;  // vertex pairs injected by tad_function_add_pattern_blocks (halo rows of other ranks)
+    // slab schedule of the second-order evaluation (rebuilt when the pattern or the options change)
+    struct Schedule
+    {
+        std::vector<Slab> slabs;
+        int64_t chunk = -2;       // slab size the schedule was built for (-1: whole terms)
+        bool whole = false;
+        bool has_final = false;   // Slab::final_values computed (needs the pattern)
+        void clear() { slabs.clear(); chunk = -2; has_final = false; }
+    };
+    Schedule sched[2];            // [0] device-pointer entry points, [1] host-buffer entry points (smaller slabs: finer D2H pipelining)
     // scratch
-    DevBuf<double> stage;          // shared staging (atomic mode)
     DevBuf<double> x_dev, g_dev, H_dev, r_dev;
+    DevBuf<double> stage;          // vector functions: staging of the current term
     DevBuf<int32_t> err;           // int32[8]
     DevBuf<double> fpart;          // block partial sums
     DevBuf<double> fterm;          // per-term sums
-    DevBuf<unsigned long long> proj_counts;   // [4]: decomposed, rebuilt, fallback, -
-    DevBuf<int64_t> proj_list;     // elements handed to the full eigensolver
-    DevBuf<double> proj_scratch;   // R and W of the fast projection path
-    DevBuf<int32_t> proj_codes;
     int projection_full = 0;       // option: 1 = always use the full eigensolver kernel
     int64_t last_proj[3] = {0, 0, 0};
     float last_ms[4] = {0, 0, 0, 0};
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    ProjSide proj_side;            // side stream + events of the fused projection / assembly path
-    std::recursive_mutex mtx;      // eval* may be called concurrently (ScalarFunctionTest.cc:255-291)
+    int64_t n_launches = 0;        // kernels launched so far (tad_function_launch_count)
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // begin / end of an evaluation on the main stream
+    cudaEvent_t ev_caller = nullptr;
+    cudaStream_t caller_stream = nullptr;
+    bool wait_caller = false;      // tad_function_set_caller_stream
+    std::vector<Lane> lanes;
+    std::vector<cudaEvent_t> slab_events;  // one per slab of the schedule: "this slab is assembled"
+    cudaStream_t copy_stream = nullptr;    // device -> host copies of finished rows (host-buffer entry points)
+    std::recursive_mutex mtx;      // eval* may be called concurrently (ScalarFunctionTest.cc:255-291): calls on one function are serialised
 };
 
 namespace
@@ -636,8 +693,9 @@ __global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t
     if (code == TinyAD::detail::PROJ_REBUILT && counts) atomicAdd(&counts[1], 1ull);
     if (code == TinyAD::detail::PROJ_FALLBACK)
     {
-        const unsigned long long slot = atomicAdd(&counts[2], 1ull);
+        const unsigned long long slot = atomicAdd(&counts[2], 1ull);  // per slab (reset by the caller): index into the list
         sc.list[slot] = el;
+        atomicAdd(&counts[3], 1ull);                                  // running total of the evaluation
     }
 }
 
@@ -670,13 +728,14 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
     using L = TinyAD::detail::ProjLayout<K>;
     constexpr size_t smem = (size_t)ProjSmem<K>::doubles_per_warp * sizeof(double);
     static PerDeviceOnce configured;
-    if (configured.first())
-    {
-        if (cudaFuncSetAttribute(project_kernel_full<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel");
-    }
+    bool config_ok = true;
+    configured.run([&] { config_ok = cudaFuncSetAttribute(project_kernel_full<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; });
+    if (!config_ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel");
     if (full_only)
+    {
+        count_launch();
         project_kernel_full<K><<<(unsigned)((n + 31) / 32), 32, smem, st>>>(hess, n, stride, eps, counts);
+    }
     else
     {
         ProjScratch sc;
@@ -685,15 +744,16 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         sc.codes = codes;
         sc.list = list;
         const unsigned g = (unsigned)((n + 127) / 128);
+        count_launch(4 + (fuse_out ? 0 : 1));
         project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
         project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
         {
             static PerDeviceOnce b2_configured;
-            if (b2_configured.first())
-            {
-                cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128));
-                cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            }
+            b2_configured.run([&] {
+                config_ok = cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128)) == cudaSuccess &&
+                            cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+            });
+            if (!config_ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel B2");
             // 2 blocks per SM at 255 registers (no spills) beat 3 blocks at 168 registers with ~400 B of spills by 3-6 % (tools/proj_bench.cu);
             // K <= 12: 128-thread blocks (61 KB of shared memory each at K = 12); larger K: smaller blocks keep the footprint per SM
             const int bt = K <= 12 ? 128 : 64;
@@ -873,11 +933,13 @@ __global__ void fill_maps(const int32_t* contrib, const int32_t* pid_incl, int64
 // ---------------------------------------------------------------------------------------------
 struct SeqTable { int16_t idx[18 * 18]; };
 
+// rec / blockbase / rstride: the term's maps, already offset to the first element of the slab, leading dimension mstride;
+// grad / hess: the slab's staging, leading dimension stride; e = position inside the slab.
 template <int D, int N>
 __global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __restrict__ rec, const int32_t* __restrict__ blockbase,
-                                                              const int32_t* __restrict__ rstride, const double* __restrict__ grad,
-                                                              const double* __restrict__ hess, int64_t n, int64_t stride,
-                                                              double* __restrict__ g, double* __restrict__ Hv, int32_t* err)
+                                                              const int32_t* __restrict__ rstride, int64_t mstride,
+                                                              const double* __restrict__ grad, const double* __restrict__ hess, int64_t n,
+                                                              int64_t stride, double* __restrict__ g, double* __restrict__ Hv, int32_t* err)
 {
     constexpr int K = D * N;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -886,7 +948,7 @@ __global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __r
 #pragma unroll
     for (int bi = 0; bi < N; ++bi)
     {
-        const int32_t vi = rec[(int64_t)bi * stride + e];
+        const int32_t vi = rec[(int64_t)bi * mstride + e];
         if (vi < 0) continue;
 #pragma unroll
         for (int a = 0; a < D; ++a)
@@ -901,19 +963,17 @@ __global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __r
 #pragma unroll
         for (int bi = 0; bi < N; ++bi)
         {
-            const int32_t rs = rstride[(int64_t)bi * stride + e];
+            const int32_t rs = rstride[(int64_t)bi * mstride + e];
 #pragma unroll
             for (int bj = 0; bj < N; ++bj)
             {
-                const int32_t base = blockbase[(int64_t)(bi * N + bj) * stride + e];
+                const int32_t base = blockbase[(int64_t)(bi * N + bj) * mstride + e];
                 if (base < 0) continue;
 #pragma unroll
                 for (int a = 0; a < D; ++a)
 #pragma unroll
                     for (int b = 0; b < D; ++b)
                     {
-                        constexpr int dummy = 0;
-                        (void)dummy;
                         const int s = hess_seq_index(K, D * bi + a, D * bj + b);
                         const double v = hess[(int64_t)s * stride + e];
                         finite = finite && isfinite(v);
@@ -931,8 +991,8 @@ __global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __r
 template <int D, int N>
 __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __restrict__ hess, int64_t stride, double eps, const ProjScratch& sc,
                                                const int32_t* __restrict__ rec, const int32_t* __restrict__ blockbase,
-                                               const int32_t* __restrict__ rstride, const double* __restrict__ grad, double* __restrict__ g,
-                                               double* __restrict__ Hv, int32_t* err, const int code)
+                                               const int32_t* __restrict__ rstride, const int64_t mstride, const double* __restrict__ grad,
+                                               double* __restrict__ g, double* __restrict__ Hv, int32_t* err, const int code)
 {
     constexpr int K = D * N;
     constexpr int H = K * (K + 1) / 2;
@@ -977,7 +1037,7 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
 #pragma unroll
     for (int bi = 0; bi < N; ++bi)
     {
-        const int32_t vi = rec[(int64_t)bi * stride + e];
+        const int32_t vi = rec[(int64_t)bi * mstride + e];
         if (vi < 0) continue;
 #pragma unroll
         for (int a = 0; a < D; ++a)
@@ -990,11 +1050,11 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
 #pragma unroll
     for (int bi = 0; bi < N; ++bi)
     {
-        const int32_t rs = rstride[(int64_t)bi * stride + e];
+        const int32_t rs = rstride[(int64_t)bi * mstride + e];
 #pragma unroll
         for (int bj = 0; bj < N; ++bj)
         {
-            const int32_t base = blockbase[(int64_t)(bi * N + bj) * stride + e];
+            const int32_t base = blockbase[(int64_t)(bi * N + bj) * mstride + e];
             if (base < 0) continue;
 #pragma unroll
             for (int a = 0; a < D; ++a)
@@ -1016,7 +1076,7 @@ template <int D, int N, bool LIST>
 __global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* __restrict__ hess, int64_t n, int64_t stride, double eps,
                                                                  ProjScratch sc, const int32_t* __restrict__ rec,
                                                                  const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
-                                                                 const double* __restrict__ grad, double* __restrict__ g,
+                                                                 int64_t mstride, const double* __restrict__ grad, double* __restrict__ g,
                                                                  double* __restrict__ Hv, int32_t* err, const unsigned long long* counts,
                                                                  bool skip_listed)
 {
@@ -1024,7 +1084,7 @@ __global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* _
     {
         const int64_t count = (int64_t)counts[2];
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-            c_assemble_one<D, N>(sc.list[i], hess, stride, eps, sc, rec, blockbase, rstride, grad, g, Hv, err, TinyAD::detail::PROJ_FALLBACK);
+            c_assemble_one<D, N>(sc.list[i], hess, stride, eps, sc, rec, blockbase, rstride, mstride, grad, g, Hv, err, TinyAD::detail::PROJ_FALLBACK);
     }
     else
     {
@@ -1032,13 +1092,22 @@ __global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* _
         if (e >= n) return;
         const int code = sc.codes[e];
         if (skip_listed && code == TinyAD::detail::PROJ_FALLBACK) return;
-        c_assemble_one<D, N>(e, hess, stride, eps, sc, rec, blockbase, rstride, grad, g, Hv, err, code);
+        c_assemble_one<D, N>(e, hess, stride, eps, sc, rec, blockbase, rstride, mstride, grad, g, Hv, err, code);
     }
 }
 
+// The scatter maps of one slab: the term's maps offset to the slab's first element (leading dimension mstride).
+struct SlabMaps
+{
+    const int32_t* rec;
+    const int32_t* blockbase;
+    const int32_t* rstride;
+    int64_t mstride;
+};
+
 template <int D, int N>
-void launch_c_assemble(const Term& t, const double* grad, const double* hess, int64_t n, double eps, ProjScratch sc, double* g, double* Hv,
-                       int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
+int launch_c_assemble(const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double eps, ProjScratch sc, double* g,
+                      double* Hv, int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
 {
     const bool split = side && side->stream;
     // ~200 registers per thread: single-warp blocks fit 10 per SM (10 warps) where 128-thread blocks fit 2 (8 warps); the kernel is
@@ -1048,51 +1117,49 @@ void launch_c_assemble(const Term& t, const double* grad, const double* hess, in
     constexpr int K = D * N;
     constexpr size_t tmp_thread = (size_t)TinyAD::detail::ProjLayout<K>::MAXV * (K + 1) * sizeof(double);  // 728 B at K = 12
     static PerDeviceOnce configured;
-    if (configured.first())
-    {
-        cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread));
-        cudaFuncSetAttribute(project_c_assemble_kernel<D, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread));
-        cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
+    bool ok = true;
+    configured.run([&] {
+        ok = cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread)) == cudaSuccess &&
+             cudaFuncSetAttribute(project_c_assemble_kernel<D, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread)) == cudaSuccess &&
+             cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+    });
+    if (!ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the fused projection/assembly kernel");
+    count_launch(split ? 2 : 1);
     project_c_assemble_kernel<D, N, false><<<(unsigned)((n + bs - 1) / bs), bs, bs * tmp_thread, st>>>(
-        hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p, t.rstride.p, grad, g, Hv, err, counts, split);
+        hess, n, stride, eps, sc, m.rec, m.blockbase, m.rstride, m.mstride, grad, g, Hv, err, counts, split);
     if (split)
     {
         cudaStreamWaitEvent(st, side->ev_list, 0);
-        project_c_assemble_kernel<D, N, true><<<8, 128, 128 * tmp_thread, st>>>(hess, n, t.stride, eps, sc, t.rec_handles.p, t.blockbase.p,
-                                                                                 t.rstride.p, grad, g, Hv, err, counts, false);
+        project_c_assemble_kernel<D, N, true><<<8, 128, 128 * tmp_thread, st>>>(hess, n, stride, eps, sc, m.rec, m.blockbase, m.rstride, m.mstride,
+                                                                                 grad, g, Hv, err, counts, false);
     }
+    return TAD_OK;
 }
 
 bool fused_c_assemble_supported(int d, int N) { return d >= 1 && d <= 3 && N >= 1 && N <= 4; }
 
-int c_assemble(int d, const Term& t, const double* grad, const double* hess, int64_t n, double eps, ProjScratch sc, double* g, double* Hv,
-               int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
+int c_assemble(int d, int N, const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double eps, ProjScratch sc,
+               double* g, double* Hv, int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
 {
     if (n <= 0) return TAD_OK;
-    switch (d * 100 + t.N)
+    int rc = TAD_OK;
+    switch (d * 100 + N)
     {
-    case 101: launch_c_assemble<1, 1>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 102: launch_c_assemble<1, 2>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 103: launch_c_assemble<1, 3>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 104: launch_c_assemble<1, 4>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 201: launch_c_assemble<2, 1>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 202: launch_c_assemble<2, 2>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 203: launch_c_assemble<2, 3>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 204: launch_c_assemble<2, 4>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 301: launch_c_assemble<3, 1>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 302: launch_c_assemble<3, 2>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 303: launch_c_assemble<3, 3>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
-    case 304: launch_c_assemble<3, 4>(t, grad, hess, n, eps, sc, g, Hv, err, counts, side, st); break;
+#define TAD_CASE(DD, NN) case DD * 100 + NN: rc = launch_c_assemble<DD, NN>(m, grad, hess, n, stride, eps, sc, g, Hv, err, counts, side, st); break;
+    TAD_CASE(1, 1) TAD_CASE(1, 2) TAD_CASE(1, 3) TAD_CASE(1, 4)
+    TAD_CASE(2, 1) TAD_CASE(2, 2) TAD_CASE(2, 3) TAD_CASE(2, 4)
+    TAD_CASE(3, 1) TAD_CASE(3, 2) TAD_CASE(3, 3) TAD_CASE(3, 4)
+#undef TAD_CASE
     default: return fail(TAD_NOT_SUPPORTED, "no fused projection/assembly kernel for this (d, N)");
     }
+    if (rc != TAD_OK) return rc;
     return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "fused projection/assembly launch failed");
 }
 
 // generic (runtime d, N) fallback
 __global__ void __launch_bounds__(128) assemble_atomic_generic(int D, int N, SeqTable seq, const int32_t* __restrict__ rec,
                                                                const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
-                                                               const double* __restrict__ grad, const double* __restrict__ hess,
+                                                               int64_t mstride, const double* __restrict__ grad, const double* __restrict__ hess,
                                                                int64_t n, int64_t stride, double* __restrict__ g, double* __restrict__ Hv,
                                                                int32_t* err)
 {
@@ -1102,7 +1169,7 @@ __global__ void __launch_bounds__(128) assemble_atomic_generic(int D, int N, Seq
     bool finite = true;
     for (int bi = 0; bi < N; ++bi)
     {
-        const int32_t vi = rec[(int64_t)bi * stride + e];
+        const int32_t vi = rec[(int64_t)bi * mstride + e];
         if (vi < 0) continue;
         for (int a = 0; a < D; ++a)
         {
@@ -1114,10 +1181,10 @@ __global__ void __launch_bounds__(128) assemble_atomic_generic(int D, int N, Seq
     if (hess)
         for (int bi = 0; bi < N; ++bi)
         {
-            const int32_t rs = rstride[(int64_t)bi * stride + e];
+            const int32_t rs = rstride[(int64_t)bi * mstride + e];
             for (int bj = 0; bj < N; ++bj)
             {
-                const int32_t base = blockbase[(int64_t)(bi * N + bj) * stride + e];
+                const int32_t base = blockbase[(int64_t)(bi * N + bj) * mstride + e];
                 if (base < 0) continue;
                 for (int a = 0; a < D; ++a)
                     for (int b = 0; b < D; ++b)
@@ -1133,40 +1200,33 @@ __global__ void __launch_bounds__(128) assemble_atomic_generic(int D, int N, Seq
 }
 
 template <int D, int N>
-void launch_assemble(const Term& t, const double* grad, const double* hess, int64_t n, double* g, double* Hv, int32_t* err, cudaStream_t st)
+void launch_assemble(const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double* g, double* Hv, int32_t* err,
+                     cudaStream_t st)
 {
-    assemble_atomic_kernel<D, N><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(t.rec_handles.p, t.blockbase.p, t.rstride.p, grad, hess,
-                                                                              n, t.stride, g, Hv, err);
+    assemble_atomic_kernel<D, N><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m.rec, m.blockbase, m.rstride, m.mstride, grad, hess, n, stride, g, Hv, err);
 }
 
-int assemble_atomic(int d, const Term& t, const double* grad, const double* hess, int64_t n, double* g, double* Hv, int32_t* err,
-                    cudaStream_t st)
+int assemble_atomic(int d, int N, const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double* g, double* Hv,
+                    int32_t* err, cudaStream_t st)
 {
     if (n <= 0) return TAD_OK;
-    const int code = d * 100 + t.N;
-    switch (code)
+    count_launch();
+    switch (d * 100 + N)
     {
-    case 101: launch_assemble<1, 1>(t, grad, hess, n, g, Hv, err, st); break;
-    case 102: launch_assemble<1, 2>(t, grad, hess, n, g, Hv, err, st); break;
-    case 103: launch_assemble<1, 3>(t, grad, hess, n, g, Hv, err, st); break;
-    case 104: launch_assemble<1, 4>(t, grad, hess, n, g, Hv, err, st); break;
-    case 201: launch_assemble<2, 1>(t, grad, hess, n, g, Hv, err, st); break;
-    case 202: launch_assemble<2, 2>(t, grad, hess, n, g, Hv, err, st); break;
-    case 203: launch_assemble<2, 3>(t, grad, hess, n, g, Hv, err, st); break;
-    case 204: launch_assemble<2, 4>(t, grad, hess, n, g, Hv, err, st); break;
-    case 301: launch_assemble<3, 1>(t, grad, hess, n, g, Hv, err, st); break;
-    case 302: launch_assemble<3, 2>(t, grad, hess, n, g, Hv, err, st); break;
-    case 303: launch_assemble<3, 3>(t, grad, hess, n, g, Hv, err, st); break;
-    case 304: launch_assemble<3, 4>(t, grad, hess, n, g, Hv, err, st); break;
+#define TAD_CASE(DD, NN) case DD * 100 + NN: launch_assemble<DD, NN>(m, grad, hess, n, stride, g, Hv, err, st); break;
+    TAD_CASE(1, 1) TAD_CASE(1, 2) TAD_CASE(1, 3) TAD_CASE(1, 4)
+    TAD_CASE(2, 1) TAD_CASE(2, 2) TAD_CASE(2, 3) TAD_CASE(2, 4)
+    TAD_CASE(3, 1) TAD_CASE(3, 2) TAD_CASE(3, 3) TAD_CASE(3, 4)
+#undef TAD_CASE
     default:
     {
-        const int K = d * t.N;
+        const int K = d * N;
         if (K > 18) return fail(TAD_NOT_SUPPORTED, "assembly supports at most 18 variables per element");
         SeqTable seq;
         for (int i = 0; i < K; ++i)
             for (int j = 0; j < K; ++j) seq.idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);
-        assemble_atomic_generic<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d, t.N, seq, t.rec_handles.p, t.blockbase.p, t.rstride.p,
-                                                                            grad, hess, n, t.stride, g, Hv, err);
+        assemble_atomic_generic<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d, N, seq, m.rec, m.blockbase, m.rstride, m.mstride, grad, hess, n, stride,
+                                                                            g, Hv, err);
     }
     }
     return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "assembly kernel launch failed");
@@ -1358,6 +1418,8 @@ int check_error_word(tad_function f, bool sync_already)
     TAD_CUDA(cudaMemcpy(h_err, f->err.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (h_err[0] & ERR_RANGE) return fail(TAD_INDEX_OUT_OF_RANGE, "variable handle out of range in element.variables(...)");
     if (h_err[0] & ERR_TOO_MANY) return fail(TAD_TOO_MANY_VARIABLES, "Too many variables requested via element.variables(...).");
+    if (h_err[0] & ERR_PATTERN)
+        return fail(TAD_PATTERN_MISMATCH, "an element requested different variable handles than when it was added (the sparsity pattern is fixed at add_elements time)");
     if (h_err[0] & ERR_NONFINITE) return fail(TAD_NONFINITE_DERIVATIVE, "non-finite element gradient or Hessian");
     return TAD_OK;
 }
@@ -1371,47 +1433,61 @@ int sum_to(tad_function f, const double* v, int64_t n, int64_t stride, int rows,
         TAD_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), f->stream));
         return TAD_OK;
     }
+    count_launch(2);
     if (square) reduce_stage1<true><<<(unsigned)nb, 256, 0, f->stream>>>(v, n, stride, rows, f->fpart.p);
     else reduce_stage1<false><<<(unsigned)nb, 256, 0, f->stream>>>(v, n, stride, rows, f->fpart.p);
     reduce_stage2<<<1, 1024, 0, f->stream>>>(f->fpart.p, nb, out_dev);
     return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "reduction launch failed");
 }
 
-void fill_launch_args(tad_function f, const Term& t, int mode, const double* x, double* stage, tad_launch_args& a)
+// Launch arguments of the slab [e_begin, e_begin + n) of term t; `stage` holds the slab's outputs with leading dimension sstride.
+void fill_launch_args(tad_function f, const Term& t, int mode, const double* x, double* stage, int64_t e_begin, int64_t n, int64_t sstride,
+                      cudaStream_t stream, tad_launch_args& a)
 {
     std::memset(&a, 0, sizeof(a));
     a.mode = mode;
     a.dedup = t.dedup ? 1 : 0;
-    a.n_elements = t.n;
-    a.stride = t.stride;
+    a.n_elements = n;
+    a.stride = sstride;
+    a.e_begin = e_begin;
+    a.rec_stride = t.stride;
     a.elem_handles = t.has_handles ? t.elem_handles.p : nullptr;
     a.x = x;
     a.n_handles = f->n_handles;
     const int rows = std::max(1, t.M);
     a.val = stage;
-    a.grad = stage ? stage + (int64_t)rows * t.stride : nullptr;
-    a.hess = (stage && t.M == 0) ? a.grad + (int64_t)t.k * t.stride : nullptr;
+    a.grad = stage ? stage + (int64_t)rows * sstride : nullptr;
+    a.hess = (stage && t.M == 0) ? a.grad + (int64_t)t.k * sstride : nullptr;
     a.rec_handles = t.rec_handles.p;
     a.rec_counts = t.rec_counts.p;
     a.error_flags = f->err.p;
-    a.stream = f->stream;
+    a.stream = stream;
+    a.launch_counter = &f->n_launches;
+}
+void fill_launch_args(tad_function f, const Term& t, int mode, const double* x, double* stage, tad_launch_args& a)
+{
+    fill_launch_args(f, t, mode, x, stage, 0, t.n, t.stride, f->stream, a);
 }
 
-size_t stage_doubles(const Term& t, int mode)
+size_t stage_doubles(const Term& t, int mode, int64_t sstride)
 {
     const int rows = std::max(1, t.M);
     size_t per = rows;
     if (mode >= TAD_MODE_FIRST) per += (size_t)rows * t.k;
     if (mode == TAD_MODE_SECOND && t.M == 0) per += (size_t)hess_size(t.k);
-    return per * (size_t)t.stride;
+    return per * (size_t)sstride;
 }
+size_t stage_doubles(const Term& t, int mode) { return stage_doubles(t, mode, t.stride); }
 
+// Device copy of the term descriptions (pattern construction, gather assembly).  Re-uploaded only when something changed
+// (the staging pointers of the gather mode move when a buffer grows).
 int upload_terms_dev(tad_function f, bool with_stage_ptrs, int mode)
 {
     std::vector<TermDev> td(f->terms.size());
     for (size_t i = 0; i < f->terms.size(); ++i)
     {
         Term& t = f->terms[i];
+        std::memset(&td[i], 0, sizeof(TermDev));
         td[i].off = t.contrib_offset;
         td[i].n = t.n;
         td[i].stride = t.stride;
@@ -1428,10 +1504,14 @@ int upload_terms_dev(tad_function f, bool with_stage_ptrs, int mode)
             td[i].hess = (mode == TAD_MODE_SECOND) ? t.stage.p + (int64_t)(1 + t.k) * t.stride : nullptr;
         }
     }
+    if (td.size() == f->terms_dev_host.size() && f->terms_dev.p &&
+        (td.empty() || std::memcmp(td.data(), f->terms_dev_host.data(), td.size() * sizeof(TermDev)) == 0))
+        return TAD_OK;
     TAD_CUDA(f->terms_dev.ensure(td.size()));
     if (!td.empty())
         TAD_CUDA(cudaMemcpyAsync(f->terms_dev.p, td.data(), td.size() * sizeof(TermDev), cudaMemcpyHostToDevice, f->stream));
     TAD_CUDA(cudaStreamSynchronize(f->stream));  // td is a local
+    f->terms_dev_host = td;
     return TAD_OK;
 }
 
@@ -1551,6 +1631,23 @@ int build_pattern_scalar(tad_function f)
     }
     f->n_blocks = n_blocks;
     f->n_outer = f->n_vars;
+    // host copy of the vertex rows (row finality of the slab schedule) and the per-term packed-index tables of the gather assembly
+    f->vrow_host.assign((size_t)f->n_handles + 1, 0);
+    TAD_CUDA(cudaMemcpy(f->vrow_host.data(), f->vrow.p, ((size_t)f->n_handles + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    {
+        std::vector<SeqTable> seqs(std::max<size_t>(f->terms.size(), 1));
+        for (size_t ti = 0; ti < f->terms.size(); ++ti)
+        {
+            const int K = f->terms[ti].k;
+            if (K > 18) continue;  // gather assembly reports TAD_NOT_SUPPORTED for such a term
+            for (int i = 0; i < K; ++i)
+                for (int j = 0; j < K; ++j) seqs[ti].idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);
+        }
+        TAD_CUDA(f->seqs_dev.ensure(seqs.size() * sizeof(SeqTable)));
+        TAD_CUDA(cudaMemcpy(f->seqs_dev.p, seqs.data(), seqs.size() * sizeof(SeqTable), cudaMemcpyHostToDevice));
+    }
+    f->sched[0].clear();
+    f->sched[1].clear();
     f->pattern_built = true;
     return TAD_OK;
 }
@@ -1634,123 +1731,313 @@ struct DeviceGuard
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-void tic(tad_function f, int i) { if (f->timing) cudaEventRecord(f->ev[i], f->stream); }
+// Smallest variable handle touched by the elements [e_begin, e_begin + n) of a term (one block per slab).
+__global__ void __launch_bounds__(256) slab_min_vertex(const int32_t* __restrict__ rec, int N, int64_t stride, const int64_t* __restrict__ begin,
+                                                       const int64_t* __restrict__ count, int32_t* __restrict__ out)
+{
+    __shared__ int32_t sh[256];
+    const int64_t e0 = begin[blockIdx.x], n = count[blockIdx.x];
+    int32_t m = INT32_MAX;
+    for (int64_t i = threadIdx.x; i < n; i += 256)
+        for (int j = 0; j < N; ++j)
+        {
+            const int32_t v = rec[(int64_t)j * stride + e0 + i];
+            if (v >= 0 && v < m) m = v;
+        }
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] = min(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
 
-// Scalar function evaluation core.  mode: PASSIVE / FIRST / SECOND.
-int eval_scalar(tad_function f, int mode, const double* x, double* f_host, double* g, double* Hv, bool project, double eps)
+// Default slab sizes (C2, one B200, sweep in profiles/r02_slab_sweep.txt): a slab costs ~0.1-0.2 ms of launch gaps and partial
+// waves, so the device-resident path uses large slabs on two lanes (a little faster than one slab per term, and memory-bounded),
+// while the host-buffer path trades some of that for a finer-grained overlap of the D2H copies with the assembly.
+constexpr int64_t kDefaultChunkDevice = 524288, kDefaultChunkHost = 131072;
+
+int64_t effective_chunk(tad_function f, bool whole_terms, bool host_path)
+{
+    if (whole_terms || f->chunk < 0) return -1;
+    static const int64_t env_chunk = [] { const char* e = getenv("TAD_CHUNK_ELEMENTS"); return e ? (int64_t)atoll(e) : (int64_t)0; }();
+    int64_t c = f->chunk > 0 ? f->chunk : (env_chunk != 0 ? env_chunk : (host_path ? kDefaultChunkHost : kDefaultChunkDevice));
+    if (c < 0) return -1;
+    return ((c + 255) / 256) * 256;  // multiples of 256: the partial sums of f do not depend on the slab size
+}
+
+// The slab schedule of an evaluation.  Atomic assembly: terms in ascending size (a small term -- e.g. a few penalty elements on
+// arbitrary vertices -- would otherwise keep rows "open" until the very end), slabs of `chunk` elements; for second-order
+// evaluations each slab records how many leading CSR values are final once it is complete (rows of vertices below the smallest
+// vertex any LATER slab touches), which is what the host-buffer entry points copy out while later slabs are assembled.
+// Gather assembly: terms in their own order, one slab per term (its kernels read every term's complete staging).
+int build_schedule(tad_function f, int mode, bool whole_terms, bool host_path, tad_function_s::Schedule** out)
+{
+    tad_function_s::Schedule& S = f->sched[host_path ? 1 : 0];
+    *out = &S;
+    const int64_t chunk = effective_chunk(f, whole_terms, host_path);
+    const bool cached = S.chunk == chunk && S.whole == whole_terms && (!S.slabs.empty() || f->n_elements == 0);
+    if (cached && (S.has_final || mode != TAD_MODE_SECOND)) return TAD_OK;
+    if (!cached)
+    {
+        S.clear();
+        std::vector<int> order(f->terms.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        if (!whole_terms) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return f->terms[(size_t)a].n < f->terms[(size_t)b].n; });
+        for (int ti : order)
+        {
+            const Term& t = f->terms[(size_t)ti];
+            if (t.n <= 0) continue;
+            const int64_t step = chunk > 0 ? chunk : t.n;
+            for (int64_t e0 = 0; e0 < t.n; e0 += step) S.slabs.push_back(Slab{ti, e0, std::min(step, t.n - e0), 0});
+        }
+        S.chunk = chunk;
+        S.whole = whole_terms;
+    }
+    const size_t ns = S.slabs.size();
+    if (mode == TAD_MODE_SECOND && !f->is_vector && f->pattern_built && ns > 0)
+    {
+        std::vector<int32_t> vmin(ns, INT32_MAX);
+        if (ns > 1)
+        {
+            std::vector<int64_t> hb(ns), hc(ns);
+            DevBuf<int64_t> db, dc;
+            DevBuf<int32_t> dout;
+            TAD_CUDA(db.ensure(ns)); TAD_CUDA(dc.ensure(ns)); TAD_CUDA(dout.ensure(ns));
+            for (size_t ti = 0; ti < f->terms.size(); ++ti)
+            {
+                // slabs of one term are contiguous in the schedule
+                size_t first = ns, cnt = 0;
+                for (size_t q = 0; q < ns; ++q)
+                    if (S.slabs[q].term == (int)ti) { if (first == ns) first = q; hb[cnt] = S.slabs[q].e_begin; hc[cnt] = S.slabs[q].n; ++cnt; }
+                if (!cnt) continue;
+                const Term& t = f->terms[ti];
+                TAD_CUDA(cudaMemcpyAsync(db.p, hb.data(), cnt * sizeof(int64_t), cudaMemcpyHostToDevice, f->stream));
+                TAD_CUDA(cudaMemcpyAsync(dc.p, hc.data(), cnt * sizeof(int64_t), cudaMemcpyHostToDevice, f->stream));
+                slab_min_vertex<<<(unsigned)cnt, 256, 0, f->stream>>>(t.rec_handles.p, t.N, t.stride, db.p, dc.p, dout.p);
+                TAD_CUDA(cudaMemcpyAsync(vmin.data() + first, dout.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+                TAD_CUDA(cudaStreamSynchronize(f->stream));
+            }
+        }
+        const int64_t dd = (int64_t)f->d * f->d;
+        int64_t later = INT64_MAX;  // smallest vertex touched by the slabs after q
+        for (size_t q = ns; q-- > 0;)
+        {
+            S.slabs[q].final_values = (later == INT64_MAX || f->vrow_host.empty()) ? f->nnz : dd * f->vrow_host[(size_t)std::min<int64_t>(later, f->n_handles)];
+            if (vmin[q] != INT32_MAX) later = std::min<int64_t>(later, vmin[q]);
+        }
+        S.has_final = true;
+    }
+    return TAD_OK;
+}
+
+int ensure_lanes(tad_function f, int n)
+{
+    while ((int)f->lanes.size() < n)
+    {
+        f->lanes.emplace_back();
+        Lane& L = f->lanes.back();
+        TAD_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        if (cudaStreamCreateWithFlags(&L.side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&L.side.ev_b, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&L.side.ev_list, cudaEventDisableTiming) != cudaSuccess)
+            L.side = ProjSide();  // no side stream: the list kernel stays on the lane's stream
+        for (auto& e : L.tev) TAD_CUDA(cudaEventCreate(&e));
+        TAD_CUDA(L.counts.ensure(4));
+    }
+    return TAD_OK;
+}
+
+int ensure_slab_events(tad_function f, size_t n)
+{
+    while (f->slab_events.size() < n)
+    {
+        cudaEvent_t e = nullptr;
+        TAD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        f->slab_events.push_back(e);
+    }
+    return TAD_OK;
+}
+
+// Every evaluation first waits for the work queued on the registered caller stream (tad_function_set_caller_stream).
+int wait_for_caller(tad_function f)
+{
+    if (!f->wait_caller) return TAD_OK;
+    TAD_CUDA(cudaEventRecord(f->ev_caller, f->caller_stream));
+    TAD_CUDA(cudaStreamWaitEvent(f->stream, f->ev_caller, 0));
+    return TAD_OK;
+}
+
+// Scalar function evaluation core.  mode: PASSIVE / FIRST / SECOND.  x, g, Hv: device pointers.  hc (optional): host
+// destinations of g and the CSR values; the values are copied out slab by slab on the copy stream as their rows become final.
+int eval_scalar(tad_function f, int mode, const double* x, double* f_host, double* g, double* Hv, bool project, double eps, const HostCopy* hc)
 {
     if (f->is_vector) return fail(TAD_INVALID_ARGUMENT, "scalar evaluation called on a vector function");
     if (!x && f->n_vars) return fail(TAD_INVALID_ARGUMENT, "x is null");
     std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
+    LaunchCounterScope counter(&f->n_launches);
     cudaStream_t st = f->stream;
     const int n_terms = (int)f->terms.size();
     if (mode == TAD_MODE_SECOND) TAD_TRY(ensure_pattern(f));
+    TAD_TRY(wait_for_caller(f));
     TAD_CUDA(cudaMemsetAsync(f->err.p, 0, 8 * sizeof(int32_t), st));
     TAD_CUDA(f->fterm.ensure((size_t)std::max(n_terms, 1)));
     const bool gather = (f->assembly == TAD_ASSEMBLY_GATHER) && mode == TAD_MODE_SECOND;
-    if (gather && !f->pattern_built) TAD_TRY(ensure_pattern(f));
     if (mode >= TAD_MODE_FIRST && !gather) TAD_CUDA(cudaMemsetAsync(g, 0, (size_t)f->n_vars * sizeof(double), st));
     if (mode == TAD_MODE_SECOND && !gather && f->nnz) TAD_CUDA(cudaMemsetAsync(Hv, 0, (size_t)f->nnz * sizeof(double), st));
-    if (mode == TAD_MODE_SECOND && project)
+    tad_function_s::Schedule* schedule = nullptr;
+    TAD_TRY(build_schedule(f, mode, gather, hc != nullptr, &schedule));
+    const std::vector<Slab>& sched = schedule->slabs;
+    const int n_slabs = (int)sched.size();
+    static const int env_lanes = [] { const char* e = getenv("TAD_LANES"); return e ? atoi(e) : 0; }();
+    const int want_lanes = env_lanes > 0 ? std::min(env_lanes, 4) : f->n_lanes;
+    const int n_lanes = std::max(1, std::min((f->timing || gather) ? 1 : want_lanes, std::max(n_slabs, 1)));
+    TAD_TRY(ensure_lanes(f, n_lanes));
+    TAD_TRY(ensure_slab_events(f, (size_t)n_slabs));
+
+    // partial sums of f: one per 256 elements, laid out term by term (independent of the slab size)
+    std::vector<int64_t> part_off((size_t)n_terms + 1, 0);
+    for (int ti = 0; ti < n_terms; ++ti) part_off[(size_t)ti + 1] = part_off[(size_t)ti] + (f->terms[(size_t)ti].n + 255) / 256;
+    TAD_CUDA(f->fpart.ensure((size_t)std::max<int64_t>(1, part_off[(size_t)n_terms])));
+
+    TAD_CUDA(cudaEventRecord(f->ev[0], st));
+    for (int l = 0; l < n_lanes; ++l)
     {
-        TAD_CUDA(f->proj_counts.ensure(4));
-        TAD_CUDA(cudaMemsetAsync(f->proj_counts.p, 0, 4 * sizeof(unsigned long long), st));
-        int64_t max_n = 0;
-        size_t max_scratch = 1;
-        for (auto& t : f->terms)
-        {
-            max_n = std::max(max_n, t.stride);
-            max_scratch = std::max(max_scratch, project_scratch_doubles_rt(t.k, t.stride));
-        }
-        TAD_CUDA(f->proj_list.ensure((size_t)std::max<int64_t>(max_n, 1)));
-        TAD_CUDA(f->proj_codes.ensure((size_t)std::max<int64_t>(max_n, 1)));
-        if (!f->projection_full) TAD_CUDA(f->proj_scratch.ensure(max_scratch));
+        Lane& L = f->lanes[(size_t)l];
+        TAD_CUDA(cudaStreamWaitEvent(L.stream, f->ev[0], 0));
+        if (mode == TAD_MODE_SECOND && project) TAD_CUDA(cudaMemsetAsync(L.counts.p, 0, 4 * sizeof(unsigned long long), L.stream));
     }
     float ms_eval = 0, ms_proj = 0, ms_asm = 0;
-    tic(f, 0);
-    for (int ti = 0; ti < n_terms; ++ti)
+    for (int q = 0; q < n_slabs; ++q)
     {
-        Term& t = f->terms[ti];
-        if (mode == TAD_MODE_SECOND && t.dedup && false) return TAD_NOT_SUPPORTED;
-        DevBuf<double>& stage = gather ? t.stage : f->stage;
-        TAD_CUDA(stage.ensure(stage_doubles(t, mode)));
+        const Slab& sl = sched[(size_t)q];
+        Term& t = f->terms[(size_t)sl.term];
+        Lane& L = f->lanes[(size_t)(q % n_lanes)];
+        cudaStream_t ls = L.stream;
+        const int64_t sstride = ((sl.n + 31) / 32) * 32;
+        DevBuf<double>& stage = gather ? t.stage : L.stage;
+        TAD_CUDA(stage.ensure(stage_doubles(t, mode, sstride)));
         tad_launch_args a;
-        fill_launch_args(f, t, mode, x, stage.p, a);
-        if (f->timing) cudaEventRecord(f->ev[1], st);
-        if (t.n > 0)
+        fill_launch_args(f, t, mode, x, stage.p, sl.e_begin, sl.n, sstride, ls, a);
+        if (f->timing) cudaEventRecord(L.tev[0], ls);
         {
             const int s = t.launch(t.user, &a);
             if (s != TAD_OK) return fail(s, "element kernel launch failed");
         }
-        if (f->timing) cudaEventRecord(f->ev[2], st);
-        TAD_TRY(sum_to(f, a.val, t.n, t.stride, 1, false, f->fterm.p + ti));
-        if (mode == TAD_MODE_SECOND && project && ti > 0)  // the fallback list is per term
-            TAD_CUDA(cudaMemsetAsync(f->proj_counts.p + 2, 0, sizeof(unsigned long long), st));
+        if (f->timing) cudaEventRecord(L.tev[1], ls);
+        count_launch();
+        reduce_stage1<false><<<(unsigned)((sl.n + 255) / 256), 256, 0, ls>>>(a.val, sl.n, sstride, 1, f->fpart.p + part_off[(size_t)sl.term] + sl.e_begin / 256);
         // atomic mode + fast projection: the last projection phase (low-rank update) is fused with the scatter
         const bool fuse = mode == TAD_MODE_SECOND && project && !gather && !f->projection_full && fused_c_assemble_supported(f->d, t.N);
         ProjScratch fused_sc;
         if (mode == TAD_MODE_SECOND && project)
-            TAD_TRY(project_dispatch(t.k, a.hess, t.n, t.stride, eps, f->proj_counts.p, f->proj_scratch.p, f->proj_codes.p, f->proj_list.p,
-                                     f->projection_full != 0, fuse ? &fused_sc : nullptr, fuse ? &f->proj_side : nullptr, st));
-        if (f->timing) cudaEventRecord(f->ev[3], st);
+        {
+            TAD_CUDA(L.proj_list.ensure((size_t)sstride));
+            TAD_CUDA(L.proj_codes.ensure((size_t)sstride));
+            if (!f->projection_full) TAD_CUDA(L.proj_scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(t.k, sstride))));
+            TAD_CUDA(cudaMemsetAsync(L.counts.p + 2, 0, sizeof(unsigned long long), ls));  // the list of the full solver is per slab
+            TAD_TRY(project_dispatch(t.k, a.hess, sl.n, sstride, eps, L.counts.p, L.proj_scratch.p, L.proj_codes.p, L.proj_list.p,
+                                     f->projection_full != 0, fuse ? &fused_sc : nullptr, fuse ? &L.side : nullptr, ls));
+        }
+        if (f->timing) cudaEventRecord(L.tev[2], ls);
+        const SlabMaps maps{t.rec_handles.p + sl.e_begin, t.blockbase.p ? t.blockbase.p + sl.e_begin : nullptr,
+                            t.rstride.p ? t.rstride.p + sl.e_begin : nullptr, t.stride};
         if (fuse)
-            TAD_TRY(c_assemble(f->d, t, a.grad, a.hess, t.n, eps, fused_sc, g, Hv, f->err.p, f->proj_counts.p, &f->proj_side, st));
+            TAD_TRY(c_assemble(f->d, t.N, maps, a.grad, a.hess, sl.n, sstride, eps, fused_sc, g, Hv, f->err.p, L.counts.p, &L.side, ls));
         else if (mode >= TAD_MODE_FIRST && !gather)
-            TAD_TRY(assemble_atomic(f->d, t, a.grad, mode == TAD_MODE_SECOND ? a.hess : nullptr, t.n, g, Hv, f->err.p, st));
+            TAD_TRY(assemble_atomic(f->d, t.N, maps, a.grad, mode == TAD_MODE_SECOND ? a.hess : nullptr, sl.n, sstride, g, Hv, f->err.p, ls));
+        TAD_CUDA(cudaEventRecord(f->slab_events[(size_t)q], ls));
         if (f->timing)
         {
-            cudaEventRecord(f->ev[4], st);
-            cudaEventSynchronize(f->ev[4]);
+            cudaEventRecord(L.tev[3], ls);
+            cudaEventSynchronize(L.tev[3]);
             float m = 0;
-            cudaEventElapsedTime(&m, f->ev[1], f->ev[2]); ms_eval += m;
-            cudaEventElapsedTime(&m, f->ev[2], f->ev[3]); ms_proj += m;
-            cudaEventElapsedTime(&m, f->ev[3], f->ev[4]); ms_asm += m;
+            cudaEventElapsedTime(&m, L.tev[0], L.tev[1]); ms_eval += m;
+            cudaEventElapsedTime(&m, L.tev[1], L.tev[2]); ms_proj += m;
+            cudaEventElapsedTime(&m, L.tev[2], L.tev[3]); ms_asm += m;
         }
+    }
+    // pipelined D2H of the rows that are final (all slabs are queued by now, so a pageable destination, whose copies block the
+    // host, cannot starve the GPU)
+    int64_t copied = 0;
+    if (hc && hc->H_host && mode == TAD_MODE_SECOND && !gather)
+        for (int q = 0; q < n_slabs; ++q)
+        {
+            TAD_CUDA(cudaStreamWaitEvent(f->copy_stream, f->slab_events[(size_t)q], 0));
+            const int64_t fin = std::min(sched[(size_t)q].final_values, f->nnz);
+            if (fin > copied)
+            {
+                TAD_CUDA(cudaMemcpyAsync(hc->H_host + copied, Hv + copied, (size_t)(fin - copied) * sizeof(double), cudaMemcpyDeviceToHost, f->copy_stream));
+                copied = fin;
+            }
+        }
+    // the main stream continues after the last slab of every lane
+    for (int q = std::max(0, n_slabs - n_lanes); q < n_slabs; ++q) TAD_CUDA(cudaStreamWaitEvent(st, f->slab_events[(size_t)q], 0));
+    for (int ti = 0; ti < n_terms; ++ti)
+    {
+        const int64_t nb = part_off[(size_t)ti + 1] - part_off[(size_t)ti];
+        if (nb > 0) { count_launch(); reduce_stage2<<<1, 1024, 0, st>>>(f->fpart.p + part_off[(size_t)ti], nb, f->fterm.p + ti); }
+        else TAD_CUDA(cudaMemsetAsync(f->fterm.p + ti, 0, sizeof(double), st));
     }
     if (gather)
     {
-        if (f->timing) cudaEventRecord(f->ev[3], st);
+        for (const Term& t : f->terms)
+            if (t.k > 18) return fail(TAD_NOT_SUPPORTED, "gather assembly supports at most 18 variables per element");
+        cudaEvent_t g0 = f->lanes[0].tev[0], g1 = f->lanes[0].tev[1];
+        if (f->timing) cudaEventRecord(g0, st);
         TAD_TRY(upload_terms_dev(f, true, mode));
-        std::vector<SeqTable> seqs((size_t)std::max(n_terms, 1));
-        for (int ti = 0; ti < n_terms; ++ti)
-        {
-            const int K = f->terms[ti].k;
-            if (K > 18) return fail(TAD_NOT_SUPPORTED, "gather assembly supports at most 18 variables per element");
-            for (int i = 0; i < K; ++i)
-                for (int j = 0; j < K; ++j) seqs[ti].idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);
-        }
-        DevBuf<SeqTable> seqs_d;
-        TAD_CUDA(seqs_d.ensure(seqs.size()));
-        TAD_CUDA(cudaMemcpyAsync(seqs_d.p, seqs.data(), seqs.size() * sizeof(SeqTable), cudaMemcpyHostToDevice, st));
         const int64_t nt = f->n_blocks * f->d * f->d;
+        count_launch(nt > 0 ? 2 : 1);
         if (nt > 0)
-            gather_hessian<<<blocks_for(nt, 128), 128, 0, st>>>(f->block_ptr.p, f->contrib.p, f->block_key.p, f->vrow.p, f->terms_dev.p,
-                                                                n_terms, seqs_d.p, f->n_blocks, f->n_handles, f->d, Hv, f->err.p);
+            gather_hessian<<<blocks_for(nt, 128), 128, 0, st>>>(f->block_ptr.p, f->contrib.p, f->block_key.p, f->vrow.p, f->terms_dev.p, n_terms,
+                                                                reinterpret_cast<const SeqTable*>(f->seqs_dev.p), f->n_blocks, f->n_handles, f->d, Hv, f->err.p);
         gather_gradient<<<blocks_for(f->n_vars, 128), 128, 0, st>>>(f->block_ptr.p, f->contrib.p, f->block_key.p, f->terms_dev.p, n_terms,
                                                                     f->n_blocks, f->n_handles, f->d, g, f->err.p);
         TAD_CUDA(cudaGetLastError());
-        TAD_CUDA(cudaStreamSynchronize(st));  // seqs_d is a local
         if (f->timing)
         {
-            cudaEventRecord(f->ev[4], st);
-            cudaEventSynchronize(f->ev[4]);
+            cudaEventRecord(g1, st);
+            cudaEventSynchronize(g1);
             float m = 0;
-            cudaEventElapsedTime(&m, f->ev[3], f->ev[4]); ms_asm += m;
+            cudaEventElapsedTime(&m, g0, g1); ms_asm += m;
         }
+    }
+    TAD_CUDA(cudaEventRecord(f->ev[1], st));
+    if (hc)
+    {
+        // what is left: g (complete only now) and any CSR values not final before the end
+        TAD_CUDA(cudaStreamWaitEvent(f->copy_stream, f->ev[1], 0));
+        if (hc->g_host && mode >= TAD_MODE_FIRST)
+            TAD_CUDA(cudaMemcpyAsync(hc->g_host, g, (size_t)f->n_vars * sizeof(double), cudaMemcpyDeviceToHost, f->copy_stream));
+        if (hc->H_host && mode == TAD_MODE_SECOND && f->nnz > copied)
+            TAD_CUDA(cudaMemcpyAsync(hc->H_host + copied, Hv + copied, (size_t)(f->nnz - copied) * sizeof(double), cudaMemcpyDeviceToHost, f->copy_stream));
     }
     // f = sum over terms in order, with the reference's INFINITY short-circuit for eval() (ScalarFunctionImpl.hh:265-270)
     std::vector<double> fterm((size_t)std::max(n_terms, 1), 0.0);
     if (n_terms)
         TAD_CUDA(cudaMemcpyAsync(fterm.data(), f->fterm.p, (size_t)n_terms * sizeof(double), cudaMemcpyDeviceToHost, st));
+    unsigned long long lane_counts[4][4] = {};
     if (mode == TAD_MODE_SECOND && project)
-        TAD_CUDA(cudaMemcpyAsync(f->last_proj, f->proj_counts.p, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        for (int l = 0; l < n_lanes; ++l)
+            TAD_CUDA(cudaMemcpyAsync(lane_counts[l], f->lanes[(size_t)l].counts.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     TAD_CUDA(cudaStreamSynchronize(st));
+    if (hc) TAD_CUDA(cudaStreamSynchronize(f->copy_stream));
+    if (mode == TAD_MODE_SECOND && project)
+    {
+        f->last_proj[0] = f->last_proj[1] = f->last_proj[2] = 0;
+        for (int l = 0; l < n_lanes; ++l)
+        {
+            f->last_proj[0] += (int64_t)lane_counts[l][0];
+            f->last_proj[1] += (int64_t)lane_counts[l][1];
+            f->last_proj[2] += (int64_t)lane_counts[l][3];
+        }
+    }
     if (f->timing)
     {
-        cudaEventRecord(f->ev[4], st);
-        cudaEventSynchronize(f->ev[4]);
-        cudaEventElapsedTime(&f->last_ms[3], f->ev[0], f->ev[4]);
+        cudaEventElapsedTime(&f->last_ms[3], f->ev[0], f->ev[1]);
         f->last_ms[0] = ms_eval; f->last_ms[1] = ms_proj; f->last_ms[2] = ms_asm;
     }
     double fv = 0.0;
@@ -1771,8 +2058,10 @@ int eval_vector(tad_function f, int what, const double* x, double* f_host, doubl
     if (!f->is_vector) return fail(TAD_INVALID_ARGUMENT, "vector evaluation called on a scalar function");
     std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
+    LaunchCounterScope counter(&f->n_launches);
     cudaStream_t st = f->stream;
     TAD_TRY(ensure_pattern(f));
+    TAD_TRY(wait_for_caller(f));
     const int n_terms = (int)f->terms.size();
     const int mode = (what == 1 || what == 3) ? TAD_MODE_FIRST : TAD_MODE_PASSIVE;
     TAD_CUDA(cudaMemsetAsync(f->err.p, 0, 8 * sizeof(int32_t), st));
@@ -1790,9 +2079,15 @@ int eval_vector(tad_function f, int what, const double* x, double* f_host, doubl
         }
         if (what == 2) TAD_TRY(sum_to(f, a.val, t.n, t.stride, t.M, true, f->fterm.p + ti));
         if (what != 2 && t.n > 0)
+        {
+            count_launch();
             scatter_residuals<<<blocks_for(t.n * t.M, 256), 256, 0, st>>>(a.val, t.n, t.stride, t.M, t.out_offset, r);
+        }
         if (mode == TAD_MODE_FIRST && t.n > 0)
+        {
+            count_launch();
             scatter_jacobian<<<blocks_for(t.n, 128), 128, 0, st>>>(a.grad, t.jslot.p, t.n, t.stride, t.M * t.k, Jv, f->err.p);
+        }
     }
     double fv = 0.0;
     if (what == 2)
@@ -1805,6 +2100,7 @@ int eval_vector(tad_function f, int what, const double* x, double* f_host, doubl
     else if (what == 3)
     {
         TAD_TRY(sum_to(f, r, f->n_outputs, f->n_outputs, 1, true, f->fterm.p + n_terms));
+        count_launch();
         jt_r<<<blocks_for(f->n_vars, 128), 128, 0, st>>>(f->outer.p, f->inner.p, Jv, r, f->n_vars, g);
         TAD_CUDA(cudaMemcpyAsync(&fv, f->fterm.p + n_terms, sizeof(double), cudaMemcpyDeviceToHost, st));
         TAD_CUDA(cudaStreamSynchronize(st));
@@ -1854,16 +2150,13 @@ int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector
     f->n_vars = (int64_t)variable_dimension * n_handles;
     f->is_vector = is_vector_function != 0;
     f->device = device;
-    if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess || f->err.ensure(8) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess || f->err.ensure(8) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&f->ev[0]) != cudaSuccess ||
+        cudaEventCreate(&f->ev[1]) != cudaSuccess || cudaEventCreateWithFlags(&f->ev_caller, cudaEventDisableTiming) != cudaSuccess)
     {
-        delete f;
+        tad_function_destroy(f);
         return fail(TAD_CUDA_ERROR, "stream / buffer creation failed");
     }
-    for (auto& e : f->ev) cudaEventCreate(&e);
-    if (cudaStreamCreateWithFlags(&f->proj_side.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&f->proj_side.ev_b, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&f->proj_side.ev_list, cudaEventDisableTiming) != cudaSuccess)
-        f->proj_side = ProjSide();  // no side stream: the list kernel stays on the main stream
     *out = f;
     return TAD_OK;
 }
@@ -1871,20 +2164,25 @@ int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector
 void tad_function_destroy(tad_function f)
 {
     if (!f) return;
-    {
-        DeviceGuard guard(f->device);
-        cudaStreamSynchronize(f->stream);
-        for (auto& t : f->terms)
-            if (t.user_free && t.user) t.user_free(t.user);
-        f->terms.clear();
-        for (auto& e : f->ev) if (e) cudaEventDestroy(e);
-        if (f->proj_side.ev_b) cudaEventDestroy(f->proj_side.ev_b);
-        if (f->proj_side.ev_list) cudaEventDestroy(f->proj_side.ev_list);
-        if (f->proj_side.stream) cudaStreamDestroy(f->proj_side.stream);
-        cudaStreamDestroy(f->stream);
-    }
     DeviceGuard guard(f->device);
-    delete f;
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    for (auto& t : f->terms)
+        if (t.user_free && t.user) t.user_free(t.user);
+    f->terms.clear();
+    for (auto& L : f->lanes)
+    {
+        if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+        if (L.side.ev_b) cudaEventDestroy(L.side.ev_b);
+        if (L.side.ev_list) cudaEventDestroy(L.side.ev_list);
+        if (L.side.stream) cudaStreamDestroy(L.side.stream);
+        for (auto& e : L.tev) if (e) cudaEventDestroy(e);
+    }
+    for (auto& e : f->slab_events) cudaEventDestroy(e);
+    for (auto& e : f->ev) if (e) cudaEventDestroy(e);
+    if (f->ev_caller) cudaEventDestroy(f->ev_caller);
+    if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;  // device buffers are freed here, still under the device guard
 }
 
 int tad_function_set_option(tad_function f, int option, int64_t value)
@@ -1896,8 +2194,12 @@ int tad_function_set_option(tad_function f, int option, int64_t value)
         if (value != TAD_ASSEMBLY_ATOMIC && value != TAD_ASSEMBLY_GATHER) return fail(TAD_INVALID_ARGUMENT, "bad assembly mode");
         f->assembly = (int)value;
         return TAD_OK;
-    case TAD_OPT_CHUNK_ELEMENTS: f->chunk = value; return TAD_OK;
+    case TAD_OPT_CHUNK_ELEMENTS: { std::lock_guard<std::recursive_mutex> lock(f->mtx); f->chunk = value; return TAD_OK; }
     case TAD_OPT_PROJECTION: f->projection_full = value != 0; return TAD_OK;
+    case TAD_OPT_LANES:
+        if (value < 1 || value > 4) return fail(TAD_INVALID_ARGUMENT, "lanes must be in 1..4");
+        f->n_lanes = (int)value;
+        return TAD_OK;
     default: return fail(TAD_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -1906,6 +2208,23 @@ int tad_function_get_stream(tad_function f, void** stream)
 {
     if (!f || !stream) return fail(TAD_INVALID_ARGUMENT, "null argument");
     *stream = f->stream;
+    return TAD_OK;
+}
+
+int tad_function_set_caller_stream(tad_function f, void* stream, int enabled)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
+    f->caller_stream = static_cast<cudaStream_t>(stream);
+    f->wait_caller = enabled != 0;
+    return TAD_OK;
+}
+
+int tad_function_launch_count(tad_function f, int64_t* count)
+{
+    if (!f || !count) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
+    *count = f->n_launches;
     return TAD_OK;
 }
 
@@ -1943,6 +2262,7 @@ int tad_function_add_term(tad_function f, int valence, int outputs_per_element, 
         const int s = launch(user, &a);
         if (s != TAD_OK) { if (user_free && user) user_free(user); return fail(s, "record kernel launch failed"); }
         scan_counts<<<blocks_for(n_elements, 256), 256, 0, f->stream>>>(t.rec_counts.p, n_elements, f->err.p + 1);
+        f->n_launches += 1;
     }
     int32_t h_err[2] = {0, 0};
     if ((ce = cudaStreamSynchronize(f->stream)) != cudaSuccess) return cuda_bail(ce);
@@ -1954,6 +2274,8 @@ int tad_function_add_term(tad_function f, int valence, int outputs_per_element, 
     f->n_outputs += (int64_t)outputs_per_element * n_elements;
     f->terms.push_back(std::move(t));
     f->pattern_built = false;
+    f->sched[0].clear();
+    f->sched[1].clear();
     return TAD_OK;
 }
 
@@ -2022,49 +2344,53 @@ int tad_function_term_table(tad_function f, int term, int32_t* handles_host)
 int tad_eval(tad_function f, const double* x_dev, double* f_host)
 {
     if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
-    return eval_scalar(f, TAD_MODE_PASSIVE, x_dev, f_host, nullptr, nullptr, false, 0.0);
+    return eval_scalar(f, TAD_MODE_PASSIVE, x_dev, f_host, nullptr, nullptr, false, 0.0, nullptr);
 }
 
 int tad_eval_with_gradient(tad_function f, const double* x_dev, double* f_host, double* g_dev)
 {
     if (!f || !g_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
-    return eval_scalar(f, TAD_MODE_FIRST, x_dev, f_host, g_dev, nullptr, false, 0.0);
+    return eval_scalar(f, TAD_MODE_FIRST, x_dev, f_host, g_dev, nullptr, false, 0.0, nullptr);
 }
 
 int tad_eval_with_derivatives(tad_function f, const double* x_dev, double* f_host, double* g_dev, double* H_values_dev,
                               int project_hessian, double projection_eps)
 {
     if (!f || !g_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
-    return eval_scalar(f, TAD_MODE_SECOND, x_dev, f_host, g_dev, H_values_dev, project_hessian != 0, projection_eps);
+    return eval_scalar(f, TAD_MODE_SECOND, x_dev, f_host, g_dev, H_values_dev, project_hessian != 0, projection_eps, nullptr);
 }
 
+// Host-buffer entry points.  The function's own device buffers (x_dev / g_dev / H_dev) are shared state, so the function
+// mutex is held from the H2D of x to the last D2H: concurrent calls on one function object (the reference's scenario,
+// tests/ScalarFunctionTest.cc:255-291) are serialised as a whole and cannot see each other's x or results.
 int tad_eval_host(tad_function f, const double* x_host, double* f_host)
 {
     if (!f || !x_host) return fail(TAD_INVALID_ARGUMENT, "null argument");
-    {
-        DeviceGuard guard(f->device);
-        TAD_CUDA(f->x_dev.ensure((size_t)f->n_vars));
-        TAD_CUDA(cudaMemcpyAsync(f->x_dev.p, x_host, (size_t)f->n_vars * sizeof(double), cudaMemcpyHostToDevice, f->stream));
-    }
-    return tad_eval(f, f->x_dev.p, f_host);
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    TAD_CUDA(f->x_dev.ensure((size_t)f->n_vars));
+    TAD_CUDA(cudaMemcpyAsync(f->x_dev.p, x_host, (size_t)f->n_vars * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    return eval_scalar(f, TAD_MODE_PASSIVE, f->x_dev.p, f_host, nullptr, nullptr, false, 0.0, nullptr);
 }
 
 int tad_eval_with_gradient_host(tad_function f, const double* x_host, double* f_host, double* g_host)
 {
     if (!f || !x_host || !g_host) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     TAD_CUDA(f->x_dev.ensure((size_t)f->n_vars));
     TAD_CUDA(f->g_dev.ensure((size_t)f->n_vars));
     TAD_CUDA(cudaMemcpyAsync(f->x_dev.p, x_host, (size_t)f->n_vars * sizeof(double), cudaMemcpyHostToDevice, f->stream));
-    TAD_TRY(tad_eval_with_gradient(f, f->x_dev.p, f_host, f->g_dev.p));
-    TAD_CUDA(cudaMemcpy(g_host, f->g_dev.p, (size_t)f->n_vars * sizeof(double), cudaMemcpyDeviceToHost));
-    return TAD_OK;
+    HostCopy hc;
+    hc.g_host = g_host;
+    return eval_scalar(f, TAD_MODE_FIRST, f->x_dev.p, f_host, f->g_dev.p, nullptr, false, 0.0, &hc);
 }
 
 int tad_eval_with_derivatives_host(tad_function f, const double* x_host, double* f_host, double* g_host, double* H_values_host,
                                    int project_hessian, double projection_eps)
 {
     if (!f || !x_host || !g_host) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
     int64_t nnz = 0;
     TAD_TRY(tad_function_pattern(f, nullptr, &nnz));
@@ -2073,11 +2399,11 @@ int tad_eval_with_derivatives_host(tad_function f, const double* x_host, double*
     TAD_CUDA(f->g_dev.ensure((size_t)f->n_vars));
     TAD_CUDA(f->H_dev.ensure((size_t)std::max<int64_t>(nnz, 1)));
     TAD_CUDA(cudaMemcpyAsync(f->x_dev.p, x_host, (size_t)f->n_vars * sizeof(double), cudaMemcpyHostToDevice, f->stream));
-    TAD_TRY(tad_eval_with_derivatives(f, f->x_dev.p, f_host, f->g_dev.p, f->H_dev.p, project_hessian, projection_eps));
-    TAD_CUDA(cudaMemcpyAsync(g_host, f->g_dev.p, (size_t)f->n_vars * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
-    if (nnz) TAD_CUDA(cudaMemcpyAsync(H_values_host, f->H_dev.p, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
-    TAD_CUDA(cudaStreamSynchronize(f->stream));
-    return TAD_OK;
+    HostCopy hc;
+    hc.g_host = g_host;
+    hc.H_host = H_values_host;
+    // the D2H of the CSR values is pipelined with the evaluation inside eval_scalar
+    return eval_scalar(f, TAD_MODE_SECOND, f->x_dev.p, f_host, f->g_dev.p, f->H_dev.p, project_hessian != 0, projection_eps, &hc);
 }
 
 int tad_veval(tad_function f, const double* x_dev, double* r_dev)
@@ -2122,10 +2448,7 @@ int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double
     TAD_CUDA(codes.ensure((size_t)std::max<int64_t>(stride, 1)));
     if (method != 1) TAD_CUDA(scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(k, stride))));
     TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts, scratch.p, codes.p, list.p, method == 1, nullptr, nullptr, st));
-    unsigned long long h_counts[3] = {0, 0, 0};
-    TAD_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     TAD_CUDA(cudaStreamSynchronize(st));  // the scratch buffers above are locals
-    (void)h_counts;
     return TAD_OK;
 }
 

@@ -26,6 +26,7 @@ namespace TinyAD
 // bits of the device error word (index = tad_status)
 constexpr int TINYAD_ERR_TOO_MANY_VARIABLES = 1 << 4;
 constexpr int TINYAD_ERR_INDEX_OUT_OF_RANGE = 1 << 5;
+constexpr int TINYAD_ERR_PATTERN_MISMATCH = 1 << 9;
 
 namespace detail
 {
@@ -49,8 +50,13 @@ struct Element
     using PassiveVectorType = Vec<double, d>;
     using OutputVectorType = Vec<ScalarT, (M > 0 ? M : 1)>;
 
-    TINYAD_HD TINYAD_INLINE Element(int64_t _handle, const double* _x, int64_t _n_handles, int32_t* _err)
-        : handle(_handle), x(_x), n_handles(_n_handles), err(_err), n_used(0) {}
+    // _rec (optional): this element's column of the recorded element -> handle table (entry of slot j at _rec[j * _rec_stride]).
+    // The reference rebuilds idx_local_to_global at every evaluation (Element.hh:208-260); here the table was recorded once at
+    // add_elements time and the CSR pattern / scatter maps were built from it, so an evaluation that requests other handles
+    // (a functor that branches on x before or between its variables() calls) must be reported, not silently mis-assembled.
+    TINYAD_HD TINYAD_INLINE Element(int64_t _handle, const double* _x, int64_t _n_handles, int32_t* _err, const int32_t* _rec = nullptr,
+                                    int64_t _rec_stride = 0)
+        : handle(_handle), x(_x), n_handles(_n_handles), err(_err), n_used(0), rec(_rec), rec_stride(_rec_stride) {}
     Element(const Element&) = delete;  // Element.hh:78
 
     TINYAD_HD TINYAD_INLINE VariableVectorType variables(int64_t vh)
@@ -80,6 +86,7 @@ struct Element
             detail::raise(err, TINYAD_ERR_TOO_MANY_VARIABLES);  // Element.hh:237-238
             slot = N - 1;
         }
+        if (rec && (int64_t)rec[slot * rec_stride] != vh) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
         const double* xv = x + d * vh;
         VariableVectorType v;
         detail::static_for<d>([&](auto ic) TINYAD_LAMBDA_INLINE {
@@ -120,7 +127,16 @@ struct Element
     int64_t n_handles;
     int32_t* err;
     int n_used;
+    const int32_t* rec;
+    int64_t rec_stride;
     int64_t seen[Dedup ? N : 1];
+
+    // after the functor ran: did it request exactly the recorded number of (distinct) handles?
+    TINYAD_HD TINYAD_INLINE void check_recorded_count(int32_t recorded) const
+    {
+        const int want = recorded < 0 ? -recorded - 1 : recorded;  // < 0 marks "a handle was requested more than once"
+        if (Dedup ? (n_used != want) : (recorded >= 0 && n_used != want)) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
+    }
 };
 
 // Passive element used once per term to record which handles an element touches.

@@ -37,6 +37,15 @@ struct functor_parts<Functor, std::void_t<decltype(Functor::tinyad_parts)>> { st
 
 TINYAD_HD TINYAD_INLINE int64_t elem_handle(const tad_launch_args& a, int64_t e) { return a.elem_handles ? a.elem_handles[e] : e; }
 
+// This thread's position i inside the launched slab [e_begin, e_begin + n_elements); false if it has no element.
+__device__ TINYAD_INLINE bool slab_index(const tad_launch_args& a, int64_t& i)
+{
+    i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    return i < a.n_elements;
+}
+// Column of element e in the recorded element -> handle table (nullptr: no table, e.g. while recording).
+TINYAD_HD TINYAD_INLINE const int32_t* rec_column(const tad_launch_args& a, int64_t e) { return a.rec_handles ? a.rec_handles + e : nullptr; }
+
 // Which part writes gradient component i: the one that owns Hessian entry (i, i) -- it needs grad[i] anyway.
 template <int k, int NP>
 TINYAD_HD constexpr int grad_owner(int i)
@@ -50,11 +59,12 @@ TINYAD_HD constexpr int grad_owner(int i)
 template <class Functor, int d, int N, int M>
 __global__ void __launch_bounds__(128) record_kernel(Functor f, tad_launch_args a)
 {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.n_elements) return;
+    int64_t i;
+    if (!slab_index(a, i)) return;
+    const int64_t e = a.e_begin + i;
     RecorderElement<d, N, M> el(elem_handle(a, e), a.n_handles, a.error_flags);
     (void)f(el);
-    for (int j = 0; j < N; ++j) a.rec_handles[j * a.stride + e] = (j < el.n_used) ? (int32_t)el.seen[j] : -1;
+    for (int j = 0; j < N; ++j) a.rec_handles[j * a.rec_stride + e] = (j < el.n_used) ? (int32_t)el.seen[j] : -1;
     // count < 0 marks "a handle was requested more than once" (element kernels then need the Dedup variant)
     a.rec_counts[e] = (el.n_calls != el.n_used) ? -el.n_used - 1 : el.n_used;
 }
@@ -62,19 +72,21 @@ __global__ void __launch_bounds__(128) record_kernel(Functor f, tad_launch_args 
 template <class Functor, int d, int N, int M, bool Dedup>
 __global__ void __launch_bounds__(128) passive_kernel(Functor f, tad_launch_args a)
 {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.n_elements) return;
-    Element<d, N, M, double, false, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags);
+    int64_t i;
+    if (!slab_index(a, i)) return;
+    const int64_t e = a.e_begin + i;
+    Element<d, N, M, double, false, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags, rec_column(a, e), a.rec_stride);
     if constexpr (M == 0)
     {
         const double r = f(el);
-        a.val[e] = r;
+        a.val[i] = r;
     }
     else
     {
         const Vec<double, M> r = f(el);
-        static_for<M>([&](auto mc) TINYAD_LAMBDA_INLINE { constexpr int m = decltype(mc)::value; a.val[m * a.stride + e] = r.a[m]; });
+        static_for<M>([&](auto mc) TINYAD_LAMBDA_INLINE { constexpr int m = decltype(mc)::value; a.val[m * a.stride + i] = r.a[m]; });
     }
+    if (a.rec_counts) el.check_recorded_count(a.rec_counts[e]);
 }
 
 template <class Functor, int d, int N, int M, bool Dedup>
@@ -82,44 +94,52 @@ __global__ void __launch_bounds__(128) first_order_kernel(Functor f, tad_launch_
 {
     constexpr int k = d * N;
     using T = Scalar<k, false>;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.n_elements) return;
-    Element<d, N, M, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags);
+    int64_t si;
+    if (!slab_index(a, si)) return;
+    const int64_t e = a.e_begin + si;
+    Element<d, N, M, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags, rec_column(a, e), a.rec_stride);
     if constexpr (M == 0)
     {
         const T r = f(el);
-        a.val[e] = r.val;
-        static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; a.grad[i * a.stride + e] = r.grad[i]; });
+        a.val[si] = r.val;
+        static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; a.grad[i * a.stride + si] = r.grad[i]; });
     }
     else
     {
         const Vec<T, M> r = f(el);
         static_for<M>([&](auto mc) TINYAD_LAMBDA_INLINE {
             constexpr int m = decltype(mc)::value;
-            a.val[m * a.stride + e] = r.a[m].val;
+            a.val[m * a.stride + si] = r.a[m].val;
             static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
                 constexpr int i = decltype(ic)::value;
-                a.grad[(m * k + i) * a.stride + e] = r.a[m].grad[i];
+                a.grad[(m * k + i) * a.stride + si] = r.a[m].grad[i];
             });
         });
     }
+    if (a.rec_counts) el.check_recorded_count(a.rec_counts[e]);
 }
 
+// si: position inside the slab (staging index), e = a.e_begin + si: the element.  Only part 0 validates the recorded handles.
 template <class Functor, int d, int N, int NP, int P, bool Dedup>
-__device__ TINYAD_INLINE void second_order_part(const Functor& f, const tad_launch_args& a, int64_t e)
+__device__ TINYAD_INLINE void second_order_part(const Functor& f, const tad_launch_args& a, int64_t si)
 {
     constexpr int k = d * N;
     using T = Scalar<k, true, NP, P>;
-    Element<d, N, 0, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags);
+    const int64_t e = a.e_begin + si;
+    Element<d, N, 0, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags, P == 0 ? rec_column(a, e) : nullptr, a.rec_stride);
     const T r = f(el);
-    if constexpr (P == 0) a.val[e] = r.val;
+    if constexpr (P == 0)
+    {
+        a.val[si] = r.val;
+        if (a.rec_counts) el.check_recorded_count(a.rec_counts[e]);
+    }
     static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int i = decltype(ic)::value;
-        if constexpr (grad_owner<k, NP>(i) == P) a.grad[i * a.stride + e] = r.grad[i];
+        if constexpr (grad_owner<k, NP>(i) == P) a.grad[i * a.stride + si] = r.grad[i];
     });
     static_for<T::nh>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int s = decltype(ic)::value;
-        a.hess[(int64_t)(T::h_begin + s) * a.stride + e] = r.hess[s];
+        a.hess[(int64_t)(T::h_begin + s) * a.stride + si] = r.hess[s];
     });
 }
 
@@ -130,9 +150,9 @@ inline int check_launch();
 template <class Functor, int d, int N, int NP, int P, bool Dedup>
 __global__ void __launch_bounds__(128) second_order_part_kernel(Functor f, tad_launch_args a)
 {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.n_elements) return;
-    second_order_part<Functor, d, N, NP, P, Dedup>(f, a, e);
+    int64_t si;
+    if (!slab_index(a, si)) return;
+    second_order_part<Functor, d, N, NP, P, Dedup>(f, a, si);
 }
 
 // Host-side launch of one part.  A plain function template so that a heavy functor can spread its NP
@@ -184,6 +204,7 @@ struct TermLauncher
         cudaStream_t st = static_cast<cudaStream_t>(a->stream);
         const int64_t n = a->n_elements;
         const unsigned g128 = (unsigned)((n + 127) / 128);
+        if (a->launch_counter) *a->launch_counter += (a->mode == TAD_MODE_SECOND) ? NP : 1;
         switch (a->mode)
         {
         case TAD_MODE_PASSIVE:
@@ -218,6 +239,7 @@ struct TermLauncher
         if (a->mode == TAD_MODE_RECORD)
         {
             cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+            if (a->launch_counter) *a->launch_counter += 1;
             detail::record_kernel<Functor, d, N, M><<<(unsigned)((a->n_elements + 127) / 128), 128, 0, st>>>(self->f, *a);
             return detail::check_launch();
         }
