@@ -485,6 +485,28 @@ int scalar_case_impl(const std::string& name, const double* p, double* out)
     if (name == "min") { put(min(kd(0), kd(3)), out); return 1; }
     if (name == "max") { put(max(kd(0), kd(3)), out); return 1; }
     if (name == "clamp") { put(clamp(kd(0), kd(3), kd(6)), out); return 1; }
+    if (name == "fmin") { put(fmin(kd(0), kd(3)), out); return 1; }
+    if (name == "fmax") { put(fmax(kd(0), kd(3)), out); return 1; }
+    if (name == "clamp_d") { put(clamp(kd(0), p[3], p[4]), out); return 1; }   // ScalarTestComparison.cc:141-160 (double bounds)
+    if (name == "cmp")   // ScalarTestComparison.cc:41-108: one bit per comparison operator
+    {
+        const A1 a = kd(0), b = kd(3);
+        const double sc = p[6];
+        unsigned m = 0;
+        int bit = 0;
+        auto put_bit = [&](bool v) { if (v) m |= 1u << bit; ++bit; };
+        put_bit(a == b); put_bit(a != b); put_bit(a < b); put_bit(a <= b); put_bit(a > b); put_bit(a >= b);
+        put_bit(a == sc); put_bit(a != sc); put_bit(a < sc); put_bit(a <= sc); put_bit(a > sc); put_bit(a >= sc);
+        put_bit(sc == a); put_bit(sc != a); put_bit(sc < a); put_bit(sc <= a); put_bit(sc > a); put_bit(sc >= a);
+        put(A1((double)m), out);
+        return 1;
+    }
+    if (name == "isnan_isinf")   // ScalarTestComparison.cc:12-32
+    {
+        const A1 v(p[0]);
+        put(A1((double)((isnan(v) ? 1 : 0) | (isinf(v) ? 2 : 0) | (isfinite(v) ? 4 : 0))), out);
+        return 1;
+    }
     if (name == "quadratic") { A1 a(p[0], 0); put(sqr(a) + a + 2.0, out); return 1; }  // ScalarTestMisc.cc:11-26
     if (name == "atan2_1")   // ScalarTestBinaryOperators.cc:468-510
     {

@@ -51,6 +51,25 @@ def assert_vec(g, g_ref, tol=TOL_G, scale=0.0):
     assert err <= tol, err
 
 
+def entry_ratio(v, v_ref, scale):
+    """SURVEY.md 8(c) per-entry metric: max over the entries of |v - v_ref| / scale_entry, where scale_entry is the sum over the
+    contributing elements of |contribution| (oracle mode | ABS_SUM) or of the element's largest |entry| (| NORM_SUM: the rounding
+    scale of one element's derivative block -- the right one after projection, whose error is relative to |H_e|, not to the entry).
+    Entries whose scale is zero (explicit structural zeros, HessianProjection leaves them exact) must agree exactly."""
+    v, v_ref, scale = np.asarray(v), np.asarray(v_ref), np.asarray(scale)
+    assert v.shape == v_ref.shape == scale.shape
+    delta = np.abs(v - v_ref)
+    zero = scale == 0.0
+    assert not delta[zero].any(), "an entry without contributions differs"
+    return float((delta[~zero] / scale[~zero]).max(initial=0.0))
+
+
+def assert_entries(v, v_ref, scale, tol):
+    r = entry_ratio(v, v_ref, scale)
+    assert r <= tol, f"per-entry |delta| / sum|contributions| = {r:.3e} > {tol:.1e}"
+    return r
+
+
 def assert_pattern(outer, inner, ref):
     assert outer.dtype == np.int32 and inner.dtype == np.int32
     assert np.array_equal(outer, ref.outer), "outer index array differs"

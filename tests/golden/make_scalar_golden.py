@@ -135,6 +135,48 @@ case("sphere", (al, be), 2, [
     {"val": sa * sb, "grad": [ca * sb, cb * sa], "hess": [[-sa * sb, ca * cb], [ca * cb, -sa * sb]]},
     {"val": ca, "grad": [-sa, 0.0], "hess": [[-ca, 0.0], [0.0, 0.0]]}], 1e-12, "ScalarTestMisc.cc:38-86", n_out=3)
 
+
+# ---- tests/ScalarTestComparison.cc ----
+C = "ScalarTestComparison.cc"
+NA = [{"val": None, "grad": [], "hess": []}]
+
+
+def flag(v):
+    return [{"val": float(v), "grad": [0.0], "hess": [[0.0]]}]
+
+
+# isnan / isinf / isfinite of passive scalars (:12-32): bit 0 isnan, bit 1 isinf, bit 2 isfinite
+for v, bits in ((0.0, 4), (math.inf, 2), (-math.inf, 2), (math.nan, 1)):
+    case("isnan_isinf", (v,), 1, flag(bits), 0.0, f"{C}:12-32")
+
+
+def cmp_mask(a, b, sc):
+    """The 18 comparisons of test_comparison (:41-108) as bits, in the order ==, !=, <, <=, >, >= for (a, b), (a, double), (double, a).
+    Comparisons look at val only (Scalar.hh:933-1095): a = (1,1,4) == b = (1,2,8)."""
+    ops = [lambda p, q: p == q, lambda p, q: p != q, lambda p, q: p < q, lambda p, q: p <= q, lambda p, q: p > q, lambda p, q: p >= q]
+    bits = [op(a, b) for op in ops] + [op(a, sc) for op in ops] + [op(sc, a) for op in ops]
+    return sum(1 << i for i, v in enumerate(bits) if v)
+
+
+ca, cb, cc = (1.0, 1.0, 4.0), (1.0, 2.0, 8.0), (2.0, 2.0, 8.0)
+for p_, q_ in ((ca, cb), (cb, ca), (ca, cc), (cc, ca), (cb, cc), (cc, cb)):
+    for sc in (1.0, 2.0):
+        case("cmp", p_ + q_ + (sc,), 1, flag(cmp_mask(p_[0], q_[0], sc)), 0.0, f"{C}:41-108")
+# spot values the reference spells out: a == b, !(a < b), a <= b, a >= b; a == 1.0, a < 2.0, !(a > 2.0)
+assert cmp_mask(1.0, 1.0, 1.0) & 0b111111 == 0b101001 and cmp_mask(1.0, 2.0, 2.0) & 0b111111 == 0b001110
+# min / fmin / max / fmax select the whole scalar (:110-139): a = (1,2,3), b = (2,3,4)
+ma = (1.0, 2.0, 3.0, 2.0, 3.0, 4.0)
+for nm in ("min", "fmin"):
+    case(nm, ma, 1, e1(1.0, 2.0, 3.0), 0.0, f"{C}:110-139")
+for nm in ("max", "fmax"):
+    case(nm, ma, 1, e1(2.0, 3.0, 4.0), 0.0, f"{C}:110-139")
+# clamp(x, lo, hi) with double bounds (:141-160): x = (4,3,2)
+case("clamp_d", (4.0, 3.0, 2.0, 0.0, 5.0), 1, e1(4.0, 3.0, 2.0), 0.0, f"{C}:141-160")
+case("clamp_d", (4.0, 3.0, 2.0, -5.0, 0.0), 1, e1(0.0, 0.0, 0.0), 0.0, f"{C}:141-160")
+case("clamp_d", (4.0, 3.0, 2.0, 5.0, 10.0), 1, e1(5.0, 0.0, 0.0), 0.0, f"{C}:141-160")
+# clamp with scalar bounds returns the bound with ITS derivatives (Scalar.hh:1133-1145)
+case("clamp", (4.0, 3.0, 2.0, 5.0, 1.0, 7.0, 10.0, 0.5, 0.25), 1, e1(5.0, 1.0, 7.0), 0.0, "Scalar.hh:1133-1145")
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scalar_cases.json")
 json.dump(cases, open(out, "w"), indent=0)
 print(len(cases), "cases ->", out)

@@ -356,6 +356,7 @@ SCALAR_CASES = [
     "sqr_pow_mul", "atan2_const", "atan2_2", "hypot", "div2d", "div2d_2", "plus_minus_mult_div_2d", "sphere",
     "c_mul", "c_mul_d", "c_d_mul", "c_div", "c_div_d", "c_add", "c_sub", "c_sqr", "c_conj", "c_abs", "c_arg", "symm_dirich6",
     "svd2", "closest_orthogonal2",
+    "fmin", "fmax", "clamp_d", "cmp", "isnan_isinf",
 ]
 
 

@@ -1,6 +1,6 @@
 """Builds the in-tree CUDA libraries for sm_100a with nvcc (cross-compiles without a GPU).
 
-  libtinyad_b200.so            csrc/runtime.cu    the C-ABI runtime (include/tinyad_b200.h)
+  libtinyad_b200.so            csrc/runtime.cu, projection.cu, assembly.cu, comm.cu, newton.cu    the C-ABI runtime (include/tinyad_b200.h)
   libtinyad_b200_energies.so   csrc/energies*.cu  element functors of the tests / benchmark (a "user TU");
                                                   the Double<12> tet kernel is split into one object per Hessian part
                                                   so that the heavy instantiations compile in parallel.
@@ -63,17 +63,22 @@ def build(force=False, verbose=False):
     jobs = []
     inc = os.path.join(HERE, "include", "TinyAD")
     api = hdrs[0]
-    # runtime library: one object per translation unit, compiled in parallel, linked into libtinyad_b200.so
-    rt_units = [("runtime.o", "runtime.cu", [os.path.join(inc, "Scalar.hh"), os.path.join(inc, "Detail", "HessLayout.hh"),
-                                             os.path.join(inc, "Detail", "Projection.hh")]),
-                ("newton.o", "newton.cu", [])]
+    # runtime library: one object per translation unit (the projection kernels once per group of K, the assembly kernels once per
+    # variable dimension, so that the heavy instantiations compile in parallel), linked into libtinyad_b200.so
+    common = os.path.join(HERE, "csrc", "rt_common.cuh")
+    proj_deps = [common, os.path.join(inc, "Scalar.hh"), os.path.join(inc, "Detail", "HessLayout.hh"), os.path.join(inc, "Detail", "Projection.hh")]
+    rt_units = [("runtime.o", "runtime.cu", proj_deps, []), ("newton.o", "newton.cu", [], []), ("comm.o", "comm.cu", [common], [])]
+    rt_units += [(f"projection{p}.o", "projection.cu", proj_deps, [f"-DTAD_PROJ_PART={p}"]) for p in range(4)]
+    rt_units += [(f"assembly{p}.o", "assembly.cu", proj_deps, [f"-DTAD_ASM_PART={p}"]) for p in range(3)]
     rt_objs, relink_runtime = [], not os.path.exists(RUNTIME_SO)
-    for obj, cu, deps in rt_units:
+    for obj, cu, deps, defs in rt_units:
         o = os.path.join(OBJ_DIR, obj)
-        rt_objs.append(o)
         src = os.path.join(HERE, "csrc", cu)
+        if not os.path.exists(src):
+            continue
+        rt_objs.append(o)
         if force or _newer(o, [src, api, os.path.abspath(__file__)] + deps):
-            jobs.append([NVCC] + FLAGS + ["-c", "-o", o, src])
+            jobs.append([NVCC] + FLAGS + ptxas + defs + ["-c", "-o", o, src])
             relink_runtime = True
     hdrs = [h for h in hdrs if not h.endswith("Projection.hh")]   # only the runtime includes the projection routines
     objs = []

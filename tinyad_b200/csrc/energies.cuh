@@ -298,6 +298,7 @@ enum ScalarCase
     SC_SQR_POW_MUL, SC_ATAN2_CONST, SC_ATAN2_2, SC_HYPOT, SC_DIV2D, SC_DIV2D_2, SC_PMMD_2D, SC_SPHERE,
     SC_C_MUL, SC_C_MUL_D, SC_C_D_MUL, SC_C_DIV, SC_C_DIV_D, SC_C_ADD, SC_C_SUB, SC_C_SQR, SC_C_CONJ, SC_C_ABS, SC_C_ARG, SC_SYMM_DIRICH6,
     SC_SVD2, SC_CLOSEST_ORTHOGONAL2,
+    SC_FMIN, SC_FMAX, SC_CLAMP_D, SC_CMP, SC_ISNAN_ISINF,   // tests/ScalarTestComparison.cc
     SC_COUNT
 };
 
@@ -365,6 +366,26 @@ TINYAD_HD inline int scalar_case_run(int id, const double* p, double* out)
     case SC_MIN: sc_put(min(a, b), out); return 1;
     case SC_MAX: sc_put(max(a, b), out); return 1;
     case SC_CLAMP: sc_put(clamp(a, b, A1::known_derivatives(p[6], p[7], p[8])), out); return 1;
+    case SC_FMIN: sc_put(fmin(a, b), out); return 1;
+    case SC_FMAX: sc_put(fmax(a, b), out); return 1;
+    case SC_CLAMP_D: sc_put(clamp(a, p[3], p[4]), out); return 1;   // double bounds convert to passive scalars (ScalarTestComparison.cc:141-160)
+    case SC_CMP:  // every comparison operator of ScalarTestComparison.cc:41-108 as one bit of the returned value
+    {
+        unsigned m = 0;
+        int bit = 0;
+        auto put_bit = [&](bool v) { if (v) m |= 1u << bit; ++bit; };
+        put_bit(a == b); put_bit(a != b); put_bit(a < b); put_bit(a <= b); put_bit(a > b); put_bit(a >= b);
+        put_bit(a == sc); put_bit(a != sc); put_bit(a < sc); put_bit(a <= sc); put_bit(a > sc); put_bit(a >= sc);
+        put_bit(sc == a); put_bit(sc != a); put_bit(sc < a); put_bit(sc <= a); put_bit(sc > a); put_bit(sc >= a);
+        sc_put(A1((double)m), out);
+        return 1;
+    }
+    case SC_ISNAN_ISINF:  // ScalarTestComparison.cc:12-32: bit 0 isnan, bit 1 isinf, bit 2 isfinite of a passive scalar
+    {
+        const A1 v(p[0]);
+        sc_put(A1((double)((isnan(v) ? 1 : 0) | (isinf(v) ? 2 : 0) | (isfinite(v) ? 4 : 0))), out);
+        return 1;
+    }
     case SC_QUADRATIC: { A1 x(p[0], 0); sc_put(sqr(x) + x + 2.0, out); return 1; }
     case SC_ATAN2_1: { A1 x(p[0], 0); A1 y = sqr(x) - x - 1.0; sc_put(atan2(y, x), out); return 1; }
     default: break;

@@ -8,184 +8,15 @@
 //   assembly kernels (FP64 atomics | deterministic gather)      <- serial loops ScalarObjectiveTerm.hh:256-277
 //   f reduction, finite checks, error word                      <- ScalarObjectiveTerm.hh:210,252-253, Utils/Out.hh:73-79
 //   VectorFunction r / J (CSC) / sum of squares / g = 2 J^T r   <- VectorObjectiveTerm.hh:158-243, VectorFunctionImpl.hh:143-283
-#include <cuda_runtime.h>
+#include "rt_common.cuh"
 
-#include <algorithm>
-#include <cmath>
-#include <cstdint>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <limits>
-#include <mutex>
-#include <string>
-#include <vector>
+using namespace tadrt;
 
-#include <cub/cub.cuh>
-
-#include <TinyAD/Detail/HessLayout.hh>
-#include <TinyAD/Detail/Projection.hh>
-#include <tinyad_b200.h>
-
-using TinyAD::detail::hess_seq_index;
-using TinyAD::detail::hess_seq_rc;
-using TinyAD::detail::hess_size;
-
-namespace
+namespace tadrt
 {
-
 thread_local std::string g_last_error = "";
-
-int fail(int status, const std::string& msg)
-{
-    g_last_error = msg;
-    return status;
-}
-
-// Function attributes (dynamic shared-memory opt-in, carve-out) are per device: run(fn) executes fn exactly once per device
-// (std::call_once: a second thread that arrives while the first is still configuring waits for it, so no launch can overtake
-// the opt-in).  One object per call site; processes normally drive one GPU, but nothing here assumes it.
-struct PerDeviceOnce
-{
-    std::once_flag flags[64];
-    template <class Fn>
-    void run(Fn&& fn)
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { fn(); return; }
-        std::call_once(flags[dev], fn);
-    }
-};
-
-// Kernel-launch accounting (tad_function_launch_count): the evaluation entry points point this at the function's counter.
 thread_local int64_t* tl_launch_counter = nullptr;
-inline void count_launch(int n = 1) { if (tl_launch_counter) *tl_launch_counter += n; }
-struct LaunchCounterScope
-{
-    int64_t* prev;
-    explicit LaunchCounterScope(int64_t* c) : prev(tl_launch_counter) { tl_launch_counter = c; }
-    ~LaunchCounterScope() { tl_launch_counter = prev; }
-};
-
-#define TAD_CUDA(expr)                                                                                   \
-    do                                                                                                   \
-    {                                                                                                    \
-        cudaError_t _e = (expr);                                                                         \
-        if (_e != cudaSuccess)                                                                           \
-            return fail(_e == cudaErrorMemoryAllocation ? TAD_OUT_OF_MEMORY : TAD_CUDA_ERROR,            \
-                        std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);          \
-    } while (0)
-
-#define TAD_TRY(expr)                    \
-    do                                   \
-    {                                    \
-        int _s = (expr);                 \
-        if (_s != TAD_OK) return _s;     \
-    } while (0)
-
-constexpr int ERR_NONFINITE = 1 << TAD_NONFINITE_DERIVATIVE;
-constexpr int ERR_TOO_MANY = 1 << TAD_TOO_MANY_VARIABLES;
-constexpr int ERR_RANGE = 1 << TAD_INDEX_OUT_OF_RANGE;
-constexpr int ERR_PATTERN = 1 << TAD_PATTERN_MISMATCH;
-
-template <class T>
-struct DevBuf
-{
-    T* p = nullptr;
-    size_t n = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; return *this; }
-    ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    cudaError_t ensure(size_t count)
-    {
-        if (count <= n) return cudaSuccess;
-        release();
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-        if (e == cudaSuccess) n = count; else p = nullptr;
-        return e;
-    }
-};
-
-struct Term
-{
-    int N = 0, M = 0, k = 0;
-    int64_t n = 0, stride = 0;
-    tad_launch_fn launch = nullptr;
-    void* user = nullptr;
-    void (*user_free)(void*) = nullptr;
-    bool dedup = false;
-    DevBuf<int64_t> elem_handles;
-    bool has_handles = false;
-    DevBuf<int32_t> rec_handles;  // [N][stride]
-    DevBuf<int32_t> rec_counts;   // [n]
-    // scalar functions: scatter map
-    DevBuf<int32_t> blockbase;    // [N*N][stride]  CSR value index of entry (0,0) of block (bi,bj); -1 = unused
-    DevBuf<int32_t> rstride;      // [N][stride]    distance between consecutive rows of that block row (= d * deg(vertex))
-    int64_t contrib_offset = 0;
-    // vector functions
-    int64_t out_offset = 0;
-    DevBuf<int32_t> jslot;        // [M*k][stride]  CSC value index; -1 = unused
-    // staging (gather mode keeps one per term)
-    DevBuf<double> stage;
-};
-
-struct TermDev  // device-visible description used by pattern / gather kernels
-{
-    int64_t off;      // first contribution id
-    int64_t n, stride;
-    int N, M, k;
-    const int32_t* rec;
-    int32_t* blockbase;
-    int32_t* rstride;
-    int32_t* jslot;
-    int64_t out_offset;
-    const double* grad;  // staging pointers (gather mode)
-    const double* hess;
-};
-
-// Side stream of the fused path: the full solver of the few listed elements runs next to the fused phase C / assembly
-// kernel (its cost is the serial latency of one full eigensolve, ~0.15 ms, not throughput).
-struct ProjSide
-{
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_b = nullptr, ev_list = nullptr;
-};
-
-// One element slab in flight: its own stream, staging, projection scratch and counters.  Consecutive slabs of an evaluation
-// alternate between the lanes, so the tail of one slab's kernels overlaps the head of the next slab's, and the memory an
-// evaluation needs is bounded by lanes x slab size instead of the term size.
-struct Lane
-{
-    cudaStream_t stream = nullptr;
-    ProjSide side;
-    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // timing mode: before element / after element / after projection / after assembly
-    DevBuf<double> stage;                  // val / grad / hess of the slab, SoA with the slab's stride
-    DevBuf<double> proj_scratch;           // R and W of the fast projection path
-    DevBuf<int32_t> proj_codes;
-    DevBuf<int64_t> proj_list;             // elements handed to the full eigensolver
-    DevBuf<unsigned long long> counts;     // [4]: decomposed, rebuilt, listed in this slab, listed in this evaluation
-};
-
-// A slab of the evaluation schedule.
-struct Slab
-{
-    int term;
-    int64_t e_begin, n;
-    int64_t final_values;  // leading CSR values that can no longer change once this slab and all earlier ones are complete
-};
-
-// Destination of the pipelined device -> host copies of the host-buffer entry points.
-struct HostCopy
-{
-    double* g_host = nullptr;
-    double* H_host = nullptr;
-};
-
-}  // namespace
+}  // namespace tadrt
 
 struct tad_function_s
 {
@@ -302,482 +133,10 @@ __global__ void __launch_bounds__(1024) reduce_stage2(const double* partial, int
     if (threadIdx.x == 0) *out = sh[0];
 }
 
-// ---------------------------------------------------------------------------------------------
-// PSD projection (Utils/HessianProjection.hh:23-101), one thread per element.
-//
-// Symmetric eigensolver: Householder tridiagonalisation + implicit QL with accumulated
-// transformations (the classic EISPACK tred2/tql2 scheme; Eigen's SelfAdjointEigenSolver is the QR
-// flavour of the same method, any backward-stable variant gives the same projected matrix to
-// O(eps |H|)).  Data placement: the K x K work matrix and the tridiagonal live in SHARED memory,
-// laid out [entry][lane] so a warp's accesses are conflict-free 256-byte rows; per-thread local
-// arrays would spill to L2/DRAM (the first version did: 10 GB of DRAM writes per launch).
-//   * rotations are generated with one rsqrt instead of hypot + two divisions;
-//   * a QL sweep keeps the running column in registers, so each rotation reads and writes one
-//     column of V instead of two;
-//   * H is rebuilt as H + sum_j (clamp(l_j) - l_j) v_j v_j^T over the clamped eigenpairs only,
-//     which leaves H bit-unchanged when nothing is clamped (HessianProjection.hh:94-95).
-// ---------------------------------------------------------------------------------------------
-template <int K>
-struct ProjSmem
+}  // namespace
+
+namespace tadrt
 {
-    static constexpr int doubles_per_warp = (K * K + 2 * K) * 32;
-};
-
-// Full eigendecomposition of one element; S = this thread's column of the [entry][lane] shared-memory block.
-template <int K>
-__device__ void project_full_one(double* __restrict__ hp, int64_t stride, double eps, double* S, const int SS, unsigned long long* counts,
-                                 bool count_decomposed)
-{
-    constexpr int H = K * (K + 1) / 2;
-#define PV(i, j) S[((i) * K + (j)) * SS]
-#define PD(i) S[(K * K + (i)) * SS]
-#define PE(i) S[(K * K + K + (i)) * SS]
-    // ---- load, and early-out 1: positive diagonally dominant (HessianProjection.hh:23-42, :62-63) ----
-    {
-        double offsum[K], diag[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) offsum[i] = 0.0;
-#pragma unroll
-        for (int s = 0; s < H; ++s)
-        {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int r = hess_seq_rc(K, s).row, c = hess_seq_rc(K, s).col;
-            const double v = hp[(int64_t)s * stride];
-            PV(r, c) = v;
-            if (r != c)
-            {
-                PV(c, r) = v;
-                offsum[r] += fabs(v);
-                offsum[c] += fabs(v);
-            }
-            else
-                diag[r] = v;
-        }
-        bool dominant = true;
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-            if (diag[i] < offsum[i] + eps) dominant = false;
-        if (dominant) return;
-    }
-
-    // ---- tridiagonalise; V holds the symmetric matrix on entry, the orthogonal transformation on exit ----
-    for (int j = 0; j < K; ++j) PD(j) = PV(K - 1, j);
-    for (int i = K - 1; i > 0; --i)
-    {
-        double scale = 0.0, h = 0.0;
-        for (int q = 0; q < i; ++q) scale += fabs(PD(q));
-        if (scale == 0.0)
-        {
-            PE(i) = PD(i - 1);
-            for (int j = 0; j < i; ++j)
-            {
-                PD(j) = PV(i - 1, j);
-                PV(i, j) = 0.0;
-                PV(j, i) = 0.0;
-            }
-        }
-        else
-        {
-            const double inv_scale = 1.0 / scale;
-            for (int q = 0; q < i; ++q)
-            {
-                const double t = PD(q) * inv_scale;
-                PD(q) = t;
-                h += t * t;
-            }
-            double f = PD(i - 1);
-            double g = sqrt(h);
-            if (f > 0) g = -g;
-            PE(i) = scale * g;
-            h -= f * g;
-            PD(i - 1) = f - g;
-            for (int j = 0; j < i; ++j) PE(j) = 0.0;
-            for (int j = 0; j < i; ++j)
-            {
-                f = PD(j);
-                PV(j, i) = f;
-                g = PE(j) + PV(j, j) * f;
-                for (int q = j + 1; q <= i - 1; ++q)
-                {
-                    const double vqj = PV(q, j);
-                    g += vqj * PD(q);
-                    PE(q) += vqj * f;
-                }
-                PE(j) = g;
-            }
-            f = 0.0;
-            const double inv_h = 1.0 / h;
-            for (int j = 0; j < i; ++j)
-            {
-                const double t = PE(j) * inv_h;
-                PE(j) = t;
-                f += t * PD(j);
-            }
-            const double hh = f / (h + h);
-            for (int j = 0; j < i; ++j) PE(j) -= hh * PD(j);
-            for (int j = 0; j < i; ++j)
-            {
-                f = PD(j);
-                g = PE(j);
-                for (int q = j; q <= i - 1; ++q) PV(q, j) -= (f * PE(q) + g * PD(q));
-                PD(j) = PV(i - 1, j);
-                PV(i, j) = 0.0;
-            }
-        }
-        PD(i) = h;
-    }
-    for (int i = 0; i < K - 1; ++i)
-    {
-        PV(K - 1, i) = PV(i, i);
-        PV(i, i) = 1.0;
-        const double h = PD(i + 1);
-        if (h != 0.0)
-        {
-            const double inv_h = 1.0 / h;
-            for (int q = 0; q <= i; ++q) PD(q) = PV(q, i + 1) * inv_h;
-            for (int j = 0; j <= i; ++j)
-            {
-                double g = 0.0;
-                for (int q = 0; q <= i; ++q) g += PV(q, i + 1) * PV(q, j);
-                for (int q = 0; q <= i; ++q) PV(q, j) -= g * PD(q);
-            }
-        }
-        for (int q = 0; q <= i; ++q) PV(q, i + 1) = 0.0;
-    }
-    for (int j = 0; j < K; ++j)
-    {
-        PD(j) = PV(K - 1, j);
-        PV(K - 1, j) = 0.0;
-    }
-    PV(K - 1, K - 1) = 1.0;
-    PE(0) = 0.0;
-    // ---- implicit QL on the tridiagonal (d, e), rotations accumulated into V ----
-    for (int i = 1; i < K; ++i) PE(i - 1) = PE(i);
-    PE(K - 1) = 0.0;
-    double f = 0.0, tst1 = 0.0;
-    const double meps = 2.220446049250313e-16;
-    for (int l = 0; l < K; ++l)
-    {
-        tst1 = fmax(tst1, fabs(PD(l)) + fabs(PE(l)));
-        int m = l;
-        while (m < K - 1)
-        {
-            if (fabs(PE(m)) <= meps * tst1) break;
-            ++m;
-        }
-        if (m > l)
-        {
-            int iter = 0;
-            double el_abs;
-            do
-            {
-                ++iter;
-                const double e_l = PE(l);
-                double g = PD(l);
-                double p = (PD(l + 1) - g) / (2.0 * e_l);
-                double r = (fabs(p) < 1e150) ? sqrt(fma(p, p, 1.0)) : fabs(p);
-                if (p < 0) r = -r;
-                const double dl = e_l / (p + r);
-                const double dl1 = e_l * (p + r);
-                PD(l) = dl;
-                PD(l + 1) = dl1;
-                double h = g - dl;
-                for (int i = l + 2; i < K; ++i) PD(i) -= h;
-                f += h;
-                p = PD(m);
-                double c = 1.0, c2 = 1.0, c3 = 1.0;
-                const double el1 = PE(l + 1);
-                double s = 0.0, s2 = 0.0;
-                double x[K];  // running column (column i+1 of V while the sweep moves down)
-#pragma unroll
-                for (int q = 0; q < K; ++q) x[q] = PV(q, m);
-                for (int i = m - 1; i >= l; --i)
-                {
-                    c3 = c2;
-                    c2 = c;
-                    s2 = s;
-                    const double ei = PE(i), di = PD(i);
-                    g = c * ei;
-                    h = c * p;
-                    const double t = fma(p, p, ei * ei);
-                    double rinv;
-                    if (t > 1e-280 && t < 1e280)
-                    {
-                        rinv = rsqrt(t);
-                        r = t * rinv;
-                    }
-                    else
-                    {
-                        r = hypot(p, ei);
-                        rinv = 1.0 / r;
-                    }
-                    PE(i + 1) = s * r;
-                    s = ei * rinv;
-                    c = p * rinv;
-                    p = c * di - s * g;
-                    PD(i + 1) = h + s * (c * g + s * di);
-#pragma unroll
-                    for (int q = 0; q < K; ++q)
-                    {
-                        const double y = PV(q, i);
-                        PV(q, i + 1) = s * y + c * x[q];
-                        x[q] = c * y - s * x[q];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < K; ++q) PV(q, l) = x[q];
-                p = -s * s2 * c3 * el1 * e_l / dl1;
-                PE(l) = s * p;
-                PD(l) = c * p;
-                el_abs = fabs(s * p);
-            } while (el_abs > meps * tst1 && iter < 60);
-        }
-        PD(l) = PD(l) + f;
-        PE(l) = 0.0;
-    }
-
-    // ---- clamp (HessianProjection.hh:71-91) and rebuild from the clamped eigenpairs only ----
-    if (counts && count_decomposed) atomicAdd(&counts[0], 1ull);
-    double acc[H];
-#pragma unroll
-    for (int s = 0; s < H; ++s) acc[s] = 0.0;
-    bool all_positive = true;
-    for (int j = 0; j < K; ++j)
-    {
-        const double lam = PD(j);
-        double target = lam;
-        if (eps < 0) { if (lam < 0) target = -lam; }
-        else if (lam < eps) target = eps;
-        if (target != lam)
-        {
-            all_positive = false;
-            const double delta = target - lam;
-            double v[K], dv[K];
-#pragma unroll
-            for (int q = 0; q < K; ++q)
-            {
-                v[q] = PV(q, j);
-                dv[q] = delta * v[q];
-            }
-#pragma unroll
-            for (int s = 0; s < H; ++s) acc[s] = fma(dv[hess_seq_rc(K, s).row], v[hess_seq_rc(K, s).col], acc[s]);
-        }
-    }
-    // early out 2: nothing clamped -> H stays bit-unchanged (:94-95)
-    if (all_positive) return;
-    if (counts) atomicAdd(&counts[1], 1ull);
-#pragma unroll
-    for (int s = 0; s < H; ++s) hp[(int64_t)s * stride] += acc[s];
-#undef PV
-#undef PD
-#undef PE
-}
-
-template <int K>
-__global__ void __launch_bounds__(32) project_kernel_full(double* __restrict__ hess, int64_t n, int64_t stride, double eps,
-                                                          unsigned long long* counts)
-{
-    extern __shared__ double proj_smem[];
-    const int64_t el = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    if (el >= n) return;
-    project_full_one<K>(hess + el, stride, eps, proj_smem + threadIdx.x, 32, counts, true);
-}
-
-// The elements the fast path could not finish (counts[2] of them: a few per million on the tet workloads): a small fixed
-// grid of single-warp blocks strides over the list.  The cost of this launch is the serial latency of one full solve, so the
-// work matrix is kept in STATIC shared memory when it fits the 48 KB static limit (K <= 12; no opt-in / carve-out switch),
-// else in a global scratch buffer laid out [entry][thread].
-constexpr int kListBlocks = 148, kListThreads = 32;
-template <int K>
-__global__ void __launch_bounds__(kListThreads) project_kernel_list(double* __restrict__ hess, int64_t stride, double eps,
-                                                                    unsigned long long* counts, const int64_t* __restrict__ list,
-                                                                    double* __restrict__ work)
-{
-    constexpr bool use_smem = (size_t)(K * K + 2 * K) * kListThreads * sizeof(double) <= 48 * 1024;
-    __shared__ double sm[use_smem ? (K * K + 2 * K) * kListThreads : 1];
-    const int64_t count = (int64_t)counts[2];
-    const int nthreads = gridDim.x * blockDim.x;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int64_t i = tid; i < count; i += nthreads)
-    {
-        if (use_smem) project_full_one<K>(hess + list[i], stride, eps, sm + threadIdx.x, kListThreads, counts, false);
-        else project_full_one<K>(hess + list[i], stride, eps, work + tid, nthreads, counts, false);
-    }
-}
-
-// Fast path (Detail/Projection.hh), three kernels with different resource profiles, one thread per element:
-//   A  tridiagonalise  -- the packed matrix in registers, fully unrolled (register-heavy, ILP-rich)
-//   B  select vectors  -- eigenvalues of T, eigenvectors of the moved eigenvalues by inverse iteration
-//                         (scalar recurrences on small arrays: few registers, runs at high occupancy)
-//   C  apply           -- back-transform through the reflectors, H += low-rank term (register-heavy)
-// Scratch between them is structure-of-arrays over the elements (coalesced 256-byte rows).
-struct ProjScratch
-{
-    double* R;       // [ProjLayout<K>::nR][stride]
-    double* W;       // [ProjLayout<K>::nW][stride]
-    int32_t* codes;  // [stride] ProjectCode per element
-    int64_t* list;   // elements handed to the full solver
-};
-
-template <int K>
-__global__ void __launch_bounds__(128) project_kernel_a(const double* __restrict__ hess, int64_t n, int64_t stride, double eps, ProjScratch sc)
-{
-    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (el >= n) return;
-    const double* hp = hess + el;
-    double* rp = sc.R + el;
-    sc.codes[el] = TinyAD::detail::proj_tridiagonalize<K>([&](int s) { return hp[(int64_t)s * stride]; },
-                                                          [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
-}
-
-// B1: eigenvalues of T (register-resident QL, Detail/Projection.hh proj_eigenvalues); few registers, high occupancy
-template <int K>
-__global__ void __launch_bounds__(128) project_kernel_b1(int64_t n, int64_t stride, ProjScratch sc)
-{
-    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (el >= n) return;
-    if (sc.codes[el] == TinyAD::detail::PROJ_DOMINANT) return;
-    double* rp = sc.R + el;
-    const int code = TinyAD::detail::proj_eigenvalues<K>([&](int i) { return rp[(int64_t)i * stride]; },
-                                                         [&](int i, double v) { rp[(int64_t)i * stride] = v; });
-    if (code == TinyAD::detail::PROJ_FALLBACK) sc.codes[el] = code;
-}
-
-// B2: selection + inverse iteration.  The sorted eigenvalues and the first B2_SMEM_VECS eigenvectors of every thread live in
-// shared memory ([slot][thread], conflict-free): they are re-read at run-time indices / by every later vector's two
-// orthogonalisation passes, and as global re-reads (L2 round trips of data the thread has just written) those loads were
-// ~25 % of the kernel's stall samples.
-constexpr int B2_SMEM_VECS = 4;
-template <int K>
-constexpr size_t b2_smem_bytes(int threads) { return (size_t)(K + B2_SMEM_VECS * K) * threads * sizeof(double); }
-
-template <int K, int MINB>
-__global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc)
-{
-    using L = TinyAD::detail::ProjLayout<K>;
-    extern __shared__ double b2_smem[];
-    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (el >= n) return;
-    int code = sc.codes[el];
-    if (code == TinyAD::detail::PROJ_DOMINANT) return;
-    double* rp = sc.R + el;
-    double* wp = sc.W + el;
-    const int bd = blockDim.x;
-    double* sl = b2_smem + threadIdx.x;        // eigenvalues: slot i
-    double* sv = sl + (size_t)K * bd;          // vectors: slot jv * K + q, jv < B2_SMEM_VECS
-    if (code != TinyAD::detail::PROJ_FALLBACK)
-        code = TinyAD::detail::proj_select_vectors<K>(
-            [&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return sl[i * bd]; }, [&](int i, double v) { sl[i * bd] = v; },
-            [&](int i, double v) { wp[(int64_t)i * stride] = v; },
-            [&](int jv, int q, double v) {
-                wp[(int64_t)(L::off_vec + jv * K + q) * stride] = v;
-                if (jv < B2_SMEM_VECS) sv[(jv * K + q) * bd] = v;
-            },
-            [&](int jv, double (&v)[K]) {
-                if (jv < B2_SMEM_VECS)
-                {
-#pragma unroll
-                    for (int q = 0; q < K; ++q) v[q] = sv[(jv * K + q) * bd];
-                }
-                else
-                {
-                    const double* p = wp + (int64_t)(L::off_vec + jv * K) * stride;
-#pragma unroll
-                    for (int q = 0; q < K; ++q) { v[q] = *p; p += stride; }
-                }
-            },
-            eps);
-    sc.codes[el] = code;
-    if (counts) atomicAdd(&counts[0], 1ull);
-    if (code == TinyAD::detail::PROJ_REBUILT && counts) atomicAdd(&counts[1], 1ull);
-    if (code == TinyAD::detail::PROJ_FALLBACK)
-    {
-        const unsigned long long slot = atomicAdd(&counts[2], 1ull);  // per slab (reset by the caller): index into the list
-        sc.list[slot] = el;
-        atomicAdd(&counts[3], 1ull);                                  // running total of the evaluation
-    }
-}
-
-template <int K>
-__global__ void __launch_bounds__(128) project_kernel_c(double* __restrict__ hess, int64_t n, int64_t stride, double eps, ProjScratch sc)
-{
-    const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (el >= n) return;
-    if (sc.codes[el] != TinyAD::detail::PROJ_REBUILT) return;
-    double* hp = hess + el;
-    const double* rp = sc.R + el;
-    const double* wp = sc.W + el;
-    TinyAD::detail::proj_apply<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
-                                  [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { hp[(int64_t)s * stride] = v; }, eps);
-}
-
-template <int K>
-size_t project_scratch_doubles(int64_t stride)
-{
-    using L = TinyAD::detail::ProjLayout<K>;
-    return (size_t)(L::nR + L::nW) * (size_t)stride + (size_t)(K * K + 2 * K) * kListBlocks * kListThreads;
-}
-
-// counts: device uint64[4] = {#decomposed, #rebuilt, #full solver, unused}.  scratch_d: project_scratch_doubles<K>(stride)
-// doubles, scratch_i: stride int32 + n int64 (see project_scratch_bytes).
-template <int K>
-int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, int32_t* codes,
-                   int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st)
-{
-    using L = TinyAD::detail::ProjLayout<K>;
-    constexpr size_t smem = (size_t)ProjSmem<K>::doubles_per_warp * sizeof(double);
-    static PerDeviceOnce configured;
-    bool config_ok = true;
-    configured.run([&] { config_ok = cudaFuncSetAttribute(project_kernel_full<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; });
-    if (!config_ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel");
-    if (full_only)
-    {
-        count_launch();
-        project_kernel_full<K><<<(unsigned)((n + 31) / 32), 32, smem, st>>>(hess, n, stride, eps, counts);
-    }
-    else
-    {
-        ProjScratch sc;
-        sc.R = scratch_d;
-        sc.W = scratch_d + (size_t)L::nR * stride;
-        sc.codes = codes;
-        sc.list = list;
-        const unsigned g = (unsigned)((n + 127) / 128);
-        count_launch(4 + (fuse_out ? 0 : 1));
-        project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
-        project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
-        {
-            static PerDeviceOnce b2_configured;
-            b2_configured.run([&] {
-                config_ok = cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128)) == cudaSuccess &&
-                            cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-            });
-            if (!config_ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel B2");
-            // 2 blocks per SM at 255 registers (no spills) beat 3 blocks at 168 registers with ~400 B of spills by 3-6 % (tools/proj_bench.cu);
-            // K <= 12: 128-thread blocks (61 KB of shared memory each at K = 12); larger K: smaller blocks keep the footprint per SM
-            const int bt = K <= 12 ? 128 : 64;
-            project_kernel_b<K, 2><<<(unsigned)((n + bt - 1) / bt), bt, b2_smem_bytes<K>(bt), st>>>(n, stride, eps, counts, sc);
-        }
-        // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
-        double* work = scratch_d + (size_t)(L::nR + L::nW) * stride;
-        if (fuse_out && side && side->stream)
-        {
-            // fused path: on the side stream, next to the phase C / assembly kernel (which skips the listed elements;
-            // the caller assembles them after ev_list)
-            if (cudaEventRecord(side->ev_b, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->ev_b, 0) != cudaSuccess)
-                return fail(TAD_CUDA_ERROR, "projection side stream");
-            project_kernel_list<K><<<kListBlocks, kListThreads, 0, side->stream>>>(hess, stride, eps, counts, list, work);
-            if (cudaEventRecord(side->ev_list, side->stream) != cudaSuccess) return fail(TAD_CUDA_ERROR, "projection side stream");
-        }
-        else
-            project_kernel_list<K><<<kListBlocks, kListThreads, 0, st>>>(hess, stride, eps, counts, list, work);
-        if (fuse_out) *fuse_out = sc;  // phase C is fused with the assembly by the caller
-        else project_kernel_c<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
-    }
-    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "project kernel launch failed");
-}
-
 size_t project_scratch_doubles_rt(int k, int64_t stride)
 {
     switch (k)
@@ -823,6 +182,10 @@ int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps,
     default: return fail(TAD_NOT_SUPPORTED, "Hessian projection is instantiated for k in {1..10,12,15,16,18}");
     }
 }
+}  // namespace tadrt
+
+namespace
+{
 
 // ---------------------------------------------------------------------------------------------
 // pattern construction (scalar functions): vertex-pair blocks -> CSR + scatter maps
@@ -926,382 +289,6 @@ __global__ void fill_maps(const int32_t* contrib, const int32_t* pid_incl, int64
     const int64_t r0 = vrow[vi], deg = vrow[vi + 1] - r0;
     T.blockbase[(int64_t)b * T.stride + e] = (int32_t)((int64_t)d * d * r0 + (int64_t)d * (p - r0));
     T.rstride[(int64_t)bi * T.stride + e] = (int32_t)(d * deg);
-}
-
-// ---------------------------------------------------------------------------------------------
-// assembly, atomic mode: one thread per element, FP64 red.global.add on g and the CSR values
-// ---------------------------------------------------------------------------------------------
-struct SeqTable { int16_t idx[18 * 18]; };
-
-// rec / blockbase / rstride: the term's maps, already offset to the first element of the slab, leading dimension mstride;
-// grad / hess: the slab's staging, leading dimension stride; e = position inside the slab.
-template <int D, int N>
-__global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __restrict__ rec, const int32_t* __restrict__ blockbase,
-                                                              const int32_t* __restrict__ rstride, int64_t mstride,
-                                                              const double* __restrict__ grad, const double* __restrict__ hess, int64_t n,
-                                                              int64_t stride, double* __restrict__ g, double* __restrict__ Hv, int32_t* err)
-{
-    constexpr int K = D * N;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    bool finite = true;
-#pragma unroll
-    for (int bi = 0; bi < N; ++bi)
-    {
-        const int32_t vi = rec[(int64_t)bi * mstride + e];
-        if (vi < 0) continue;
-#pragma unroll
-        for (int a = 0; a < D; ++a)
-        {
-            const double v = grad[(int64_t)(D * bi + a) * stride + e];
-            finite = finite && isfinite(v);
-            atomicAdd(&g[(int64_t)D * vi + a], v);
-        }
-    }
-    if (hess)
-    {
-#pragma unroll
-        for (int bi = 0; bi < N; ++bi)
-        {
-            const int32_t rs = rstride[(int64_t)bi * mstride + e];
-#pragma unroll
-            for (int bj = 0; bj < N; ++bj)
-            {
-                const int32_t base = blockbase[(int64_t)(bi * N + bj) * mstride + e];
-                if (base < 0) continue;
-#pragma unroll
-                for (int a = 0; a < D; ++a)
-#pragma unroll
-                    for (int b = 0; b < D; ++b)
-                    {
-                        const int s = hess_seq_index(K, D * bi + a, D * bj + b);
-                        const double v = hess[(int64_t)s * stride + e];
-                        finite = finite && isfinite(v);
-                        atomicAdd(&Hv[(int64_t)base + (int64_t)a * rs + b], v);
-                    }
-            }
-        }
-    }
-    if (!finite) atomicOr(err, ERR_NONFINITE);
-}
-
-// Projection phase C fused with the atomic assembly: the projected Hessian of an element is formed in registers
-// (low-rank update of H, Detail/Projection.hh proj_apply) and scattered from there, instead of being written back to
-// the staging buffer and read again by the assembly kernel (saves 1.35 KB of HBM traffic per tet and one launch).
-template <int D, int N>
-__device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __restrict__ hess, int64_t stride, double eps, const ProjScratch& sc,
-                                               const int32_t* __restrict__ rec, const int32_t* __restrict__ blockbase,
-                                               const int32_t* __restrict__ rstride, const int64_t mstride, const double* __restrict__ grad,
-                                               double* __restrict__ g, double* __restrict__ Hv, int32_t* err, const int code)
-{
-    constexpr int K = D * N;
-    constexpr int H = K * (K + 1) / 2;
-    const double* hp = hess + e;
-    double acc[H];
-    if (code == TinyAD::detail::PROJ_REBUILT)
-    {
-        const double* rp = sc.R + e;
-        const double* wp = sc.W + e;
-        // scratch of proj_apply in shared memory: [slot][thread of the block], conflict-free
-        extern __shared__ double casm_tmp[];
-        double* tp = casm_tmp + threadIdx.x;
-        const int bd = blockDim.x;
-        TinyAD::detail::proj_apply<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
-                                      [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { acc[s] = v; }, eps,
-                                      [&](int i, double v) { tp[i * bd] = v; }, [&](int i) { return tp[i * bd]; },
-                                      [&](int nv) {
-                                          // asynchronous global -> shared copies of the nv vectors and their weights (cp.async, 8 bytes
-                                          // each): no registers, and they overlap the reflector loads that follow
-                                          using L = TinyAD::detail::ProjLayout<K>;
-                                          const unsigned dst0 = (unsigned)__cvta_generic_to_shared(tp);
-                                          for (int jv = 0; jv < nv; ++jv)
-                                          {
-#pragma unroll
-                                              for (int i = 0; i <= K; ++i)
-                                              {
-                                                  const double* src = wp + (int64_t)(i < K ? L::off_vec + jv * K + i : L::off_wgt + jv) * stride;
-                                                  const unsigned dst = dst0 + (unsigned)((jv * (K + 1) + i) * bd) * 8u;
-                                                  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-                                              }
-                                          }
-                                          return true;
-                                      },
-                                      [&] { asm volatile("cp.async.wait_all;" ::: "memory"); });
-    }
-    else
-    {
-#pragma unroll
-        for (int s = 0; s < H; ++s) acc[s] = hp[(int64_t)s * stride];
-    }
-    bool finite = true;
-#pragma unroll
-    for (int bi = 0; bi < N; ++bi)
-    {
-        const int32_t vi = rec[(int64_t)bi * mstride + e];
-        if (vi < 0) continue;
-#pragma unroll
-        for (int a = 0; a < D; ++a)
-        {
-            const double v = grad[(int64_t)(D * bi + a) * stride + e];
-            finite = finite && isfinite(v);
-            atomicAdd(&g[(int64_t)D * vi + a], v);
-        }
-    }
-#pragma unroll
-    for (int bi = 0; bi < N; ++bi)
-    {
-        const int32_t rs = rstride[(int64_t)bi * mstride + e];
-#pragma unroll
-        for (int bj = 0; bj < N; ++bj)
-        {
-            const int32_t base = blockbase[(int64_t)(bi * N + bj) * mstride + e];
-            if (base < 0) continue;
-#pragma unroll
-            for (int a = 0; a < D; ++a)
-#pragma unroll
-                for (int b = 0; b < D; ++b)
-                {
-                    const double v = acc[hess_seq_index(K, D * bi + a, D * bj + b)];
-                    finite = finite && isfinite(v);
-                    atomicAdd(&Hv[(int64_t)base + (int64_t)a * rs + b], v);
-                }
-        }
-    }
-    if (!finite) atomicOr(err, ERR_NONFINITE);
-}
-
-// LIST = false: all elements except those handed to the full solver (code PROJ_FALLBACK) when `skip_listed`;
-// LIST = true: the listed elements (their staged Hessian was projected in place by project_kernel_list).
-template <int D, int N, bool LIST>
-__global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* __restrict__ hess, int64_t n, int64_t stride, double eps,
-                                                                 ProjScratch sc, const int32_t* __restrict__ rec,
-                                                                 const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
-                                                                 int64_t mstride, const double* __restrict__ grad, double* __restrict__ g,
-                                                                 double* __restrict__ Hv, int32_t* err, const unsigned long long* counts,
-                                                                 bool skip_listed)
-{
-    if constexpr (LIST)
-    {
-        const int64_t count = (int64_t)counts[2];
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-            c_assemble_one<D, N>(sc.list[i], hess, stride, eps, sc, rec, blockbase, rstride, mstride, grad, g, Hv, err, TinyAD::detail::PROJ_FALLBACK);
-    }
-    else
-    {
-        const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if (e >= n) return;
-        const int code = sc.codes[e];
-        if (skip_listed && code == TinyAD::detail::PROJ_FALLBACK) return;
-        c_assemble_one<D, N>(e, hess, stride, eps, sc, rec, blockbase, rstride, mstride, grad, g, Hv, err, code);
-    }
-}
-
-// The scatter maps of one slab: the term's maps offset to the slab's first element (leading dimension mstride).
-struct SlabMaps
-{
-    const int32_t* rec;
-    const int32_t* blockbase;
-    const int32_t* rstride;
-    int64_t mstride;
-};
-
-template <int D, int N>
-int launch_c_assemble(const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double eps, ProjScratch sc, double* g,
-                      double* Hv, int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
-{
-    const bool split = side && side->stream;
-    // ~200 registers per thread: single-warp blocks fit 10 per SM (10 warps) where 128-thread blocks fit 2 (8 warps); the kernel is
-    // bound by the latency of its load phases, so the extra warps pay (C2: 1.18 -> 1.08 ms; capping the registers at 170 for 12 warps: 1.21 ms).
-    // TAD_CASM_BLOCK overrides (tuning knob).
-    static const int bs = [] { const char* e = getenv("TAD_CASM_BLOCK"); const int v = e ? atoi(e) : 32; return (v == 32 || v == 64 || v == 128) ? v : 32; }();
-    constexpr int K = D * N;
-    constexpr size_t tmp_thread = (size_t)TinyAD::detail::ProjLayout<K>::MAXV * (K + 1) * sizeof(double);  // 728 B at K = 12
-    static PerDeviceOnce configured;
-    bool ok = true;
-    configured.run([&] {
-        ok = cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread)) == cudaSuccess &&
-             cudaFuncSetAttribute(project_c_assemble_kernel<D, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread)) == cudaSuccess &&
-             cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-    });
-    if (!ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the fused projection/assembly kernel");
-    count_launch(split ? 2 : 1);
-    project_c_assemble_kernel<D, N, false><<<(unsigned)((n + bs - 1) / bs), bs, bs * tmp_thread, st>>>(
-        hess, n, stride, eps, sc, m.rec, m.blockbase, m.rstride, m.mstride, grad, g, Hv, err, counts, split);
-    if (split)
-    {
-        cudaStreamWaitEvent(st, side->ev_list, 0);
-        project_c_assemble_kernel<D, N, true><<<8, 128, 128 * tmp_thread, st>>>(hess, n, stride, eps, sc, m.rec, m.blockbase, m.rstride, m.mstride,
-                                                                                 grad, g, Hv, err, counts, false);
-    }
-    return TAD_OK;
-}
-
-bool fused_c_assemble_supported(int d, int N) { return d >= 1 && d <= 3 && N >= 1 && N <= 4; }
-
-int c_assemble(int d, int N, const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double eps, ProjScratch sc,
-               double* g, double* Hv, int32_t* err, const unsigned long long* counts, const ProjSide* side, cudaStream_t st)
-{
-    if (n <= 0) return TAD_OK;
-    int rc = TAD_OK;
-    switch (d * 100 + N)
-    {
-#define TAD_CASE(DD, NN) case DD * 100 + NN: rc = launch_c_assemble<DD, NN>(m, grad, hess, n, stride, eps, sc, g, Hv, err, counts, side, st); break;
-    TAD_CASE(1, 1) TAD_CASE(1, 2) TAD_CASE(1, 3) TAD_CASE(1, 4)
-    TAD_CASE(2, 1) TAD_CASE(2, 2) TAD_CASE(2, 3) TAD_CASE(2, 4)
-    TAD_CASE(3, 1) TAD_CASE(3, 2) TAD_CASE(3, 3) TAD_CASE(3, 4)
-#undef TAD_CASE
-    default: return fail(TAD_NOT_SUPPORTED, "no fused projection/assembly kernel for this (d, N)");
-    }
-    if (rc != TAD_OK) return rc;
-    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "fused projection/assembly launch failed");
-}
-
-// generic (runtime d, N) fallback
-__global__ void __launch_bounds__(128) assemble_atomic_generic(int D, int N, SeqTable seq, const int32_t* __restrict__ rec,
-                                                               const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
-                                                               int64_t mstride, const double* __restrict__ grad, const double* __restrict__ hess,
-                                                               int64_t n, int64_t stride, double* __restrict__ g, double* __restrict__ Hv,
-                                                               int32_t* err)
-{
-    const int K = D * N;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    bool finite = true;
-    for (int bi = 0; bi < N; ++bi)
-    {
-        const int32_t vi = rec[(int64_t)bi * mstride + e];
-        if (vi < 0) continue;
-        for (int a = 0; a < D; ++a)
-        {
-            const double v = grad[(int64_t)(D * bi + a) * stride + e];
-            finite = finite && isfinite(v);
-            atomicAdd(&g[(int64_t)D * vi + a], v);
-        }
-    }
-    if (hess)
-        for (int bi = 0; bi < N; ++bi)
-        {
-            const int32_t rs = rstride[(int64_t)bi * mstride + e];
-            for (int bj = 0; bj < N; ++bj)
-            {
-                const int32_t base = blockbase[(int64_t)(bi * N + bj) * mstride + e];
-                if (base < 0) continue;
-                for (int a = 0; a < D; ++a)
-                    for (int b = 0; b < D; ++b)
-                    {
-                        const int s = seq.idx[(D * bi + a) * K + (D * bj + b)];
-                        const double v = hess[(int64_t)s * stride + e];
-                        finite = finite && isfinite(v);
-                        atomicAdd(&Hv[(int64_t)base + (int64_t)a * rs + b], v);
-                    }
-            }
-        }
-    if (!finite) atomicOr(err, ERR_NONFINITE);
-}
-
-template <int D, int N>
-void launch_assemble(const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double* g, double* Hv, int32_t* err,
-                     cudaStream_t st)
-{
-    assemble_atomic_kernel<D, N><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m.rec, m.blockbase, m.rstride, m.mstride, grad, hess, n, stride, g, Hv, err);
-}
-
-int assemble_atomic(int d, int N, const SlabMaps& m, const double* grad, const double* hess, int64_t n, int64_t stride, double* g, double* Hv,
-                    int32_t* err, cudaStream_t st)
-{
-    if (n <= 0) return TAD_OK;
-    count_launch();
-    switch (d * 100 + N)
-    {
-#define TAD_CASE(DD, NN) case DD * 100 + NN: launch_assemble<DD, NN>(m, grad, hess, n, stride, g, Hv, err, st); break;
-    TAD_CASE(1, 1) TAD_CASE(1, 2) TAD_CASE(1, 3) TAD_CASE(1, 4)
-    TAD_CASE(2, 1) TAD_CASE(2, 2) TAD_CASE(2, 3) TAD_CASE(2, 4)
-    TAD_CASE(3, 1) TAD_CASE(3, 2) TAD_CASE(3, 3) TAD_CASE(3, 4)
-#undef TAD_CASE
-    default:
-    {
-        const int K = d * N;
-        if (K > 18) return fail(TAD_NOT_SUPPORTED, "assembly supports at most 18 variables per element");
-        SeqTable seq;
-        for (int i = 0; i < K; ++i)
-            for (int j = 0; j < K; ++j) seq.idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);
-        assemble_atomic_generic<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d, N, seq, m.rec, m.blockbase, m.rstride, m.mstride, grad, hess, n, stride,
-                                                                            g, Hv, err);
-    }
-    }
-    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "assembly kernel launch failed");
-}
-
-// ---------------------------------------------------------------------------------------------
-// assembly, gather mode: one thread per CSR entry, contributions summed in (term, element) order --
-// the order in which the reference's setFromTriplets adds duplicates -- deterministic, no atomics.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gather_hessian(const int64_t* __restrict__ block_ptr, const int32_t* __restrict__ contrib,
-                                                      const int64_t* __restrict__ block_key, const int64_t* __restrict__ vrow,
-                                                      const TermDev* __restrict__ terms, int n_terms, SeqTable const* __restrict__ seqs,
-                                                      int64_t n_blocks, int64_t n_handles, int d, double* __restrict__ Hv, int32_t* err)
-{
-    const int dd = d * d;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t p = tid / dd;
-    if (p >= n_blocks) return;
-    const int ab = (int)(tid % dd), a = ab / d, b = ab % d;
-    double acc = 0.0;
-    for (int64_t i = block_ptr[p]; i < block_ptr[p + 1]; ++i)
-    {
-        const int64_t c = contrib[i];
-        if (c < 0) continue;  // structural-only block
-        int t = 0;
-        while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
-        const TermDev& T = terms[t];
-        const int64_t local = c - T.off;
-        const int64_t nn = (int64_t)T.N * T.N;
-        const int64_t e = local / nn;
-        const int bb = (int)(local % nn);
-        const int bi = bb / T.N, bj = bb % T.N;
-        const int s = seqs[t].idx[(d * bi + a) * T.k + (d * bj + b)];
-        acc += T.hess[(int64_t)s * T.stride + e];
-    }
-    if (!isfinite(acc)) atomicOr(err, ERR_NONFINITE);
-    const int64_t vi = block_key[p] / n_handles;
-    const int64_t r0 = vrow[vi], deg = vrow[vi + 1] - r0;
-    Hv[(int64_t)dd * r0 + (int64_t)a * d * deg + (int64_t)d * (p - r0) + b] = acc;
-}
-
-__global__ void __launch_bounds__(128) gather_gradient(const int64_t* __restrict__ block_ptr, const int32_t* __restrict__ contrib,
-                                                       const int64_t* __restrict__ block_key, const TermDev* __restrict__ terms,
-                                                       int n_terms, int64_t n_blocks, int64_t n_handles, int d, double* __restrict__ g,
-                                                       int32_t* err)
-{
-    // one thread per (vertex, component); contributions of vertex v are those of its diagonal block (v, v)
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t v = tid / d;
-    if (v >= n_handles) return;
-    const int a = (int)(tid % d);
-    const int64_t target = v * n_handles + v;
-    int64_t lo = 0, hi = n_blocks;
-    while (lo < hi)
-    {
-        const int64_t mid = (lo + hi) / 2;
-        if (block_key[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    double acc = 0.0;
-    if (lo < n_blocks && block_key[lo] == target)
-        for (int64_t i = block_ptr[lo]; i < block_ptr[lo + 1]; ++i)
-        {
-            const int64_t c = contrib[i];
-            if (c < 0) continue;  // structural-only block
-            int t = 0;
-            while (t + 1 < n_terms && terms[t + 1].off <= c) ++t;
-            const TermDev& T = terms[t];
-            const int64_t local = c - T.off;
-            const int64_t nn = (int64_t)T.N * T.N;
-            const int64_t e = local / nn;
-            const int bi = (int)(local % nn) / T.N;
-            acc += T.grad[(int64_t)(d * bi + a) * T.stride + e];
-        }
-    if (!isfinite(acc)) atomicOr(err, ERR_NONFINITE);
-    g[(int64_t)d * v + a] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1409,7 +396,6 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 // ---------------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------------
-unsigned blocks_for(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
 
 int check_error_word(tad_function f, bool sync_already)
 {
@@ -1989,14 +975,8 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         cudaEvent_t g0 = f->lanes[0].tev[0], g1 = f->lanes[0].tev[1];
         if (f->timing) cudaEventRecord(g0, st);
         TAD_TRY(upload_terms_dev(f, true, mode));
-        const int64_t nt = f->n_blocks * f->d * f->d;
-        count_launch(nt > 0 ? 2 : 1);
-        if (nt > 0)
-            gather_hessian<<<blocks_for(nt, 128), 128, 0, st>>>(f->block_ptr.p, f->contrib.p, f->block_key.p, f->vrow.p, f->terms_dev.p, n_terms,
-                                                                reinterpret_cast<const SeqTable*>(f->seqs_dev.p), f->n_blocks, f->n_handles, f->d, Hv, f->err.p);
-        gather_gradient<<<blocks_for(f->n_vars, 128), 128, 0, st>>>(f->block_ptr.p, f->contrib.p, f->block_key.p, f->terms_dev.p, n_terms,
-                                                                    f->n_blocks, f->n_handles, f->d, g, f->err.p);
-        TAD_CUDA(cudaGetLastError());
+        TAD_TRY(gather_assemble(f->block_ptr.p, f->contrib.p, f->block_key.p, f->vrow.p, f->terms_dev.p, n_terms,
+                                reinterpret_cast<const SeqTable*>(f->seqs_dev.p), f->n_blocks, f->n_handles, f->n_vars, f->d, g, Hv, f->err.p, st));
         if (f->timing)
         {
             cudaEventRecord(g1, st);
