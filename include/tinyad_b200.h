@@ -87,6 +87,7 @@ typedef struct tad_launch_args
 typedef int (*tad_launch_fn)(void* user, const tad_launch_args* args);
 
 typedef struct tad_function_s* tad_function;
+typedef struct tad_comm_s* tad_comm;   /* one rank's view of the group of GPUs that share a partitioned function */
 
 /* Options (tad_function_set_option). */
 #define TAD_OPT_ASSEMBLY 1      /* 0 = FP64 atomics (default), 1 = deterministic gather in element order */
@@ -97,6 +98,8 @@ typedef struct tad_function_s* tad_function;
                                     0 = default (524288 for the device-pointer entry points, 131072 for the host-buffer ones), < 0 = whole term in one slab.  Gather assembly always stages whole terms. */
 #define TAD_OPT_PROJECTION 3    /* 0 = low-rank update via selected eigenvectors (default), 1 = full eigendecomposition */
 #define TAD_OPT_LANES 4         /* number of slabs in flight (1..4, default 2) */
+#define TAD_OPT_REPLICATE_GRADIENT 5 /* multi-GPU: 0 = halo-only exchange, every rank ends with the complete g entries of the vertices it
+                                        OWNS (default); 1 = all-reduce, every rank ends with the complete global g */
 #define TAD_ASSEMBLY_ATOMIC 0
 #define TAD_ASSEMBLY_GATHER 1
 
@@ -127,6 +130,34 @@ int tad_function_add_term(tad_function f, int valence, int outputs_per_element, 
 /* Multi-GPU: inject structural-only d x d blocks (handle pairs vi, vj) into the Hessian pattern, e.g. the halo-row
  * blocks other ranks will send to this rank.  They get explicit zero slots; the pattern is rebuilt on next use. */
 int tad_function_add_pattern_blocks(tad_function f, int64_t n_blocks, const int64_t* vi_host, const int64_t* vj_host);
+
+/* ---- multi-GPU: one process per GPU, the ELEMENTS are partitioned over the ranks --------------------------
+ * In the reference the reduction of element results into shared rows of g and H is one serial loop (ScalarObjectiveTerm.hh:256-277);
+ * here it crosses ranks for interface vertices.  Every rank creates the same function (same d, same n_handles: handle numbering stays
+ * GLOBAL), adds ITS elements with the same sequence of add_term calls, and attaches the communicator before the first evaluation.
+ * The runtime then
+ *   - assigns every vertex to the lowest rank that touches it (ncclAllReduce MIN) -- tad_function_vertex_owner;
+ *   - adds to each rank's pattern the blocks of its owned rows that other ranks contribute to, so that the rows a rank owns have
+ *     exactly the columns of the single-rank pattern (bit-exact per row);
+ *   - inside every evaluation, as soon as the slabs that touch halo rows are assembled (they are scheduled first), packs the
+ *     halo-row H values and halo g entries, sends them to their owners (grouped ncclSend / ncclRecv over NVLink) and adds what it
+ *     receives into its own rows, while the remaining slabs are still being assembled; f is all-reduced.
+ * After eval_with_derivatives every rank holds: f (global), the complete CSR rows of the vertices it owns (a row-distributed
+ * matrix), the complete g entries of those vertices (TAD_OPT_REPLICATE_GRADIENT = 1: all of g).  Rows / entries of vertices owned
+ * elsewhere hold this rank's partial sums.  All ranks must call the same evaluation functions in the same order.
+ * The communicator wraps NCCL, which is loaded at run time (dlopen libnccl.so.2): tad_comm_unique_id on one rank, the 128 bytes
+ * travel to the others by the caller's means (MPI, torch.distributed, a file), tad_comm_create on every rank.  tad_comm_adopt
+ * wraps an existing ncclComm_t instead (not destroyed by tad_comm_destroy). */
+#define TAD_COMM_ID_BYTES 128
+int tad_comm_unique_id(void* id_out /* TAD_COMM_ID_BYTES */);
+int tad_comm_create(const void* id, int rank, int world, int device, tad_comm* out);
+int tad_comm_adopt(void* nccl_comm, int rank, int world, int device, tad_comm* out);
+void tad_comm_destroy(tad_comm c);
+int tad_comm_rank(tad_comm c);
+int tad_comm_world(tad_comm c);
+int tad_function_set_comm(tad_function f, tad_comm c);                 /* c = NULL detaches; the pattern is rebuilt on next use */
+int tad_function_vertex_owner(tad_function f, int32_t* owner_host);     /* n_handles entries; `world` = touched by no rank */
+int tad_function_halo_bytes(tad_function f, int64_t* sent_per_evaluation); /* bytes this rank sends per eval_with_derivatives */
 
 int tad_function_variable_dimension(tad_function f);
 int64_t tad_function_n_vars(tad_function f);

@@ -22,7 +22,8 @@ STATUS_NAMES = {0: "TAD_OK", 1: "TAD_INVALID_ARGUMENT", 2: "TAD_NONFINITE_DERIVA
                 4: "TAD_TOO_MANY_VARIABLES", 5: "TAD_INDEX_OUT_OF_RANGE", 6: "TAD_NOT_SUPPORTED", 7: "TAD_OUT_OF_MEMORY",
                 8: "TAD_SOLVER_FAILED", 9: "TAD_PATTERN_MISMATCH", 10: "TAD_COMM_ERROR"}
 ASSEMBLY_ATOMIC, ASSEMBLY_GATHER = 0, 1
-OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION, OPT_LANES = 1, 2, 3, 4
+OPT_ASSEMBLY, OPT_CHUNK_ELEMENTS, OPT_PROJECTION, OPT_LANES, OPT_REPLICATE_GRADIENT = 1, 2, 3, 4, 5
+COMM_ID_BYTES = 128
 
 # term kinds of csrc/energies.cu
 SYMDIRICHLET2D, PENALTY2D, SYMDIRICHLET3D, PENALTY3D = 1, 2, 3, 4
@@ -42,6 +43,8 @@ ABI_SYMBOLS = [
     "tad_veval_sum_of_squares", "tad_veval_sum_of_squares_with_derivatives", "tad_project_batch",
     "tad_function_projection_stats", "tad_function_last_timings", "tad_function_set_timing", "tad_bench_fp64_peak",
     "tad_set_last_error", "tad_function_variable_dimension",
+    "tad_comm_unique_id", "tad_comm_create", "tad_comm_adopt", "tad_comm_destroy", "tad_comm_rank", "tad_comm_world",
+    "tad_function_set_comm", "tad_function_vertex_owner", "tad_function_halo_bytes",
     "tad_pcg_solve", "tad_newton_direction", "tad_gauss_newton_direction", "tad_newton_decrement", "tad_line_search",
 ]
 
@@ -98,6 +101,16 @@ def runtime():
         L.tad_device_count.argtypes = [vp]
         L.tad_bench_fp64_peak.argtypes = [ctypes.c_int, dbl, vp]
         L.tad_function_variable_dimension.argtypes = [vp]
+        L.tad_comm_unique_id.argtypes = [vp]
+        L.tad_comm_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.tad_comm_adopt.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.tad_comm_destroy.argtypes = [vp]
+        L.tad_comm_destroy.restype = None
+        L.tad_comm_rank.argtypes = [vp]
+        L.tad_comm_world.argtypes = [vp]
+        L.tad_function_set_comm.argtypes = [vp, vp]
+        L.tad_function_vertex_owner.argtypes = [vp, vp]
+        L.tad_function_halo_bytes.argtypes = [vp, vp]
         L.tad_pcg_solve.argtypes = [i64, ctypes.c_int, vp, vp, vp, dbl, vp, dbl, vp, dbl, ctypes.c_int, vp, vp, vp]
         L.tad_newton_direction.argtypes = [vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
         L.tad_gauss_newton_direction.argtypes = [vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
@@ -146,6 +159,38 @@ def _ptr(a):
     return a.data_ptr()
 
 
+class Comm:
+    """One rank's handle on the group of GPUs that share a partitioned function (tad_comm of the C ABI; NCCL underneath)."""
+
+    def __init__(self, id_bytes, rank, world, device):
+        self.rank, self.world, self.device = rank, world, device
+        self.h = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(id_bytes))
+        _check(runtime().tad_comm_create(buf, rank, world, device, ctypes.byref(self.h)))
+
+    @staticmethod
+    def unique_id():
+        buf = (ctypes.c_ubyte * COMM_ID_BYTES)()
+        _check(runtime().tad_comm_unique_id(buf))
+        return bytes(buf)
+
+    @staticmethod
+    def from_torch_distributed(device, group=None):
+        """The 128-byte NCCL id is created on rank 0 and broadcast with torch.distributed (plumbing only; the exchange itself runs
+        inside the runtime on its own communicator)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return Comm(box[0], rank, world, device)
+
+    def close(self):
+        if self.h:
+            runtime().tad_comm_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+
 class Function:
     """A ScalarFunction<d> / VectorFunction<d> built from the functors in csrc/energies.cu.
 
@@ -191,6 +236,23 @@ class Function:
         vj = np.ascontiguousarray(vj, dtype=np.int64)
         _check(runtime().tad_function_add_pattern_blocks(self.h, len(vi), vi.ctypes.data, vj.ctypes.data))
         self._pattern = None
+
+    def set_comm(self, comm):
+        """Partitioned evaluation: this rank's terms hold ITS elements (global handles); see include/tinyad_b200.h."""
+        _check(runtime().tad_function_set_comm(self.h, comm.h if comm is not None else None))
+        self._comm = comm
+        self._pattern = None
+
+    def vertex_owner(self):
+        """int32 per vertex: the rank that owns its rows after the exchange (lowest rank touching it)."""
+        o = np.empty(self.n_vertices, dtype=np.int32)
+        _check(runtime().tad_function_vertex_owner(self.h, o.ctypes.data))
+        return o
+
+    def halo_bytes(self):
+        n = ctypes.c_int64()
+        _check(runtime().tad_function_halo_bytes(self.h, ctypes.byref(n)))
+        return n.value
 
     def set_option(self, opt, value):
         _check(runtime().tad_function_set_option(self.h, opt, value))

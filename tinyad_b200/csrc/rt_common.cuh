@@ -25,6 +25,14 @@ using TinyAD::detail::hess_seq_index;
 using TinyAD::detail::hess_seq_rc;
 using TinyAD::detail::hess_size;
 
+// One rank's handle on the GPU group (tad_comm of the C ABI); `nccl` is an ncclComm_t.
+struct tad_comm_s
+{
+    void* nccl = nullptr;
+    int rank = 0, world = 1, device = 0;
+    bool owned = false;
+};
+
 namespace tadrt
 {
 
@@ -222,6 +230,36 @@ int assemble_atomic(int d, int N, const SlabMaps& m, const double* grad, const d
 int gather_assemble(const int64_t* block_ptr, const int32_t* contrib, const int64_t* block_key, const int64_t* vrow, const TermDev* terms,
                     int n_terms, const SeqTable* seqs, int64_t n_blocks, int64_t n_handles, int64_t n_vars, int d, double* g, double* Hv,
                     int32_t* err, cudaStream_t st);
+
+// ---- multi-GPU exchange (comm.cu) ----
+// Who sends which blocks / gradient entries to whom (built with the pattern, runtime.cu build_halo_plan).  Blocks and vertices are
+// stored peer by peer: segment [blk_off[p], blk_off[p+1]) of the send lists goes to rank p, likewise for the receive lists.
+struct HaloPlan
+{
+    bool ready = false;
+    std::vector<int32_t> owner_host;                 // per vertex; world = untouched
+    DevBuf<int32_t> owner;
+    std::vector<int64_t> send_blk_off, recv_blk_off; // [world + 1], in blocks
+    std::vector<int64_t> send_vtx_off, recv_vtx_off; // [world + 1], in vertices
+    std::vector<int64_t> send_h_off, recv_h_off;     // the same in doubles (blocks * d * d)
+    std::vector<int64_t> send_g_off, recv_g_off;     // (vertices * d)
+    DevBuf<int32_t> send_base, send_rs, recv_base, recv_rs;   // CSR value index of entry (0,0) and row stride of every block
+    DevBuf<int32_t> send_vtx, recv_vtx;
+    DevBuf<double> send_h, recv_h, send_g, recv_g;
+    std::vector<int64_t> keys_from_peers;            // blocks other ranks send here: structural slots of the local pattern
+    int64_t recv_min_value = INT64_MAX;              // CSR values from this index on may receive halo contributions
+    void clear() { *this = HaloPlan(); }
+};
+int comm_allreduce_min_i32(tad_comm c, int32_t* buf_dev, int64_t n, cudaStream_t st);
+int comm_allreduce_sum_f64(tad_comm c, double* buf_dev, int64_t n, cudaStream_t st);
+int comm_allgather_i64(tad_comm c, const int64_t* send_dev, int64_t* recv_dev, int64_t n_per_rank, cudaStream_t st);
+int comm_group_begin();
+int comm_group_end();
+int comm_exchange(tad_comm c, const void* sendbuf, const int64_t* off, void* recvbuf, const int64_t* roff, int bytes_per_element, cudaStream_t st);
+int halo_pack(const double* Hv, const double* g, const int32_t* base, const int32_t* rs, int64_t n_blocks, const int32_t* vtx, int64_t n_vtx, int d,
+              double* bufH, double* bufG, cudaStream_t st);
+int halo_add(double* Hv, double* g, const int32_t* base, const int32_t* rs, int64_t n_blocks, const int32_t* vtx, int64_t n_vtx, int d,
+             const double* bufH, const double* bufG, cudaStream_t st);
 
 inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)std::max<int64_t>(1, (n + bs - 1) / bs); }
 

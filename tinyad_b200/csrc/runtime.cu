@@ -52,7 +52,8 @@ struct tad_function_s
         int64_t chunk = -2;       // slab size the schedule was built for (-1: whole terms)
         bool whole = false;
         bool has_final = false;   // Slab::final_values computed (needs the pattern)
-        void clear() { slabs.clear(); chunk = -2; has_final = false; }
+        int n_halo_slabs = 0;     // multi-GPU: the first n_halo_slabs slabs touch vertices owned by other ranks (scheduled first)
+        void clear() { slabs.clear(); chunk = -2; has_final = false; n_halo_slabs = 0; }
     };
     Schedule sched[2];            // [0] device-pointer entry points, [1] host-buffer entry points (smaller slabs: finer D2H pipelining)
     // scratch
@@ -72,6 +73,12 @@ struct tad_function_s
     std::vector<Lane> lanes;
     std::vector<cudaEvent_t> slab_events;  // one per slab of the schedule: "this slab is assembled"
     cudaStream_t copy_stream = nullptr;    // device -> host copies of finished rows (host-buffer entry points)
+    // multi-GPU (tad_function_set_comm): the halo plan is built with the pattern; all NCCL calls of an evaluation go to comm_stream
+    tad_comm comm = nullptr;
+    HaloPlan halo;
+    int replicate_gradient = 0;            // TAD_OPT_REPLICATE_GRADIENT
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_comm[2] = {nullptr, nullptr};   // main stream -> comm stream, comm stream -> main stream
     std::recursive_mutex mtx;      // eval* may be called concurrently (ScalarFunctionTest.cc:255-291): calls on one function are serialised
 };
 
@@ -512,7 +519,9 @@ int build_pattern_scalar(tad_function f)
         nC += (int64_t)t.N * t.N * t.n;
     }
     const int64_t n_term_contrib = nC;
-    nC += (int64_t)f->extra_keys.size();
+    std::vector<int64_t> structural = f->extra_keys;   // structural-only blocks: injected by the user, or sent here by other ranks
+    structural.insert(structural.end(), f->halo.keys_from_peers.begin(), f->halo.keys_from_peers.end());
+    nC += (int64_t)structural.size();
     if (nC >= (int64_t)INT32_MAX) return fail(TAD_NOT_SUPPORTED, "more than 2^31 block contributions");
     f->n_contrib = nC;
     for (auto& t : f->terms)
@@ -538,11 +547,11 @@ int build_pattern_scalar(tad_function f)
         const int64_t cnt = (int64_t)td[i].N * td[i].N * td[i].n;
         if (cnt) gen_block_keys<<<blocks_for(cnt, 256), 256, 0, st>>>(td[i], f->n_handles, keys_a.p, pay_a.p);
     }
-    if (!f->extra_keys.empty())
+    if (!structural.empty())
     {
         // structural-only blocks (no local contribution): payload -1
-        const size_t ne = f->extra_keys.size();
-        TAD_CUDA(cudaMemcpyAsync(keys_a.p + n_term_contrib, f->extra_keys.data(), ne * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        const size_t ne = structural.size();
+        TAD_CUDA(cudaMemcpyAsync(keys_a.p + n_term_contrib, structural.data(), ne * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         fill_i32<<<blocks_for((int64_t)ne, 256), 256, 0, st>>>(pay_a.p + n_term_contrib, (int64_t)ne, -1);
     }
     int64_t n_valid = 0, n_blocks = 0;
@@ -704,10 +713,156 @@ int build_pattern_vector(tad_function f)
     return TAD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: vertex ownership, halo blocks, exchange lists.  Collective: every rank of the communicator runs
+// this at the same point (the first pattern query / evaluation after tad_function_set_comm).
+// ---------------------------------------------------------------------------------------------
+__global__ void mark_touched(const int32_t* __restrict__ rec, int N, int64_t stride, int64_t n, int rank, int32_t* __restrict__ owner)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    for (int j = 0; j < N; ++j)
+    {
+        const int32_t v = rec[(int64_t)j * stride + e];
+        if (v >= 0) atomicMin(&owner[v], rank);
+    }
+}
+
+// CSR position of the d x d blocks `keys` (vi * n_handles + vj): value index of entry (0,0) and distance between its rows.
+__global__ void lookup_blocks(const int64_t* __restrict__ keys, int64_t n, const int64_t* __restrict__ block_key, int64_t n_blocks,
+                              const int64_t* __restrict__ vrow, int64_t n_handles, int d, int32_t* __restrict__ base, int32_t* __restrict__ rs,
+                              int32_t* __restrict__ missing)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t key = keys[i];
+    int64_t lo = 0, hi = n_blocks;
+    while (lo < hi)
+    {
+        const int64_t mid = (lo + hi) / 2;
+        if (block_key[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= n_blocks || block_key[lo] != key) { atomicAdd(missing, 1); base[i] = 0; rs[i] = 0; return; }
+    const int64_t vi = key / n_handles;
+    const int64_t r0 = vrow[vi], deg = vrow[vi + 1] - r0;
+    base[i] = (int32_t)((int64_t)d * d * r0 + (int64_t)d * (lo - r0));
+    rs[i] = (int32_t)(d * deg);
+}
+
+int build_halo_plan(tad_function f)
+{
+    HaloPlan& P = f->halo;
+    tad_comm c = f->comm;
+    const int W = c->world, R = c->rank, d = f->d;
+    const int64_t nh = f->n_handles;
+    cudaStream_t st = f->stream;
+    // 1. ownership: lowest rank that touches the vertex
+    TAD_CUDA(P.owner.ensure((size_t)nh));
+    fill_i32<<<blocks_for(nh, 256), 256, 0, st>>>(P.owner.p, nh, W);
+    for (const Term& t : f->terms)
+        if (t.n > 0) mark_touched<<<blocks_for(t.n, 256), 256, 0, st>>>(t.rec_handles.p, t.N, t.stride, t.n, R, P.owner.p);
+    TAD_CUDA(cudaGetLastError());
+    TAD_TRY(comm_allreduce_min_i32(c, P.owner.p, nh, st));
+    P.owner_host.assign((size_t)nh, W);
+    TAD_CUDA(cudaMemcpyAsync(P.owner_host.data(), P.owner.p, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    // 2. blocks of the local pattern whose row vertex is owned elsewhere, by destination (block keys are sorted)
+    std::vector<int64_t> bk((size_t)f->n_blocks);
+    if (f->n_blocks) TAD_CUDA(cudaMemcpyAsync(bk.data(), f->block_key.p, (size_t)f->n_blocks * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TAD_CUDA(cudaStreamSynchronize(st));
+    std::vector<std::vector<int64_t>> send_keys((size_t)W);
+    for (int64_t key : bk)
+    {
+        const int32_t o = P.owner_host[(size_t)(key / nh)];
+        if (o != R && o < W) send_keys[(size_t)o].push_back(key);
+    }
+    // 3. who sends how many blocks to whom
+    std::vector<int64_t> cnt((size_t)W, 0), all((size_t)W * W, 0);
+    for (int p = 0; p < W; ++p) cnt[(size_t)p] = (int64_t)send_keys[(size_t)p].size();
+    DevBuf<int64_t> cnt_d, all_d;
+    TAD_CUDA(cnt_d.ensure((size_t)W)); TAD_CUDA(all_d.ensure((size_t)W * W));
+    TAD_CUDA(cudaMemcpyAsync(cnt_d.p, cnt.data(), (size_t)W * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    TAD_TRY(comm_allgather_i64(c, cnt_d.p, all_d.p, W, st));
+    TAD_CUDA(cudaMemcpyAsync(all.data(), all_d.p, (size_t)W * W * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TAD_CUDA(cudaStreamSynchronize(st));
+    P.send_blk_off.assign((size_t)W + 1, 0); P.recv_blk_off.assign((size_t)W + 1, 0);
+    for (int p = 0; p < W; ++p)
+    {
+        P.send_blk_off[(size_t)p + 1] = P.send_blk_off[(size_t)p] + cnt[(size_t)p];
+        P.recv_blk_off[(size_t)p + 1] = P.recv_blk_off[(size_t)p] + (p == R ? 0 : all[(size_t)p * W + R]);
+    }
+    const int64_t ns = P.send_blk_off[(size_t)W], nr = P.recv_blk_off[(size_t)W];
+    // 4. the keys themselves
+    std::vector<int64_t> sk((size_t)ns), rk((size_t)nr);
+    for (int p = 0; p < W; ++p) std::copy(send_keys[(size_t)p].begin(), send_keys[(size_t)p].end(), sk.begin() + P.send_blk_off[(size_t)p]);
+    DevBuf<int64_t> sk_d, rk_d;
+    TAD_CUDA(sk_d.ensure((size_t)std::max<int64_t>(ns, 1))); TAD_CUDA(rk_d.ensure((size_t)std::max<int64_t>(nr, 1)));
+    if (ns) TAD_CUDA(cudaMemcpyAsync(sk_d.p, sk.data(), (size_t)ns * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    TAD_TRY(comm_group_begin());
+    TAD_TRY(comm_exchange(c, sk_d.p, P.send_blk_off.data(), rk_d.p, P.recv_blk_off.data(), (int)sizeof(int64_t), st));
+    TAD_TRY(comm_group_end());
+    if (nr) TAD_CUDA(cudaMemcpyAsync(rk.data(), rk_d.p, (size_t)nr * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TAD_CUDA(cudaStreamSynchronize(st));
+    for (int64_t key : rk)
+        if (key < 0 || key / nh >= nh || P.owner_host[(size_t)(key / nh)] != R) return fail(TAD_COMM_ERROR, "halo exchange: received a block of a row this rank does not own");
+    // 5. rebuild the pattern with structural slots for the received blocks: owned rows now have the columns of the 1-rank pattern
+    P.keys_from_peers = rk;
+    TAD_TRY(build_pattern_scalar(f));
+    // 6. positions of the exchanged blocks in the local CSR; gradient entries travel with the DIAGONAL blocks' vertices
+    TAD_CUDA(P.send_base.ensure((size_t)std::max<int64_t>(ns, 1))); TAD_CUDA(P.send_rs.ensure((size_t)std::max<int64_t>(ns, 1)));
+    TAD_CUDA(P.recv_base.ensure((size_t)std::max<int64_t>(nr, 1))); TAD_CUDA(P.recv_rs.ensure((size_t)std::max<int64_t>(nr, 1)));
+    DevBuf<int32_t> missing;
+    TAD_CUDA(missing.ensure(1));
+    TAD_CUDA(cudaMemsetAsync(missing.p, 0, sizeof(int32_t), st));
+    if (ns) lookup_blocks<<<blocks_for(ns, 256), 256, 0, st>>>(sk_d.p, ns, f->block_key.p, f->n_blocks, f->vrow.p, nh, d, P.send_base.p, P.send_rs.p, missing.p);
+    if (nr) lookup_blocks<<<blocks_for(nr, 256), 256, 0, st>>>(rk_d.p, nr, f->block_key.p, f->n_blocks, f->vrow.p, nh, d, P.recv_base.p, P.recv_rs.p, missing.p);
+    int32_t n_missing = 0;
+    TAD_CUDA(cudaMemcpyAsync(&n_missing, missing.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> sv, rv;
+    P.send_vtx_off.assign((size_t)W + 1, 0); P.recv_vtx_off.assign((size_t)W + 1, 0);
+    int64_t min_recv_vertex = INT64_MAX;
+    for (int p = 0; p < W; ++p)
+    {
+        for (int64_t i = P.send_blk_off[(size_t)p]; i < P.send_blk_off[(size_t)p + 1]; ++i)
+            if (sk[(size_t)i] / nh == sk[(size_t)i] % nh) sv.push_back((int32_t)(sk[(size_t)i] / nh));
+        for (int64_t i = P.recv_blk_off[(size_t)p]; i < P.recv_blk_off[(size_t)p + 1]; ++i)
+        {
+            const int64_t vi = rk[(size_t)i] / nh;
+            min_recv_vertex = std::min(min_recv_vertex, vi);
+            if (vi == rk[(size_t)i] % nh) rv.push_back((int32_t)vi);
+        }
+        P.send_vtx_off[(size_t)p + 1] = (int64_t)sv.size();
+        P.recv_vtx_off[(size_t)p + 1] = (int64_t)rv.size();
+    }
+    TAD_CUDA(P.send_vtx.ensure(std::max<size_t>(sv.size(), 1))); TAD_CUDA(P.recv_vtx.ensure(std::max<size_t>(rv.size(), 1)));
+    if (!sv.empty()) TAD_CUDA(cudaMemcpyAsync(P.send_vtx.p, sv.data(), sv.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (!rv.empty()) TAD_CUDA(cudaMemcpyAsync(P.recv_vtx.p, rv.data(), rv.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    TAD_CUDA(cudaStreamSynchronize(st));
+    if (n_missing) return fail(TAD_COMM_ERROR, "halo exchange: a block is missing from the local pattern");
+    const int64_t dd = (int64_t)d * d;
+    P.send_h_off.resize((size_t)W + 1); P.recv_h_off.resize((size_t)W + 1); P.send_g_off.resize((size_t)W + 1); P.recv_g_off.resize((size_t)W + 1);
+    for (int p = 0; p <= W; ++p)
+    {
+        P.send_h_off[(size_t)p] = dd * P.send_blk_off[(size_t)p]; P.recv_h_off[(size_t)p] = dd * P.recv_blk_off[(size_t)p];
+        P.send_g_off[(size_t)p] = d * P.send_vtx_off[(size_t)p]; P.recv_g_off[(size_t)p] = d * P.recv_vtx_off[(size_t)p];
+    }
+    TAD_CUDA(P.send_h.ensure((size_t)std::max<int64_t>(dd * ns, 1))); TAD_CUDA(P.recv_h.ensure((size_t)std::max<int64_t>(dd * nr, 1)));
+    TAD_CUDA(P.send_g.ensure(std::max<size_t>(d * sv.size(), 1))); TAD_CUDA(P.recv_g.ensure(std::max<size_t>(d * rv.size(), 1)));
+    P.recv_min_value = (min_recv_vertex == INT64_MAX) ? INT64_MAX : dd * f->vrow_host[(size_t)min_recv_vertex];
+    P.ready = true;
+    return TAD_OK;
+}
+
 int ensure_pattern(tad_function f)
 {
-    if (f->pattern_built) return TAD_OK;
-    return f->is_vector ? build_pattern_vector(f) : build_pattern_scalar(f);
+    if (f->pattern_built && (!f->comm || f->is_vector || f->halo.ready)) return TAD_OK;
+    if (f->is_vector) return build_pattern_vector(f);
+    if (f->comm)
+    {
+        f->halo.clear();                 // first the local pattern alone, then ownership and the blocks the peers send
+        TAD_TRY(build_pattern_scalar(f));
+        return build_halo_plan(f);
+    }
+    return build_pattern_scalar(f);
 }
 
 struct DeviceGuard
@@ -718,18 +873,23 @@ struct DeviceGuard
 };
 
 // Smallest variable handle touched by the elements [e_begin, e_begin + n) of a term (one block per slab).
+// owner / rank (multi-GPU, owner may be null): halo[slab] = 1 if the slab touches a vertex owned by another rank.
 __global__ void __launch_bounds__(256) slab_min_vertex(const int32_t* __restrict__ rec, int N, int64_t stride, const int64_t* __restrict__ begin,
-                                                       const int64_t* __restrict__ count, int32_t* __restrict__ out)
+                                                       const int64_t* __restrict__ count, int32_t* __restrict__ out,
+                                                       const int32_t* __restrict__ owner, int rank, int32_t* __restrict__ halo)
 {
     __shared__ int32_t sh[256];
     const int64_t e0 = begin[blockIdx.x], n = count[blockIdx.x];
     int32_t m = INT32_MAX;
+    bool foreign = false;
     for (int64_t i = threadIdx.x; i < n; i += 256)
         for (int j = 0; j < N; ++j)
         {
             const int32_t v = rec[(int64_t)j * stride + e0 + i];
             if (v >= 0 && v < m) m = v;
+            if (owner && v >= 0 && owner[v] != rank) foreign = true;
         }
+    if (owner && __syncthreads_or(foreign ? 1 : 0) && threadIdx.x == 0) halo[blockIdx.x] = 1;
     sh[threadIdx.x] = m;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1)
@@ -765,7 +925,7 @@ int build_schedule(tad_function f, int mode, bool whole_terms, bool host_path, t
     *out = &S;
     const int64_t chunk = effective_chunk(f, whole_terms, host_path);
     const bool cached = S.chunk == chunk && S.whole == whole_terms && (!S.slabs.empty() || f->n_elements == 0);
-    if (cached && (S.has_final || mode != TAD_MODE_SECOND)) return TAD_OK;
+    if (cached && (S.has_final || (mode != TAD_MODE_SECOND && !(f->comm && f->halo.ready)))) return TAD_OK;
     if (!cached)
     {
         S.clear();
@@ -783,15 +943,16 @@ int build_schedule(tad_function f, int mode, bool whole_terms, bool host_path, t
         S.whole = whole_terms;
     }
     const size_t ns = S.slabs.size();
-    if (mode == TAD_MODE_SECOND && !f->is_vector && f->pattern_built && ns > 0)
+    const bool partitioned = f->comm && f->halo.ready;
+    if ((mode == TAD_MODE_SECOND || partitioned) && !f->is_vector && f->pattern_built && ns > 0)
     {
-        std::vector<int32_t> vmin(ns, INT32_MAX);
-        if (ns > 1)
+        std::vector<int32_t> vmin(ns, INT32_MAX), halo(ns, 0);
+        if (ns > 1 || partitioned)
         {
             std::vector<int64_t> hb(ns), hc(ns);
             DevBuf<int64_t> db, dc;
-            DevBuf<int32_t> dout;
-            TAD_CUDA(db.ensure(ns)); TAD_CUDA(dc.ensure(ns)); TAD_CUDA(dout.ensure(ns));
+            DevBuf<int32_t> dout, dhalo;
+            TAD_CUDA(db.ensure(ns)); TAD_CUDA(dc.ensure(ns)); TAD_CUDA(dout.ensure(ns)); TAD_CUDA(dhalo.ensure(ns));
             for (size_t ti = 0; ti < f->terms.size(); ++ti)
             {
                 // slabs of one term are contiguous in the schedule
@@ -802,16 +963,34 @@ int build_schedule(tad_function f, int mode, bool whole_terms, bool host_path, t
                 const Term& t = f->terms[ti];
                 TAD_CUDA(cudaMemcpyAsync(db.p, hb.data(), cnt * sizeof(int64_t), cudaMemcpyHostToDevice, f->stream));
                 TAD_CUDA(cudaMemcpyAsync(dc.p, hc.data(), cnt * sizeof(int64_t), cudaMemcpyHostToDevice, f->stream));
-                slab_min_vertex<<<(unsigned)cnt, 256, 0, f->stream>>>(t.rec_handles.p, t.N, t.stride, db.p, dc.p, dout.p);
+                TAD_CUDA(cudaMemsetAsync(dhalo.p, 0, cnt * sizeof(int32_t), f->stream));
+                slab_min_vertex<<<(unsigned)cnt, 256, 0, f->stream>>>(t.rec_handles.p, t.N, t.stride, db.p, dc.p, dout.p,
+                                                                      partitioned ? f->halo.owner.p : nullptr, partitioned ? f->comm->rank : 0, dhalo.p);
                 TAD_CUDA(cudaMemcpyAsync(vmin.data() + first, dout.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+                TAD_CUDA(cudaMemcpyAsync(halo.data() + first, dhalo.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
                 TAD_CUDA(cudaStreamSynchronize(f->stream));
             }
+        }
+        if (partitioned && !S.has_final)
+        {
+            // slabs that touch halo rows go first: their contributions can travel to the owners while the rest is assembled
+            std::vector<size_t> order(ns);
+            for (size_t q = 0; q < ns; ++q) order[q] = q;
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return halo[a] > halo[b]; });
+            std::vector<Slab> slabs(ns);
+            std::vector<int32_t> vm(ns);
+            int nh = 0;
+            for (size_t q = 0; q < ns; ++q) { slabs[q] = S.slabs[order[q]]; vm[q] = vmin[order[q]]; nh += halo[order[q]] ? 1 : 0; }
+            S.slabs.swap(slabs);
+            vmin.swap(vm);
+            S.n_halo_slabs = nh;
         }
         const int64_t dd = (int64_t)f->d * f->d;
         int64_t later = INT64_MAX;  // smallest vertex touched by the slabs after q
         for (size_t q = ns; q-- > 0;)
         {
             S.slabs[q].final_values = (later == INT64_MAX || f->vrow_host.empty()) ? f->nnz : dd * f->vrow_host[(size_t)std::min<int64_t>(later, f->n_handles)];
+            if (partitioned) S.slabs[q].final_values = std::min(S.slabs[q].final_values, f->halo.recv_min_value);   // rows that receive halo values stay open
             if (vmin[q] != INT32_MAX) later = std::min<int64_t>(later, vmin[q]);
         }
         S.has_final = true;
@@ -867,7 +1046,8 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     LaunchCounterScope counter(&f->n_launches);
     cudaStream_t st = f->stream;
     const int n_terms = (int)f->terms.size();
-    if (mode == TAD_MODE_SECOND) TAD_TRY(ensure_pattern(f));
+    if (mode == TAD_MODE_SECOND || f->comm) TAD_TRY(ensure_pattern(f));   // partitioned: ownership and exchange lists come with the pattern
+    const bool partitioned = f->comm && f->halo.ready;
     TAD_TRY(wait_for_caller(f));
     TAD_CUDA(cudaMemsetAsync(f->err.p, 0, 8 * sizeof(int32_t), st));
     TAD_CUDA(f->fterm.ensure((size_t)std::max(n_terms, 1)));
@@ -946,6 +1126,27 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
             cudaEventElapsedTime(&m, L.tev[2], L.tev[3]); ms_asm += m;
         }
     }
+    // multi-GPU: as soon as the slabs that touch halo rows are assembled (scheduled first), their H values and g entries travel to
+    // the owners on the communication stream, and what the peers send is added into this rank's rows -- next to the assembly of
+    // the remaining slabs (atomics on both sides)
+    const bool halo_g = partitioned && mode >= TAD_MODE_FIRST && !f->replicate_gradient;
+    const bool halo_h = partitioned && mode == TAD_MODE_SECOND;
+    if ((halo_g || halo_h) && !gather)
+    {
+        const HaloPlan& P = f->halo;
+        cudaStream_t cs = f->comm_stream;
+        const int W = f->comm->world;
+        TAD_CUDA(cudaStreamWaitEvent(cs, f->ev[0], 0));
+        for (int q = 0; q < std::min(schedule->n_halo_slabs, n_slabs); ++q) TAD_CUDA(cudaStreamWaitEvent(cs, f->slab_events[(size_t)q], 0));
+        TAD_TRY(halo_pack(halo_h ? Hv : nullptr, halo_g ? g : nullptr, P.send_base.p, P.send_rs.p, P.send_blk_off[(size_t)W], P.send_vtx.p,
+                          P.send_vtx_off[(size_t)W], f->d, P.send_h.p, P.send_g.p, cs));
+        TAD_TRY(comm_group_begin());
+        if (halo_h) TAD_TRY(comm_exchange(f->comm, P.send_h.p, P.send_h_off.data(), P.recv_h.p, P.recv_h_off.data(), (int)sizeof(double), cs));
+        if (halo_g) TAD_TRY(comm_exchange(f->comm, P.send_g.p, P.send_g_off.data(), P.recv_g.p, P.recv_g_off.data(), (int)sizeof(double), cs));
+        TAD_TRY(comm_group_end());
+        TAD_TRY(halo_add(halo_h ? Hv : nullptr, halo_g ? g : nullptr, P.recv_base.p, P.recv_rs.p, P.recv_blk_off[(size_t)W], P.recv_vtx.p,
+                         P.recv_vtx_off[(size_t)W], f->d, P.recv_h.p, P.recv_g.p, cs));
+    }
     // pipelined D2H of the rows that are final (all slabs are queued by now, so a pageable destination, whose copies block the
     // host, cannot starve the GPU)
     int64_t copied = 0;
@@ -984,6 +1185,31 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
             float m = 0;
             cudaEventElapsedTime(&m, g0, g1); ms_asm += m;
         }
+    }
+    if (partitioned)
+    {
+        // the per-term sums of f (and, on request, all of g) are all-reduced on the communication stream, after the halo exchange
+        const HaloPlan& P = f->halo;
+        cudaStream_t cs = f->comm_stream;
+        const int W = f->comm->world;
+        TAD_CUDA(cudaEventRecord(f->ev_comm[0], st));
+        TAD_CUDA(cudaStreamWaitEvent(cs, f->ev_comm[0], 0));
+        if ((halo_g || halo_h) && gather)
+        {
+            // gather assembly writes g and the CSR values at the end of the evaluation: the exchange follows it (no overlap)
+            TAD_TRY(halo_pack(halo_h ? Hv : nullptr, halo_g ? g : nullptr, P.send_base.p, P.send_rs.p, P.send_blk_off[(size_t)W], P.send_vtx.p,
+                              P.send_vtx_off[(size_t)W], f->d, P.send_h.p, P.send_g.p, cs));
+            TAD_TRY(comm_group_begin());
+            if (halo_h) TAD_TRY(comm_exchange(f->comm, P.send_h.p, P.send_h_off.data(), P.recv_h.p, P.recv_h_off.data(), (int)sizeof(double), cs));
+            if (halo_g) TAD_TRY(comm_exchange(f->comm, P.send_g.p, P.send_g_off.data(), P.recv_g.p, P.recv_g_off.data(), (int)sizeof(double), cs));
+            TAD_TRY(comm_group_end());
+            TAD_TRY(halo_add(halo_h ? Hv : nullptr, halo_g ? g : nullptr, P.recv_base.p, P.recv_rs.p, P.recv_blk_off[(size_t)W], P.recv_vtx.p,
+                             P.recv_vtx_off[(size_t)W], f->d, P.recv_h.p, P.recv_g.p, cs));
+        }
+        if (n_terms) TAD_TRY(comm_allreduce_sum_f64(f->comm, f->fterm.p, n_terms, cs));
+        if (mode >= TAD_MODE_FIRST && f->replicate_gradient) TAD_TRY(comm_allreduce_sum_f64(f->comm, g, f->n_vars, cs));
+        TAD_CUDA(cudaEventRecord(f->ev_comm[1], cs));
+        TAD_CUDA(cudaStreamWaitEvent(st, f->ev_comm[1], 0));
     }
     TAD_CUDA(cudaEventRecord(f->ev[1], st));
     if (hc)
@@ -1132,7 +1358,10 @@ int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector
     f->device = device;
     if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess || f->err.ensure(8) != cudaSuccess ||
         cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&f->ev[0]) != cudaSuccess ||
-        cudaEventCreate(&f->ev[1]) != cudaSuccess || cudaEventCreateWithFlags(&f->ev_caller, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreate(&f->ev[1]) != cudaSuccess || cudaEventCreateWithFlags(&f->ev_caller, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&f->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f->ev_comm[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f->ev_comm[1], cudaEventDisableTiming) != cudaSuccess)
     {
         tad_function_destroy(f);
         return fail(TAD_CUDA_ERROR, "stream / buffer creation failed");
@@ -1161,6 +1390,8 @@ void tad_function_destroy(tad_function f)
     for (auto& e : f->ev) if (e) cudaEventDestroy(e);
     if (f->ev_caller) cudaEventDestroy(f->ev_caller);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
+    if (f->comm_stream) { cudaStreamSynchronize(f->comm_stream); cudaStreamDestroy(f->comm_stream); }
+    for (auto& e : f->ev_comm) if (e) cudaEventDestroy(e);
     if (f->stream) cudaStreamDestroy(f->stream);
     delete f;  // device buffers are freed here, still under the device guard
 }
@@ -1180,8 +1411,45 @@ int tad_function_set_option(tad_function f, int option, int64_t value)
         if (value < 1 || value > 4) return fail(TAD_INVALID_ARGUMENT, "lanes must be in 1..4");
         f->n_lanes = (int)value;
         return TAD_OK;
+    case TAD_OPT_REPLICATE_GRADIENT: f->replicate_gradient = value != 0; return TAD_OK;
     default: return fail(TAD_INVALID_ARGUMENT, "unknown option");
     }
+}
+
+int tad_function_set_comm(tad_function f, tad_comm c)
+{
+    if (!f) return fail(TAD_INVALID_ARGUMENT, "null function");
+    if (c && f->is_vector) return fail(TAD_NOT_SUPPORTED, "partitioned evaluation is implemented for scalar functions");
+    if (c && c->device != f->device) return fail(TAD_INVALID_ARGUMENT, "the communicator lives on another device than the function");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
+    f->comm = c;
+    f->halo.clear();
+    f->pattern_built = false;   // ownership, the peers' blocks and the exchange lists are built with the pattern
+    return TAD_OK;
+}
+
+int tad_function_vertex_owner(tad_function f, int32_t* owner_host)
+{
+    if (!f || !owner_host) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    if (!f->comm) { for (int64_t v = 0; v < f->n_handles; ++v) owner_host[v] = 0; return TAD_OK; }
+    TAD_TRY(ensure_pattern(f));
+    std::memcpy(owner_host, f->halo.owner_host.data(), (size_t)f->n_handles * sizeof(int32_t));
+    return TAD_OK;
+}
+
+int tad_function_halo_bytes(tad_function f, int64_t* sent_per_evaluation)
+{
+    if (!f || !sent_per_evaluation) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(f->mtx);
+    DeviceGuard guard(f->device);
+    *sent_per_evaluation = 0;
+    if (!f->comm) return TAD_OK;
+    TAD_TRY(ensure_pattern(f));
+    const size_t W = (size_t)f->comm->world;
+    *sent_per_evaluation = (int64_t)sizeof(double) * (f->halo.send_h_off[W] + f->halo.send_g_off[W]);
+    return TAD_OK;
 }
 
 int tad_function_get_stream(tad_function f, void** stream)
