@@ -47,7 +47,11 @@ typedef enum tad_mode
     TAD_MODE_RECORD = 0,  /* run the functor on a recorder element: which handles does each element touch, in first-access order (RecorderElement, ScalarFunctionImpl.hh:106-129) */
     TAD_MODE_PASSIVE = 1, /* plain double        (ScalarObjectiveTerm.hh:162-186) */
     TAD_MODE_FIRST = 2,   /* Scalar<k,false>     (ScalarObjectiveTerm.hh:188-222, VectorObjectiveTerm.hh:180-243) */
-    TAD_MODE_SECOND = 3   /* Scalar<k,true>      (ScalarObjectiveTerm.hh:224-278) */
+    TAD_MODE_SECOND = 3,  /* Scalar<k,true>      (ScalarObjectiveTerm.hh:224-278) */
+    TAD_MODE_SECOND_FUSED = 4 /* Scalar<k,true> + PSD projection (HessianProjection.hh:48-101) + assembly (ScalarObjectiveTerm.hh:256-277)
+                             in ONE kernel, nothing but `val` staged: for terms with few variables per element (k <= 6, e.g. Double<6>
+                             triangles), whose value, gradient and packed Hessian fit one thread.  A launcher that has no such kernel
+                             returns TAD_NOT_SUPPORTED and the runtime falls back to TAD_MODE_SECOND + its own projection / assembly kernels. */
 } tad_mode;
 
 /* Arguments of one element-kernel launch.  All pointers are device pointers.  A launch covers the element SLAB
@@ -81,6 +85,16 @@ typedef struct tad_launch_args
     int64_t e_begin;            /* first element of the slab */
     int64_t rec_stride;         /* leading dimension of rec_handles */
     int64_t* launch_counter;    /* HOST counter (may be NULL): the launcher adds the number of kernels it launched */
+    /* TAD_MODE_SECOND_FUSED only: where the element kernel scatters to.  The maps are the term's scatter maps, indexed by the element
+     * itself like rec_handles (leading dimension rec_stride): blockbase[(bi * N + bj) * rec_stride + e] = CSR value index of entry (0,0)
+     * of the d x d block of vertex pair (bi, bj), -1 = unused; rstride[bi * rec_stride + e] = distance between the rows of that block row. */
+    const int32_t* blockbase;
+    const int32_t* rstride;
+    double* g;                  /* n_vars, accumulated with FP64 atomics */
+    double* H_values;           /* nnz, accumulated with FP64 atomics */
+    int32_t project;            /* 1: project every element Hessian to PSD first */
+    double eps;                 /* projection_eps */
+    unsigned long long* counts; /* device uint64[4], may be NULL: [0] += elements decomposed, [1] += rebuilt, [3] += finished by the full solver */
 } tad_launch_args;
 
 /* Launches the element kernel of one term; returns a tad_status (TAD_CUDA_ERROR on launch failure). */
@@ -95,7 +109,7 @@ typedef struct tad_comm_s* tad_comm;   /* one rank's view of the group of GPUs t
                                     by slab, so staging + projection scratch are bounded by `lanes` slabs (2.3 KB per tet) instead of the
                                     whole term, consecutive slabs overlap on different streams, and the host-buffer entry points copy
                                     finished CSR rows to the host while later slabs are still being assembled.
-                                    0 = default (524288 for the device-pointer entry points, 131072 for the host-buffer ones), < 0 = whole term in one slab.  Gather assembly always stages whole terms. */
+                                    0 = default (about a fifth of the function, 512 k .. 2 M elements, for the device-pointer entry points; about a nineteenth, 128 k .. 1 M, for the host-buffer ones), < 0 = whole term in one slab.  Gather assembly always stages whole terms. */
 #define TAD_OPT_PROJECTION 3    /* 0 = low-rank update via selected eigenvectors (default), 1 = full eigendecomposition */
 #define TAD_OPT_LANES 4         /* number of slabs in flight (1..4, default 2) */
 #define TAD_OPT_REPLICATE_GRADIENT 5 /* multi-GPU: 0 = halo-only exchange, every rank ends with the complete g entries of the vertices it

@@ -30,4 +30,26 @@ extern "C" int host_project(int k, double* packed, double eps)
     }
 }
 
+// the in-kernel fallback of the fused small-k element kernel (cyclic Jacobi, Projection.hh project_full_jacobi)
+template <int K>
+static int run_jacobi(double* packed, double eps)
+{
+    return TinyAD::detail::project_full_jacobi<K>([&](int s) { return packed[s]; }, [&](int s, double v) { packed[s] = v; }, eps);
+}
+
+extern "C" int host_project_jacobi(int k, double* packed, double eps)
+{
+    switch (k)
+    {
+    case 1: return run_jacobi<1>(packed, eps);
+    case 2: return run_jacobi<2>(packed, eps);
+    case 3: return run_jacobi<3>(packed, eps);
+    case 4: return run_jacobi<4>(packed, eps);
+    case 5: return run_jacobi<5>(packed, eps);
+    case 6: return run_jacobi<6>(packed, eps);
+    case 8: return run_jacobi<8>(packed, eps);
+    default: return -1;
+    }
+}
+
 extern "C" int host_seq_index(int k, int i, int j) { return TinyAD::detail::hess_seq_index(k, i, j); }

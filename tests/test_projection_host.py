@@ -23,6 +23,7 @@ def hostlib():
                         "-o", so, src], check=True)
     L = ctypes.CDLL(so)
     L.host_project.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
+    L.host_project_jacobi.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
     return L
 
 
@@ -102,6 +103,23 @@ def test_projection_host(hostlib, k, eps):
         assert (code == 0) == (ocode == 0)
         assert np.abs(got - ora).max() / scale <= 5e-12
     assert n_fallback <= len(mats) // 20, n_fallback
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 8])
+@pytest.mark.parametrize("eps", [1e-9, -1.0, 0.0])
+def test_jacobi_fallback_host(hostlib, k, eps):
+    """project_full_jacobi (the in-kernel full solver of the fused small-k element kernel): H + sum (clamp(l) - l) v v^T."""
+    rng = np.random.default_rng(2000 + k)
+    for idx, A in enumerate(matrices(k, rng)):
+        p = pack(hostlib, A)
+        code = hostlib.host_project_jacobi(k, p.ctypes.data, eps)
+        assert code in (1, 2), (k, idx, code)
+        got = unpack(hostlib, p, k)
+        ref = reference_projection(A, eps)
+        scale = max(np.abs(A).max(), abs(eps), 1e-300)
+        assert np.abs(got - ref).max() / scale <= 5e-12, (k, idx, code)
+        if code == 1:
+            assert np.array_equal(got, A)
 
 
 def test_projection_host_element_hessians(hostlib):

@@ -68,7 +68,7 @@ def build(force=False, verbose=False):
     common = os.path.join(HERE, "csrc", "rt_common.cuh")
     proj_deps = [common, os.path.join(inc, "Scalar.hh"), os.path.join(inc, "Detail", "HessLayout.hh"), os.path.join(inc, "Detail", "Projection.hh")]
     rt_units = [("runtime.o", "runtime.cu", proj_deps, []), ("newton.o", "newton.cu", [], []), ("comm.o", "comm.cu", [common], [])]
-    rt_units += [(f"projection{p}.o", "projection.cu", proj_deps, [f"-DTAD_PROJ_PART={p}"]) for p in range(4)]
+    rt_units += [(f"projection{p}.o", "projection.cu", proj_deps, [f"-DTAD_PROJ_PART={p}"]) for p in range(6)]
     rt_units += [(f"assembly{p}.o", "assembly.cu", proj_deps, [f"-DTAD_ASM_PART={p}"]) for p in range(3)]
     rt_objs, relink_runtime = [], not os.path.exists(RUNTIME_SO)
     for obj, cu, deps, defs in rt_units:

@@ -1,5 +1,5 @@
 // tinyad_b200 runtime -- batched PSD projection (Utils/HessianProjection.hh:23-101).  Compiled once per group of K
-// (-DTAD_PROJ_PART=0..3) so that the heavy instantiations build in parallel; the run-time dispatch lives in runtime.cu.
+// (-DTAD_PROJ_PART=0..5) so that the heavy instantiations build in parallel; the run-time dispatch lives in runtime.cu.
 #include "rt_common.cuh"
 
 #ifndef TAD_PROJ_PART
@@ -487,8 +487,12 @@ TAD_INST(1) TAD_INST(2) TAD_INST(3) TAD_INST(4) TAD_INST(5) TAD_INST(6)
 TAD_INST(7) TAD_INST(8) TAD_INST(9) TAD_INST(10)
 #elif TAD_PROJ_PART == 2
 TAD_INST(12)
+#elif TAD_PROJ_PART == 3
+TAD_INST(15)
+#elif TAD_PROJ_PART == 4
+TAD_INST(16)
 #else
-TAD_INST(15) TAD_INST(16) TAD_INST(18)
+TAD_INST(18)
 #endif
 #undef TAD_INST
 

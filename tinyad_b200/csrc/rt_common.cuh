@@ -120,6 +120,7 @@ struct Term
     void* user = nullptr;
     void (*user_free)(void*) = nullptr;
     bool dedup = false;
+    int fused = -1;               // TAD_MODE_SECOND_FUSED: -1 not tried yet, 0 the launcher has no such kernel, 1 available
     DevBuf<int64_t> elem_handles;
     bool has_handles = false;
     DevBuf<int32_t> rec_handles;  // [N][stride]

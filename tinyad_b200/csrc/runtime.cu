@@ -900,16 +900,24 @@ __global__ void __launch_bounds__(256) slab_min_vertex(const int32_t* __restrict
     if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
-// Default slab sizes (C2, one B200, sweep in profiles/r02_slab_sweep.txt): a slab costs ~0.1-0.2 ms of launch gaps and partial
-// waves, so the device-resident path uses large slabs on two lanes (a little faster than one slab per term, and memory-bounded),
-// while the host-buffer path trades some of that for a finer-grained overlap of the D2H copies with the assembly.
-constexpr int64_t kDefaultChunkDevice = 524288, kDefaultChunkHost = 131072;
+// Default slab sizes (one B200; sweeps in profiles/r02_slab_sweep.txt for C2 and profiles/r02c_sweep_c5.txt for C5): a slab costs
+// ~0.1-0.2 ms of launch gaps and partial waves, so the device-resident path uses few large slabs on two lanes (about a fifth of the
+// function, 512 k .. 2 M elements: as fast as one slab per term, but memory-bounded: 2.3 KB of staging + scratch per tet and lane),
+// while the host-buffer path trades some of that for a finer-grained overlap of the D2H copies with the assembly (about a
+// nineteenth of the function, 128 k .. 1 M elements: C2 131072, C5 ~557 k).
+int64_t default_chunk(tad_function f, bool host_path)
+{
+    const int64_t n = std::max<int64_t>(f->n_elements, 1);
+    auto round_up = [](int64_t v, int64_t q) { return (v + q - 1) / q * q; };
+    if (host_path) return std::min<int64_t>(1048576, std::max<int64_t>(131072, round_up(n / 19, 32768)));
+    return std::min<int64_t>(2097152, std::max<int64_t>(524288, round_up(n / 5, 65536)));
+}
 
 int64_t effective_chunk(tad_function f, bool whole_terms, bool host_path)
 {
     if (whole_terms || f->chunk < 0) return -1;
     static const int64_t env_chunk = [] { const char* e = getenv("TAD_CHUNK_ELEMENTS"); return e ? (int64_t)atoll(e) : (int64_t)0; }();
-    int64_t c = f->chunk > 0 ? f->chunk : (env_chunk != 0 ? env_chunk : (host_path ? kDefaultChunkHost : kDefaultChunkDevice));
+    int64_t c = f->chunk > 0 ? f->chunk : (env_chunk != 0 ? env_chunk : default_chunk(f, host_path));
     if (c < 0) return -1;
     return ((c + 255) / 256) * 256;  // multiples of 256: the partial sums of f do not depend on the slab size
 }
@@ -1085,10 +1093,34 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         cudaStream_t ls = L.stream;
         const int64_t sstride = ((sl.n + 31) / 32) * 32;
         DevBuf<double>& stage = gather ? t.stage : L.stage;
-        TAD_CUDA(stage.ensure(stage_doubles(t, mode, sstride)));
+        static const bool fused_enabled = [] { const char* e = getenv("TAD_FUSED_SMALL_K"); return !e || atoi(e) != 0; }();
+        const bool try_fused = mode == TAD_MODE_SECOND && !gather && t.M == 0 && t.fused != 0 && fused_enabled && !(project && f->projection_full) &&
+                               t.blockbase.p != nullptr;
+        // a term known to run fused stages nothing but its values
+        TAD_CUDA(stage.ensure(stage_doubles(t, (try_fused && t.fused == 1) ? TAD_MODE_PASSIVE : mode, sstride)));
         tad_launch_args a;
         fill_launch_args(f, t, mode, x, stage.p, sl.e_begin, sl.n, sstride, ls, a);
         if (f->timing) cudaEventRecord(L.tev[0], ls);
+        // few variables per element (Double<6> triangles ...): evaluation, projection and assembly in ONE kernel of the user's
+        // translation unit, nothing staged but the values (TAD_MODE_SECOND_FUSED); launchers without such a kernel decline once
+        bool fused_done = false;
+        if (try_fused)
+        {
+            tad_launch_args af = a;
+            af.mode = TAD_MODE_SECOND_FUSED;
+            af.blockbase = t.blockbase.p;
+            af.rstride = t.rstride.p;
+            af.g = g;
+            af.H_values = Hv;
+            af.project = project ? 1 : 0;
+            af.eps = eps;
+            af.counts = project ? L.counts.p : nullptr;
+            const int s = t.launch(t.user, &af);
+            if (s == TAD_OK) { fused_done = true; t.fused = 1; }
+            else if (s == TAD_NOT_SUPPORTED && t.fused < 0) t.fused = 0;
+            else return fail(s, "element kernel launch failed");
+        }
+        if (!fused_done)
         {
             const int s = t.launch(t.user, &a);
             if (s != TAD_OK) return fail(s, "element kernel launch failed");
@@ -1097,9 +1129,9 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         count_launch();
         reduce_stage1<false><<<(unsigned)((sl.n + 255) / 256), 256, 0, ls>>>(a.val, sl.n, sstride, 1, f->fpart.p + part_off[(size_t)sl.term] + sl.e_begin / 256);
         // atomic mode + fast projection: the last projection phase (low-rank update) is fused with the scatter
-        const bool fuse = mode == TAD_MODE_SECOND && project && !gather && !f->projection_full && fused_c_assemble_supported(f->d, t.N);
+        const bool fuse = !fused_done && mode == TAD_MODE_SECOND && project && !gather && !f->projection_full && fused_c_assemble_supported(f->d, t.N);
         ProjScratch fused_sc;
-        if (mode == TAD_MODE_SECOND && project)
+        if (mode == TAD_MODE_SECOND && project && !fused_done)
         {
             TAD_CUDA(L.proj_list.ensure((size_t)sstride));
             TAD_CUDA(L.proj_codes.ensure((size_t)sstride));
@@ -1113,7 +1145,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
                             t.rstride.p ? t.rstride.p + sl.e_begin : nullptr, t.stride};
         if (fuse)
             TAD_TRY(c_assemble(f->d, t.N, maps, a.grad, a.hess, sl.n, sstride, eps, fused_sc, g, Hv, f->err.p, L.counts.p, &L.side, ls));
-        else if (mode >= TAD_MODE_FIRST && !gather)
+        else if (mode >= TAD_MODE_FIRST && !gather && !fused_done)
             TAD_TRY(assemble_atomic(f->d, t.N, maps, a.grad, mode == TAD_MODE_SECOND ? a.hess : nullptr, sl.n, sstride, g, Hv, f->err.p, ls));
         TAD_CUDA(cudaEventRecord(f->slab_events[(size_t)q], ls));
         if (f->timing)

@@ -259,9 +259,10 @@ TINYAD_HD TINYAD_INLINE double rcp_fast(double x)
 }
 
 // The QL iteration as a resumable state machine: ql_init loads and scales T, ql_advance runs ONE iteration of the loop described
-// above (at most one QL step, then the deflation test).  proj_eigenvalues drives it for one matrix per thread; the warp-queue kernel
-// (runtime: project_kernel_b1) lets a lane whose matrix is finished pick up the next one of its warp's chunk, so that lanes needing
-// different numbers of steps do not idle.
+// above (at most one QL step, then the deflation test).  proj_eigenvalues drives it for one matrix per thread.  (Two multi-matrix
+// drivers were measured and dropped, profiles/README.md: lanes that pick up the next matrix of a per-warp queue on demand, and
+// static per-lane lists with register prefetch.  Both were slower than one matrix per thread: the kernel is bound by the latency
+// of its dependent FP64 chains, which many short-lived warps hide better than few long-lived ones.)
 template <int K>
 struct QlState
 {
@@ -789,6 +790,85 @@ TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const doubl
     return PROJ_REBUILT;
 }
 
+
+// Full eigendecomposition of one packed matrix by cyclic Jacobi rotations, all in thread-local arrays: the in-kernel fallback of
+// the fused small-k element kernel (TinyAD/Kernels.cuh) for the few elements per million whose inverse iteration does not converge
+// (code PROJ_FALLBACK of project_element).  Any backward-stable solver gives the same projected matrix to O(macheps |H|).  Like the
+// fast path, H is rebuilt as H + sum_j (clamp(l_j) - l_j) v_j v_j^T over the moved eigenpairs only, which leaves H bit-unchanged
+// when nothing moves (HessianProjection.hh:94-95).  Returns PROJ_UNCHANGED or PROJ_REBUILT.
+template <int K, class LoadFn, class StoreFn>
+TINYAD_HD inline int project_full_jacobi(LoadFn&& load, StoreFn&& store, const double eps)
+{
+    constexpr int H = K * (K + 1) / 2;
+    double A[K][K], V[K][K];
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+    double h[H];
+    static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+        constexpr int s = decltype(sc)::value;
+        constexpr int r = hess_seq_rc(K, s).row, c = hess_seq_rc(K, s).col;
+        h[s] = load(s);
+        A[r][c] = h[s];
+        A[c][r] = h[s];
+    });
+    double nrm = 0.0;
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) nrm += A[i][j] * A[i][j];
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        double off = 0.0;
+        for (int p = 0; p < K; ++p)
+            for (int q = p + 1; q < K; ++q) off += A[p][q] * A[p][q];
+        if (off <= 1e-32 * nrm) break;
+        for (int p = 0; p < K - 1; ++p)
+            for (int q = p + 1; q < K; ++q)
+            {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int r = 0; r < K; ++r)
+                {
+                    const double arp = A[r][p], arq = A[r][q];
+                    A[r][p] = c * arp - sn * arq;
+                    A[r][q] = sn * arp + c * arq;
+                }
+                for (int r = 0; r < K; ++r)
+                {
+                    const double apr = A[p][r], aqr = A[q][r];
+                    A[p][r] = c * apr - sn * aqr;
+                    A[q][r] = sn * apr + c * aqr;
+                }
+                for (int r = 0; r < K; ++r)
+                {
+                    const double vrp = V[r][p], vrq = V[r][q];
+                    V[r][p] = c * vrp - sn * vrq;
+                    V[r][q] = sn * vrp + c * vrq;
+                }
+            }
+    }
+    bool moved = false;
+    for (int j = 0; j < K; ++j)
+    {
+        const double lam = A[j][j];
+        double w = 0.0;
+        if (eps < 0.0) { if (lam < 0.0) w = -2.0 * lam; }      // |l| - l
+        else if (lam < eps) w = eps - lam;
+        if ((eps < 0.0 && lam < 0.0) || (eps >= 0.0 && lam < eps))
+        {
+            moved = true;
+            static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+                constexpr int s = decltype(sc)::value;
+                constexpr int r = hess_seq_rc(K, s).row, c = hess_seq_rc(K, s).col;
+                h[s] = fma(w * V[r][j], V[c][j], h[s]);
+            });
+        }
+    }
+    if (!moved) return PROJ_UNCHANGED;
+    static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE { constexpr int s = decltype(sc)::value; store(s, h[s]); });
+    return PROJ_REBUILT;
+}
 
 }  // namespace detail
 }  // namespace TinyAD

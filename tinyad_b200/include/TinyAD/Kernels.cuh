@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include <TinyAD/Detail/Projection.hh>
 #include <TinyAD/Element.hh>
 #include <tinyad_b200.h>
 
@@ -143,6 +144,79 @@ __device__ TINYAD_INLINE void second_order_part(const Functor& f, const tad_laun
     });
 }
 
+// TAD_MODE_SECOND_FUSED: evaluation, PSD projection and assembly of one element in one thread, nothing staged but the value.
+// For k <= TINYAD_FUSED_MAX_K the value, the gradient and the packed Hessian (1 + k + k(k+1)/2 doubles: 28 for Double<6>) live in
+// registers from the functor call to the FP64 atomics; the projection is the same three-phase routine the staged path runs
+// (Detail/Projection.hh project_element: tridiagonalise, eigenvalues, inverse iteration for the moved eigenpairs, low-rank update),
+// so both paths give the same values, with a thread-local cyclic Jacobi for the few elements per million it hands back.
+// Replaces ScalarObjectiveTerm.hh:242-277 (element evaluation, project_positive_definite, accumulation) in one pass.
+#ifndef TINYAD_FUSED_MAX_K
+#define TINYAD_FUSED_MAX_K 6
+#endif
+#ifndef TINYAD_FUSED_MIN_BLOCKS
+#define TINYAD_FUSED_MIN_BLOCKS 2   // blocks of 128 threads per SM the register allocation aims at
+#endif
+template <class Functor, int d, int N, bool Dedup>
+__global__ void __launch_bounds__(128, TINYAD_FUSED_MIN_BLOCKS) second_order_fused_kernel(Functor f, tad_launch_args a)
+{
+    constexpr int k = d * N;
+    using T = Scalar<k, true, 1, 0>;
+    constexpr int nh = T::nh;
+    int64_t si;
+    if (!slab_index(a, si)) return;
+    const int64_t e = a.e_begin + si;
+    Element<d, N, 0, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags, rec_column(a, e), a.rec_stride);
+    const T r = f(el);
+    a.val[si] = r.val;
+    if (a.rec_counts) el.check_recorded_count(a.rec_counts[e]);
+    double h[nh];
+    static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int s = decltype(ic)::value; h[s] = r.hess[s]; });
+    bool finite = true;
+    static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int s = decltype(ic)::value; finite = finite && isfinite(h[s]); });
+    if (a.project && finite)
+    {
+        int code = project_element<k>([&](int s) { return h[s]; }, [&](int s, double v) { h[s] = v; }, a.eps);
+        if (code == PROJ_FALLBACK)
+        {
+            code = project_full_jacobi<k>([&](int s) { return h[s]; }, [&](int s, double v) { h[s] = v; }, a.eps);
+            if (a.counts) atomicAdd(&a.counts[3], 1ull);
+        }
+        if (a.counts && code != PROJ_DOMINANT) atomicAdd(&a.counts[0], 1ull);
+        if (a.counts && code == PROJ_REBUILT) atomicAdd(&a.counts[1], 1ull);
+    }
+    // assembly: FP64 atomics on g and the fixed CSR values through the block scatter map
+    const int32_t* rec = a.rec_handles + e;
+    static_for<N>([&](auto bc) TINYAD_LAMBDA_INLINE {
+        constexpr int bi = decltype(bc)::value;
+        const int32_t vi = rec[(int64_t)bi * a.rec_stride];
+        if (vi >= 0)
+            static_for<d>([&](auto ac) TINYAD_LAMBDA_INLINE {
+                constexpr int c = decltype(ac)::value;
+                const double v = r.grad[d * bi + c];
+                finite = finite && isfinite(v);
+                atomicAdd(&a.g[(int64_t)d * vi + c], v);
+            });
+    });
+    const int32_t* bb = a.blockbase + e;
+    const int32_t* rsp = a.rstride + e;
+    static_for<N>([&](auto bc) TINYAD_LAMBDA_INLINE {
+        constexpr int bi = decltype(bc)::value;
+        const int32_t rs = rsp[(int64_t)bi * a.rec_stride];
+        static_for<N>([&](auto cc) TINYAD_LAMBDA_INLINE {
+            constexpr int bj = decltype(cc)::value;
+            const int32_t base = bb[(int64_t)(bi * N + bj) * a.rec_stride];
+            if (base >= 0)
+                static_for<d * d>([&](auto qc) TINYAD_LAMBDA_INLINE {
+                    constexpr int q = decltype(qc)::value, ra = q / d, cb = q % d;
+                    const double v = h[hess_seq_index(k, d * bi + ra, d * bj + cb)];
+                    finite = finite && isfinite(v);
+                    atomicAdd(&a.H_values[(int64_t)base + (int64_t)ra * rs + cb], v);
+                });
+        });
+    });
+    if (!finite) atomicOr(a.error_flags, 1 << TAD_NONFINITE_DERIVATIVE);
+}
+
 inline int check_launch();
 
 // One kernel per Hessian part: all threads of a launch run the same instantiation
@@ -204,6 +278,17 @@ struct TermLauncher
         cudaStream_t st = static_cast<cudaStream_t>(a->stream);
         const int64_t n = a->n_elements;
         const unsigned g128 = (unsigned)((n + 127) / 128);
+        if (a->mode == TAD_MODE_SECOND_FUSED)
+        {
+            if constexpr (M == 0 && NP == 1 && k <= TINYAD_FUSED_MAX_K)
+            {
+                if (a->launch_counter) *a->launch_counter += 1;
+                detail::second_order_fused_kernel<Functor, d, N, Dedup><<<g128, 128, 0, st>>>(self->f, *a);
+                return detail::check_launch();
+            }
+            else
+                return TAD_NOT_SUPPORTED;   // the runtime falls back to TAD_MODE_SECOND + its projection / assembly kernels
+        }
         if (a->launch_counter) *a->launch_counter += (a->mode == TAD_MODE_SECOND) ? NP : 1;
         switch (a->mode)
         {

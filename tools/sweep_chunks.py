@@ -20,7 +20,8 @@ H = torch.empty(nnz, dtype=torch.float64, device="cuda")
 xh = torch.from_numpy(x.copy()).pin_memory()
 gh = torch.empty(fn.n_vars, dtype=torch.float64).pin_memory()
 Hh = torch.empty(nnz, dtype=torch.float64).pin_memory()
-configs = [(-1, 1), (524288, 1), (524288, 2), (262144, 1), (262144, 2), (262144, 3), (131072, 1), (131072, 2), (131072, 3), (65536, 2), (65536, 4)]
+reps = 20 if n <= 60 else 8
+configs = eval("[" + sys.argv[2] + "]") if len(sys.argv) > 2 else [(-1, 1), (524288, 1), (524288, 2), (262144, 1), (262144, 2), (262144, 3), (131072, 1), (131072, 2), (131072, 3), (65536, 2), (65536, 4)]
 for chunk, lanes in configs:
     fn.set_option(tad.OPT_CHUNK_ELEMENTS, chunk)
     fn.set_option(tad.OPT_LANES, lanes)
@@ -28,14 +29,14 @@ for chunk, lanes in configs:
         fn.eval_with_hessian_proj(xd, g, H)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(20):
+    for _ in range(reps):
         fn.eval_with_hessian_proj(xd, g, H)
     torch.cuda.synchronize()
-    dev = (time.perf_counter() - t0) / 20
+    dev = (time.perf_counter() - t0) / reps
     for _ in range(2):
         fn.eval_with_hessian_proj_host(xh.numpy(), out_g=gh.numpy(), out_H=Hh.numpy())
     t0 = time.perf_counter()
-    for _ in range(10):
+    for _ in range(max(3, reps // 2)):
         fn.eval_with_hessian_proj_host(xh.numpy(), out_g=gh.numpy(), out_H=Hh.numpy())
-    e2e = (time.perf_counter() - t0) / 10
+    e2e = (time.perf_counter() - t0) / max(3, reps // 2)
     print(f"chunk {chunk:8d} lanes {lanes}: device {dev*1e3:7.3f} ms  e2e {e2e*1e3:7.3f} ms", flush=True)
