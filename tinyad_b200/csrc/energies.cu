@@ -254,6 +254,30 @@ int tadx_selftest(int device)
             try { newton_direction(gq, Hneg, solver); } catch (const std::runtime_error&) { threw = true; }
             if (!threw) return 19;
         }
+        // mesh-library handle types (Support/Common.hh; reference Support/{OpenMesh,PMP,Polymesh,GeometryCentral}.hh): handles with
+        // .idx(), .idx.value or .getIndex() enumerate variables and elements on the host; the device functor sees the integer
+        {
+            struct IdxHandle { int i; int idx() const { return i; } };                       // OpenMesh::BaseHandle / pmp::Handle
+            struct PmIndex { int value; };
+            struct PmHandle { PmIndex idx; };                                               // pm::primitive_handle<tag>
+            struct GcHandle { size_t i; size_t getIndex() const { return i; } };             // geometrycentral::Element<T, M>
+            if (idx_from_handle(IdxHandle{3}) != 3 || idx_from_handle(PmHandle{{4}}) != 4 || idx_from_handle(GcHandle{5}) != 5 ||
+                idx_from_handle(7) != 7 || idx_from_handle((int64_t)8) != 8) return 20;
+            threw = false;
+            try { struct Opaque {}; idx_from_handle(Opaque{}); } catch (const std::runtime_error&) { threw = true; }
+            if (!threw) return 21;
+            std::vector<IdxHandle> vertices = {{0}};
+            std::vector<GcHandle> faces = {{0}};
+            auto fm = scalar_function<2>(vertices, es);
+            fm.add_elements<1>(faces, Quadratic2D{C, D});
+            if (fm.eval(x) != 12.0) return 22;
+            auto xm = fm.x_from_data([](IdxHandle v) { return std::vector<double>{1.0 + v.idx(), 2.0}; });
+            if (xm.size() != 2 || xm[0] != 1.0 || xm[1] != 2.0) return 23;
+            std::vector<IdxHandle> sparse_ids = {{0}, {2}};                                // not compact -> rejected like integer handles
+            threw = false;
+            try { auto bad = scalar_function<2>(sparse_ids, es); } catch (const std::runtime_error&) { threw = true; }
+            if (!threw) return 24;
+        }
         return 0;
     }
     catch (const std::exception& e)

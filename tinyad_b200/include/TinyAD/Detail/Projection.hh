@@ -258,144 +258,114 @@ TINYAD_HD TINYAD_INLINE double rcp_fast(double x)
 #endif
 }
 
-// The QL iteration as a resumable state machine: ql_init loads and scales T, ql_advance runs ONE iteration of the loop described
-// above (at most one QL step, then the deflation test).  proj_eigenvalues drives it for one matrix per thread.  (Two multi-matrix
-// drivers were measured and dropped, profiles/README.md: lanes that pick up the next matrix of a per-warp queue on demand, and
-// static per-lane lists with register prefetch.  Both were slower than one matrix per thread: the kernel is bound by the latency
-// of its dependent FP64 chains, which many short-lived warps hide better than few long-lived ones.)
-template <int K>
-struct QlState
-{
-    double lam[K], ee[K];
-    double f, thr, onenrm;
-    int done, steps;
-};
-
-// Returns false for NaN / Inf input (PROJ_FALLBACK: the caller's finite check reports it).
-template <int K, class LoadRFn>
-TINYAD_HD TINYAD_INLINE bool ql_init(QlState<K>& q, LoadRFn&& load_r)
+// (Two multi-matrix drivers of this iteration were measured and dropped, profiles/README.md: lanes that pick up the next matrix of a
+// per-warp queue on demand, and static per-lane lists with register prefetch.  Both were slower than one matrix per thread -- the
+// kernel is bound by the latency of its dependent FP64 chains, which many short-lived warps hide better than few long-lived ones --
+// and the resumable-state form they needed cost 18 registers (80 -> 98) and 13 % of this kernel's time.)
+template <int K, class LoadRFn, class StoreRFn>
+TINYAD_HD inline int proj_eigenvalues(LoadRFn&& load_r, StoreRFn&& store_r)
 {
     using L = ProjLayout<K>;
     constexpr double macheps = 2.220446049250313e-16;
+    double lam[K], ee[K];
     double onenrm = 0.0;
     static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int i = decltype(ic)::value;
-        q.lam[i] = load_r(L::off_d + i);
-        if constexpr (i + 1 < K) q.ee[i] = load_r(L::off_e + i);
-        else q.ee[i] = 0.0;
+        lam[i] = load_r(L::off_d + i);
+        if constexpr (i + 1 < K) ee[i] = load_r(L::off_e + i);
+        else ee[i] = 0.0;
     });
     static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int i = decltype(ic)::value;
-        double rowsum = fabs(q.lam[i]) + fabs(q.ee[i]);
-        if constexpr (i > 0) rowsum += fabs(q.ee[i - 1]);
+        double rowsum = fabs(lam[i]) + fabs(ee[i]);
+        if constexpr (i > 0) rowsum += fabs(ee[i - 1]);
         onenrm = fmax(onenrm, rowsum);
     });
-    q.onenrm = onenrm;
-    q.f = 0.0;
-    q.done = 0;
-    q.steps = 0;
-    q.thr = 0.0;
-    if (!(onenrm == onenrm) || onenrm > 1e300) return false;
+    if (!(onenrm == onenrm) || onenrm > 1e300) return PROJ_FALLBACK;  // NaN / Inf input: the caller's finite check reports it
     const double inv_nrm = onenrm > 0.0 ? 1.0 / onenrm : 0.0;
     double tn = 0.0;
     static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
         constexpr int i = decltype(ic)::value;
-        q.lam[i] *= inv_nrm;
-        q.ee[i] *= inv_nrm;
-        tn = fmax(tn, fabs(q.lam[i]) + fabs(q.ee[i]));
+        lam[i] *= inv_nrm;
+        ee[i] *= inv_nrm;
+        tn = fmax(tn, fabs(lam[i]) + fabs(ee[i]));
     });
-    q.thr = macheps * tn;
-    return true;
-}
-
-// One iteration.  Returns 0: continue, 1: all K eigenvalues stored (PROJ_UNCHANGED), 2: no convergence (PROJ_FALLBACK).
-template <int K, class StoreRFn>
-TINYAD_HD TINYAD_INLINE int ql_advance(QlState<K>& q, StoreRFn&& store_r)
-{
-    using L = ProjLayout<K>;
-    double(&lam)[K] = q.lam;
-    double(&ee)[K] = q.ee;
-    const double thr = q.thr;
-    // m = first index with a negligible sub-diagonal entry (e[K-1] = 0 always)
-    int m = K - 1;
-    static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
-        constexpr int i = K - 2 - decltype(ic)::value;  // K-2 down to 0: the smallest index wins
-        if (fabs(ee[i]) <= thr) m = i;
-    });
-    if constexpr (K > 1)
+    const double thr = macheps * tn;
+    double f = 0.0;
+    int done = 0, steps = 0;
+    while (done < K)
     {
-        if (m > 0)
+        // m = first index with a negligible sub-diagonal entry (e[K-1] = 0 always)
+        int m = K - 1;
+        static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = K - 2 - decltype(ic)::value;  // K-2 down to 0: the smallest index wins
+            if (fabs(ee[i]) <= thr) m = i;
+        });
+        if constexpr (K > 1)
         {
-            // one QL step on the block [0, m], shift from the leading 2 x 2 block
-            if (++q.steps > 40 * K) return 2;
-            const double e_l = ee[0];
-            double g = lam[0];
-            double p = (lam[1] - g) * rcp_fast(2.0 * e_l);
-            const double pp1 = fma(p, p, 1.0);
-            double r = pp1 * rsqrt_fast(pp1);
-            if (p < 0) r = -r;
-            const double qq = p + r;  // |qq| >= 1
-            const double qinv = rcp_fast(qq);
-            const double dl = e_l * qinv;
-            lam[0] = dl;
-            lam[1] = e_l * qq;
-            double h = g - dl;
-            static_for<(K > 2 ? K - 2 : 0)>([&](auto ic) TINYAD_LAMBDA_INLINE { lam[2 + decltype(ic)::value] -= h; });
-            q.f += h;
-            p = lam[K - 1];
-            static_for<(K > 2 ? K - 2 : 0)>([&](auto ic) TINYAD_LAMBDA_INLINE {
-                constexpr int i = 1 + decltype(ic)::value;  // 1 .. K-2
-                if (m == i) p = lam[i];
-            });
-            double c = 1.0, c3 = 1.0;  // c3: c after rotation 2 (1 if it does not run)
-            const double el1 = ee[1];
-            double s = 0.0, s2 = 0.0;  // s2: s after rotation 1 (0 if it does not run)
+            if (m > 0)
+            {
+                // one QL step on the block [0, m], shift from the leading 2 x 2 block
+                if (++steps > 40 * K) return PROJ_FALLBACK;
+                const double e_l = ee[0];
+                double g = lam[0];
+                double p = (lam[1] - g) * rcp_fast(2.0 * e_l);
+                const double pp1 = fma(p, p, 1.0);
+                double r = pp1 * rsqrt_fast(pp1);
+                if (p < 0) r = -r;
+                const double q = p + r;  // |q| >= 1
+                const double qinv = rcp_fast(q);
+                const double dl = e_l * qinv;
+                lam[0] = dl;
+                lam[1] = e_l * q;
+                double h = g - dl;
+                static_for<(K > 2 ? K - 2 : 0)>([&](auto ic) TINYAD_LAMBDA_INLINE { lam[2 + decltype(ic)::value] -= h; });
+                f += h;
+                p = lam[K - 1];
+                static_for<(K > 2 ? K - 2 : 0)>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = 1 + decltype(ic)::value;  // 1 .. K-2
+                    if (m == i) p = lam[i];
+                });
+                double c = 1.0, c3 = 1.0;  // c3: c after rotation 2 (1 if it does not run)
+                const double el1 = ee[1];
+                double s = 0.0, s2 = 0.0;  // s2: s after rotation 1 (0 if it does not run)
+                static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = K - 2 - decltype(ic)::value;  // K-2 down to 0
+                    if (i < m)
+                    {
+                        const double ei = ee[i], di = lam[i];
+                        g = c * ei;
+                        h = c * p;
+                        const double t = fma(p, p, ei * ei);
+                        const double rinv = rsqrt_fast(t);
+                        ee[i + 1] = s * (t * rinv);
+                        s = ei * rinv;
+                        c = p * rinv;
+                        p = c * di - s * g;
+                        lam[i + 1] = h + s * (c * g + s * di);
+                        if constexpr (i == 2) c3 = c;
+                        if constexpr (i == 1) s2 = s;
+                    }
+                });
+                p = -s * s2 * c3 * el1 * qinv;  // = -s s2 c3 el1 e_l / lam[1]
+                ee[0] = s * p;
+                lam[0] = c * p;
+            }
+        }
+        if (fabs(ee[0]) <= thr)
+        {
+            // deflate: eigenvalue found; shift the arrays so that the remaining block starts at 0 again
+            store_r(L::off_lam + done, (lam[0] + f) * onenrm);
+            ++done;
             static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
-                constexpr int i = K - 2 - decltype(ic)::value;  // K-2 down to 0
-                if (i < m)
-                {
-                    const double ei = ee[i], di = lam[i];
-                    g = c * ei;
-                    h = c * p;
-                    const double t = fma(p, p, ei * ei);
-                    const double rinv = rsqrt_fast(t);
-                    ee[i + 1] = s * (t * rinv);
-                    s = ei * rinv;
-                    c = p * rinv;
-                    p = c * di - s * g;
-                    lam[i + 1] = h + s * (c * g + s * di);
-                    if constexpr (i == 2) c3 = c;
-                    if constexpr (i == 1) s2 = s;
-                }
+                constexpr int i = decltype(ic)::value;
+                lam[i] = lam[i + 1];
+                ee[i] = ee[i + 1];
             });
-            p = -s * s2 * c3 * el1 * qinv;  // = -s s2 c3 el1 e_l / lam[1]
-            ee[0] = s * p;
-            lam[0] = c * p;
+            ee[K - 1] = 0.0;
         }
     }
-    if (fabs(ee[0]) <= thr)
-    {
-        // deflate: eigenvalue found; shift the arrays so that the remaining block starts at 0 again
-        store_r(L::off_lam + q.done, (lam[0] + q.f) * q.onenrm);
-        ++q.done;
-        static_for<K - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
-            constexpr int i = decltype(ic)::value;
-            lam[i] = lam[i + 1];
-            ee[i] = ee[i + 1];
-        });
-        ee[K - 1] = 0.0;
-    }
-    return q.done < K ? 0 : 1;
-}
-
-template <int K, class LoadRFn, class StoreRFn>
-TINYAD_HD inline int proj_eigenvalues(LoadRFn&& load_r, StoreRFn&& store_r)
-{
-    QlState<K> q;
-    if (!ql_init<K>(q, load_r)) return PROJ_FALLBACK;
-    int st = 0;
-    while ((st = ql_advance<K>(q, store_r)) == 0) {}
-    return st == 1 ? PROJ_UNCHANGED : PROJ_FALLBACK;
+    return PROJ_UNCHANGED;
 }
 
 // Ascending sort of K doubles held in registers: compare-exchange network with compile-time indices (an optimal

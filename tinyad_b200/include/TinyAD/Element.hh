@@ -56,7 +56,7 @@ struct Element
     // (a functor that branches on x before or between its variables() calls) must be reported, not silently mis-assembled.
     TINYAD_HD TINYAD_INLINE Element(int64_t _handle, const double* _x, int64_t _n_handles, int32_t* _err, const int32_t* _rec = nullptr,
                                     int64_t _rec_stride = 0)
-        : handle(_handle), x(_x), n_handles(_n_handles), err(_err), n_used(0), rec(_rec), rec_stride(_rec_stride) {}
+        : handle(_handle), x(_x), n_handles(_n_handles), err(_err), n_used(0), rec(_rec), rec_stride(_rec_stride), mismatch(false) {}
     Element(const Element&) = delete;  // Element.hh:78
 
     TINYAD_HD TINYAD_INLINE VariableVectorType variables(int64_t vh)
@@ -86,7 +86,10 @@ struct Element
             detail::raise(err, TINYAD_ERR_TOO_MANY_VARIABLES);  // Element.hh:237-238
             slot = N - 1;
         }
-        if (rec && (int64_t)rec[slot * rec_stride] != vh) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
+        // compared without a branch and reported once, after the functor (check_recorded_count): a branch here would sit between the
+        // load of the recorded handle and the loads of x, and the GPU does not speculate -- every variables() call then costs two
+        // dependent memory round trips instead of one (measured: +40 % on the first tet kernel)
+        if (rec) mismatch = mismatch || ((int64_t)rec[slot * rec_stride] != vh);
         const double* xv = x + d * vh;
         VariableVectorType v;
         detail::static_for<d>([&](auto ic) TINYAD_LAMBDA_INLINE {
@@ -129,13 +132,14 @@ struct Element
     int n_used;
     const int32_t* rec;
     int64_t rec_stride;
+    bool mismatch;  // some variables() call requested another handle than the recorded one
     int64_t seen[Dedup ? N : 1];
 
-    // after the functor ran: did it request exactly the recorded number of (distinct) handles?
+    // after the functor ran: did it request the recorded handles, and exactly the recorded number of (distinct) handles?
     TINYAD_HD TINYAD_INLINE void check_recorded_count(int32_t recorded) const
     {
         const int want = recorded < 0 ? -recorded - 1 : recorded;  // < 0 marks "a handle was requested more than once"
-        if (Dedup ? (n_used != want) : (recorded >= 0 && n_used != want)) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
+        if (mismatch || (Dedup ? (n_used != want) : (recorded >= 0 && n_used != want))) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
     }
 };
 

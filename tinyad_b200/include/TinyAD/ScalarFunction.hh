@@ -27,7 +27,10 @@
 #include <vector>
 
 #include <TinyAD/Kernels.cuh>
+#include <TinyAD/Support/Common.hh>
 #include <tinyad_b200.h>
+
+#define TINYAD_ScalarFunction_DEFINED
 
 namespace TinyAD
 {
@@ -82,7 +85,7 @@ bool is_identity_range(const Range& r, std::vector<int64_t>& out)
 {
     bool identity = true;
     int64_t i = 0;
-    for (auto h : r) { out.push_back((int64_t)h); identity = identity && ((int64_t)h == i); ++i; }
+    for (auto h : r) { const int64_t idx = idx_from_handle(h); out.push_back(idx); identity = identity && (idx == i); ++i; }
     return identity;
 }
 }  // namespace detail
@@ -102,9 +105,10 @@ struct ScalarFunction
         std::vector<bool> used(variable_handles.size(), false);
         for (auto v : variable_handles)
         {
-            if ((int64_t)v < 0 || (int64_t)v >= (int64_t)variable_handles.size() || used[(size_t)v])
+            const int64_t iv = idx_from_handle(v);
+            if (iv < 0 || iv >= (int64_t)variable_handles.size() || used[(size_t)iv])
                 throw std::runtime_error("[TinyAD-B200] variable indices are not compact");
-            used[(size_t)v] = true;
+            used[(size_t)iv] = true;
         }
         if (variable_handles.empty()) throw std::runtime_error("[TinyAD-B200] no variables");
         detail::check(tad_function_create(variable_dimension, (int64_t)variable_handles.size(), 0, settings.device, &h));
@@ -195,7 +199,7 @@ struct ScalarFunction
         for (auto v : variable_handles)
         {
             const auto user_vec = _read_user_data(v);
-            for (int i = 0; i < variable_dimension; ++i) x[(size_t)(variable_dimension * (int64_t)v + i)] = user_vec[i];
+            for (int i = 0; i < variable_dimension; ++i) x[(size_t)(variable_dimension * idx_from_handle(v) + i)] = user_vec[i];
         }
         for (double xi : x)
             if (!std::isfinite(xi)) throw std::runtime_error("[TinyAD-B200] x_from_data: non-finite entry");
@@ -208,7 +212,7 @@ struct ScalarFunction
         for (auto v : variable_handles)
         {
             Vec<double, variable_dimension> vec;
-            for (int i = 0; i < variable_dimension; ++i) vec[i] = _x[(size_t)(variable_dimension * (int64_t)v + i)];
+            for (int i = 0; i < variable_dimension; ++i) vec[i] = _x[(size_t)(variable_dimension * idx_from_handle(v) + i)];
             _write_user_data(v, vec);
         }
     }

@@ -27,9 +27,10 @@ struct VectorFunction
         std::vector<bool> used(variable_handles.size(), false);
         for (auto v : variable_handles)
         {
-            if ((int64_t)v < 0 || (int64_t)v >= (int64_t)variable_handles.size() || used[(size_t)v])
+            const int64_t iv = idx_from_handle(v);
+            if (iv < 0 || iv >= (int64_t)variable_handles.size() || used[(size_t)iv])
                 throw std::runtime_error("[TinyAD-B200] variable indices are not compact");
-            used[(size_t)v] = true;
+            used[(size_t)iv] = true;
         }
         if (variable_handles.empty()) throw std::runtime_error("[TinyAD-B200] no variables");
         detail::check(tad_function_create(variable_dimension, (int64_t)variable_handles.size(), 1, settings.device, &h));
