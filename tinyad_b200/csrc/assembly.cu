@@ -78,6 +78,19 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
     constexpr int K = D * N;
     constexpr int H = K * (K + 1) / 2;
     const double* hp = hess + e;
+    // The scatter map of the element (N handles, N row strides, N^2 block bases) is loaded FIRST: in the scatter phase below every
+    // block was "load base -> test -> 9 REDs", and with ~210 registers taken by the accumulator the compiler did not hoist those
+    // loads, so their latency was exposed 16 times per tet (ncu: 62 % of the stall samples were long-scoreboard waits on the
+    // instructions consuming them).  Loaded here, their latency hides behind the projection phase C.
+    int32_t m_vi[N], m_rs[N], m_base[N * N];
+#pragma unroll
+    for (int bi = 0; bi < N; ++bi)
+    {
+        m_vi[bi] = rec[(int64_t)bi * mstride + e];
+        m_rs[bi] = rstride[(int64_t)bi * mstride + e];
+#pragma unroll
+        for (int bj = 0; bj < N; ++bj) m_base[bi * N + bj] = blockbase[(int64_t)(bi * N + bj) * mstride + e];
+    }
     double acc[H];
     if (code == TinyAD::detail::PROJ_REBUILT)
     {
@@ -118,7 +131,7 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
 #pragma unroll
     for (int bi = 0; bi < N; ++bi)
     {
-        const int32_t vi = rec[(int64_t)bi * mstride + e];
+        const int32_t vi = m_vi[bi];
         if (vi < 0) continue;
 #pragma unroll
         for (int a = 0; a < D; ++a)
@@ -131,11 +144,11 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
 #pragma unroll
     for (int bi = 0; bi < N; ++bi)
     {
-        const int32_t rs = rstride[(int64_t)bi * mstride + e];
+        const int32_t rs = m_rs[bi];
 #pragma unroll
         for (int bj = 0; bj < N; ++bj)
         {
-            const int32_t base = blockbase[(int64_t)(bi * N + bj) * mstride + e];
+            const int32_t base = m_base[bi * N + bj];
             if (base < 0) continue;
 #pragma unroll
             for (int a = 0; a < D; ++a)

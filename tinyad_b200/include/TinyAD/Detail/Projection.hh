@@ -261,7 +261,9 @@ TINYAD_HD TINYAD_INLINE double rcp_fast(double x)
 // (Two multi-matrix drivers of this iteration were measured and dropped, profiles/README.md: lanes that pick up the next matrix of a
 // per-warp queue on demand, and static per-lane lists with register prefetch.  Both were slower than one matrix per thread -- the
 // kernel is bound by the latency of its dependent FP64 chains, which many short-lived warps hide better than few long-lived ones --
-// and the resumable-state form they needed cost 18 registers (80 -> 98) and 13 % of this kernel's time.)
+// and the resumable-state form they needed cost 18 registers (80 -> 98) and 13 % of this kernel's time.  A third variant with d / e
+// in shared memory and run-time loops (EISPACK tql1 as written: ~32 instead of ~70 instructions per rotation slot, 68 registers) took
+// 2.7 ms instead of 0.54 ms: every rotation then waits for a shared-memory store -> load round trip of the previous one.)
 template <int K, class LoadRFn, class StoreRFn>
 TINYAD_HD inline int proj_eigenvalues(LoadRFn&& load_r, StoreRFn&& store_r)
 {
