@@ -109,7 +109,7 @@ typedef struct tad_comm_s* tad_comm;   /* one rank's view of the group of GPUs t
                                     by slab, so staging + projection scratch are bounded by `lanes` slabs (2.3 KB per tet) instead of the
                                     whole term, consecutive slabs overlap on different streams, and the host-buffer entry points copy
                                     finished CSR rows to the host while later slabs are still being assembled.
-                                    0 = default (about a fifth of the function, 512 k .. 2 M elements, for the device-pointer entry points; about a nineteenth, 128 k .. 1 M, for the host-buffer ones), < 0 = whole term in one slab.  Gather assembly always stages whole terms. */
+                                    0 = default (half of the function, 512 k .. 2 M elements, for the device-pointer entry points; about a nineteenth, 128 k .. 1 M, for the host-buffer ones), < 0 = whole term in one slab.  Gather assembly always stages whole terms. */
 #define TAD_OPT_PROJECTION 3    /* 0 = low-rank update via selected eigenvectors (default), 1 = full eigendecomposition */
 #define TAD_OPT_LANES 4         /* number of slabs in flight (1..4, default 2) */
 #define TAD_OPT_REPLICATE_GRADIENT 5 /* multi-GPU: 0 = halo-only exchange, every rank ends with the complete g entries of the vertices it

@@ -24,6 +24,16 @@
 using namespace TinyAD;
 using namespace tadx;
 
+// tests/HandleTypeTest.cc:8-42: a user-defined handle type becomes usable by overloading idx_from_handle (found by
+// argument-dependent lookup in the handle's namespace, or declared in namespace TinyAD before the facade is included)
+namespace tadx
+{
+struct CustomVariableHandle { int idx = -1; };
+struct CustomElementHandle { int idx = -1; };
+inline int64_t idx_from_handle(const CustomVariableHandle& vh) { return vh.idx; }
+inline int64_t idx_from_handle(const CustomElementHandle& eh) { return eh.idx; }
+}  // namespace tadx
+
 // The Double<12> tet kernels are compiled in parallel, one Hessian part per translation unit (energies_tet_part.cu).
 namespace TinyAD { namespace detail {
 #define TADX_EXTERN_PART(P) extern template int launch_second_order_part<tadx::SymDirichlet3D, 3, 4, TADX_TET_PARTS, P, false>(const tadx::SymDirichlet3D&, const tad_launch_args&);
@@ -273,6 +283,14 @@ int tadx_selftest(int device)
             if (fm.eval(x) != 12.0) return 22;
             auto xm = fm.x_from_data([](IdxHandle v) { return std::vector<double>{1.0 + v.idx(), 2.0}; });
             if (xm.size() != 2 || xm[0] != 1.0 || xm[1] != 2.0) return 23;
+            // tests/HandleTypeTest.cc:44-66: custom variable / element handle types with user overloads of idx_from_handle
+            std::vector<tadx::CustomVariableHandle> cv = {{0}};
+            std::vector<tadx::CustomElementHandle> ce = {{0}};
+            auto fc = scalar_function<2>(cv, es);
+            fc.add_elements<1>(ce, Quadratic2D{C, D});
+            if (fc.eval(x) != 12.0) return 25;
+            auto [fcv, fcg, fcH] = fc.eval_with_hessian_proj(x);
+            if (fcv != 12.0 || fcH.nonZeros() != 4) return 26;
             std::vector<IdxHandle> sparse_ids = {{0}, {2}};                                // not compact -> rejected like integer handles
             threw = false;
             try { auto bad = scalar_function<2>(sparse_ids, es); } catch (const std::runtime_error&) { threw = true; }

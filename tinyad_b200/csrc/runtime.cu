@@ -900,17 +900,18 @@ __global__ void __launch_bounds__(256) slab_min_vertex(const int32_t* __restrict
     if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
-// Default slab sizes (one B200; sweeps in profiles/r02_slab_sweep.txt for C2 and profiles/r02c_sweep_c5.txt for C5): a slab costs
-// ~0.1-0.2 ms of launch gaps and partial waves, so the device-resident path uses few large slabs on two lanes (about a fifth of the
-// function, 512 k .. 2 M elements: as fast as one slab per term, but memory-bounded: 2.3 KB of staging + scratch per tet and lane),
-// while the host-buffer path trades some of that for a finer-grained overlap of the D2H copies with the assembly (about a
-// nineteenth of the function, 128 k .. 1 M elements: C2 131072, C5 ~557 k).
+// Default slab sizes (sweeps in profiles/r02_slab_sweep.txt for C2, profiles/r02c_sweep_c5.txt for C5 on one B200, and
+// profiles/r02i_n8_*.json for the 1.27 M tets per rank of C5 on 8 GPUs): a slab costs ~0.1-0.2 ms of launch gaps and partial
+// waves, so the device-resident path uses TWO slabs (one per lane; also what lets the halo exchange of a partitioned function
+// hide behind the second slab) until a slab would exceed 2 M elements, which bounds the memory: 2.3 KB of staging + scratch per
+// tet and lane.  The host-buffer path trades some of that for a finer-grained overlap of the D2H copies with the assembly (about
+// a nineteenth of the function, 128 k .. 1 M elements: C2 131072, C5 ~557 k).  Slabs of a term are balanced (build_schedule).
 int64_t default_chunk(tad_function f, bool host_path)
 {
     const int64_t n = std::max<int64_t>(f->n_elements, 1);
     auto round_up = [](int64_t v, int64_t q) { return (v + q - 1) / q * q; };
     if (host_path) return std::min<int64_t>(1048576, std::max<int64_t>(131072, round_up(n / 19, 32768)));
-    return std::min<int64_t>(2097152, std::max<int64_t>(524288, round_up(n / 5, 65536)));
+    return std::min<int64_t>(2097152, std::max<int64_t>(524288, round_up(n / 2, 65536)));
 }
 
 int64_t effective_chunk(tad_function f, bool whole_terms, bool host_path)
@@ -944,7 +945,13 @@ int build_schedule(tad_function f, int mode, bool whole_terms, bool host_path, t
         {
             const Term& t = f->terms[(size_t)ti];
             if (t.n <= 0) continue;
-            const int64_t step = chunk > 0 ? chunk : t.n;
+            // slabs of (almost) equal size, at most `chunk` elements: no small trailing slab with its partial waves
+            int64_t step = t.n;
+            if (chunk > 0 && t.n > chunk)
+            {
+                const int64_t n_slabs = (t.n + chunk - 1) / chunk;
+                step = (((t.n + n_slabs - 1) / n_slabs + 255) / 256) * 256;
+            }
             for (int64_t e0 = 0; e0 < t.n; e0 += step) S.slabs.push_back(Slab{ti, e0, std::min(step, t.n - e0), 0});
         }
         S.chunk = chunk;
