@@ -219,6 +219,16 @@ int tad_veval_sum_of_squares(tad_function f, const double* x_dev, double* f_host
 int tad_veval_sum_of_squares_with_derivatives(tad_function f, const double* x_dev, double* f_host, double* g_dev,
                                               double* r_dev, double* J_values_dev);
 
+/* eval_with_derivatives of a VectorFunction (VectorFunctionImpl.hh:203-236, VectorObjectiveTerm.hh:245-324): residuals, Jacobian
+ * values and the Hessian of EVERY residual.  The reference returns one n_vars x n_vars sparse matrix per residual, each holding the
+ * k x k entries of its element; here they come back as what they are: one dense row-major k x k block per residual in the
+ * element's local variable order (local index = d * slot + component; slot -> handle: tad_function_term_table), term after term,
+ * residual (e, m) of term t at H_blocks_dev[offset_t + ((M * e + m) * k) * k].  tad_function_residual_hessian_layout gives
+ * offset_t, k and the number of residuals of a term (term < 0: only `total`, the length of H_blocks_dev in doubles).
+ * Elements with more than 6 variables report TAD_NOT_SUPPORTED (one thread holds all M second-order scalars of an element). */
+int tad_veval_with_derivatives(tad_function f, const double* x_dev, double* r_dev, double* J_values_dev, double* H_blocks_dev);
+int tad_function_residual_hessian_layout(tad_function f, int term, int64_t* offset, int* k, int64_t* n_residuals, int64_t* total);
+
 /* ---- building blocks exposed for tests / reuse ---- */
 /* Batched in-place projection of n packed symmetric k x k matrices (SoA, tile order, leading dim stride):
  * project_positive_definite (Utils/HessianProjection.hh:48-101) incl. both early-outs and the eps < 0 mode.

@@ -83,3 +83,78 @@ def test_sos_equals_scalar_formulation(torch_cuda):
     f = fv.veval_sum_of_squares_with_derivatives(xd, g, r, J)
     assert abs(f - f_ref) < 1e-12 and np.abs(g.cpu().numpy() - g_ref).max() < 1e-12
     fs.close(); fv.close()
+
+
+def test_eval_with_derivatives_golden(torch_cuda):
+    """tests/VectorFunctionTest.cc:73-140 (test_eval): R^2 -> R^3, residuals (2 x0, x0^2, x1^2) at x = (3, 4): r, J and the Hessian of
+    every residual, exact values."""
+    torch = torch_cuda
+    fn = tad.Function(1, 2, is_vector=True)
+    fn.add_term(tad.SOS_TEST1D_A, np.array([[0]], dtype=np.int32), np.zeros((1, 1)))
+    fn.add_term(tad.SOS_TEST1D_B, np.array([[1]], dtype=np.int32), np.zeros((1, 1)))
+    try:
+        outer, inner = fn.pattern()
+        assert fn.n_outputs == 3 and list(outer) == [0, 2, 3] and list(inner) == [0, 1, 2]
+        total = fn.residual_hessian_layout(-1)[3]
+        assert total == 3 and fn.residual_hessian_layout(0)[:3] == (0, 1, 2) and fn.residual_hessian_layout(1)[:3] == (2, 1, 1)
+        xd = torch.tensor([3.0, 4.0], dtype=torch.float64, device="cuda")
+        r = torch.empty(3, dtype=torch.float64, device="cuda")
+        J = torch.empty(3, dtype=torch.float64, device="cuda")
+        Hb = torch.empty(total, dtype=torch.float64, device="cuda")
+        fn.veval_with_derivatives(xd, r, J, Hb)
+        assert r.cpu().tolist() == [6.0, 9.0, 16.0]
+        assert J.cpu().tolist() == [2.0, 6.0, 8.0]            # d r0 / d x0, d r1 / d x0, d r2 / d x1
+        assert Hb.cpu().tolist() == [0.0, 2.0, 2.0]           # H_0 = 0, H_1(0,0) = 2, H_2(1,1) = 2
+    finally:
+        fn.close()
+
+
+def test_per_residual_hessians_sum_to_the_scalar_hessian(torch_cuda):
+    """H(sum_i r_i^2) = 2 (J^T J + sum_i r_i H_i): the per-residual Hessians of the sum-of-squares formulation
+    (tests/GaussNewtonTest.cc:34-72, 8 residuals x Double<6> per triangle) must reproduce the unprojected Hessian of the scalar twin
+    (tests/NewtonTest.cc:28-55), which the scalar tests compare with the oracle."""
+    import scipy.sparse as sp
+    torch = torch_cuda
+    N = 16
+    V, F = meshes.grid_2d(N)
+    x = meshes.deform(V, 1.0 / N, seed=5).reshape(-1)
+    s = 1.0 / np.sqrt(len(F))
+    b = np.array([[0], [N], [(N + 1) * N]], dtype=np.int32)
+    bc = V[b[:, 0]] + 0.02
+    fv = tad.Function(2, len(V), is_vector=True)
+    fv.add_term(tad.SOS_SYMDIRICHLET2D, F, meshes.tri_rest_data(V, F, weight=s))
+    fv.add_term(tad.SOS_PENALTY2D, b, bc)
+    fs = tad.Function(2, len(V))
+    fs.add_term(tad.SYMDIRICHLET2D, F, meshes.tri_rest_data(V, F, weight=s * s))
+    fs.add_term(tad.PENALTY2D, b, bc)
+    try:
+        n, m = fv.n_vars, fv.n_outputs
+        outer, inner = fv.pattern()
+        total = fv.residual_hessian_layout(-1)[3]
+        xd = torch.from_numpy(x).cuda()
+        r = torch.empty(m, dtype=torch.float64, device="cuda")
+        J = torch.empty(len(inner), dtype=torch.float64, device="cuda")
+        Hb = torch.empty(total, dtype=torch.float64, device="cuda")
+        fv.veval_with_derivatives(xd, r, J, Hb)
+        rh, Hbh = r.cpu().numpy(), Hb.cpu().numpy()
+        Jm = sp.csc_matrix((J.cpu().numpy(), inner, outer), shape=(m, n))
+        Hf = (2.0 * (Jm.T @ Jm)).toarray()
+        row0 = 0
+        for term, (conn, valence, M) in enumerate(((F, 3, 8), (b, 1, 2))):
+            off, k, n_res, _ = fv.residual_hessian_layout(term)
+            assert k == 2 * valence and n_res == M * len(conn)
+            table = fv.term_table(term, valence, len(conn))                         # slot -> handle, per element
+            blocks = Hbh[off:off + n_res * k * k].reshape(len(conn), M, k, k)
+            assert np.abs(blocks - blocks.transpose(0, 1, 3, 2)).max() == 0.0       # packed symmetric storage
+            for e in range(len(conn)):
+                gv = (2 * table[:, e][:, None] + np.arange(2)[None, :]).reshape(-1)  # local index -> global variable
+                w = rh[row0 + M * e: row0 + M * (e + 1)]
+                Hf[np.ix_(gv, gv)] += 2.0 * np.einsum("m,mij->ij", w, blocks[e])
+            row0 += n_res
+        f, g, Hs = fs.eval_with_derivatives_host(x)
+        so, si = fs.pattern()
+        Hsd = sp.csr_matrix((Hs, si, so), shape=(n, n)).toarray()
+        assert np.abs(Hf - Hsd).max() <= 1e-11 * np.abs(Hsd).max()
+        assert abs(float(rh @ rh) - f) <= 1e-12 * abs(f)
+    finally:
+        fv.close(); fs.close()

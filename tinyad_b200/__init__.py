@@ -32,6 +32,7 @@ BRANCH_ON_X1D = 13                      # variables() calls depend on x -> TAD_P
 ARAP2D = 12                             # w |J - closest_orthogonal(J)|^2 (Operations/SVD.hh inside an element functor)
 DYN_SUM_SQR2D, DYN_ONERING1D = 10, 11   # add_elements_dynamic (tests/DynamicElementsTest.cc)
 SOS_SYMDIRICHLET2D, SOS_PENALTY2D, SOS_POLYCURL2D = 101, 102, 103
+SOS_TEST1D_A, SOS_TEST1D_B = 104, 105     # tests/VectorFunctionTest.cc:73-93
 
 # every symbol include/tinyad_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -40,7 +41,8 @@ ABI_SYMBOLS = [
     "tad_function_n_outputs", "tad_function_pattern", "tad_function_pattern_copy", "tad_function_pattern_device",
     "tad_function_term_table", "tad_eval", "tad_eval_with_gradient", "tad_eval_with_derivatives", "tad_eval_host",
     "tad_eval_with_gradient_host", "tad_eval_with_derivatives_host", "tad_veval", "tad_veval_with_jacobian",
-    "tad_veval_sum_of_squares", "tad_veval_sum_of_squares_with_derivatives", "tad_project_batch",
+    "tad_veval_sum_of_squares", "tad_veval_sum_of_squares_with_derivatives", "tad_veval_with_derivatives",
+    "tad_function_residual_hessian_layout", "tad_project_batch",
     "tad_function_projection_stats", "tad_function_last_timings", "tad_function_set_timing", "tad_bench_fp64_peak",
     "tad_set_last_error", "tad_function_variable_dimension",
     "tad_comm_unique_id", "tad_comm_create", "tad_comm_adopt", "tad_comm_destroy", "tad_comm_rank", "tad_comm_world",
@@ -94,6 +96,8 @@ def runtime():
         L.tad_veval_with_jacobian.argtypes = [vp, vp, vp, vp]
         L.tad_veval_sum_of_squares.argtypes = [vp, vp, vp]
         L.tad_veval_sum_of_squares_with_derivatives.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.tad_veval_with_derivatives.argtypes = [vp, vp, vp, vp, vp]
+        L.tad_function_residual_hessian_layout.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
         L.tad_project_batch.argtypes = [ctypes.c_int, i64, i64, vp, dbl, ctypes.c_int, vp, vp]
         L.tad_function_projection_stats.argtypes = [vp, vp]
         L.tad_function_last_timings.argtypes = [vp, vp]
@@ -395,6 +399,20 @@ class Function:
         f = ctypes.c_double()
         _check(runtime().tad_veval_sum_of_squares_with_derivatives(self.h, _ptr(x_dev), ctypes.byref(f), _ptr(g_dev), _ptr(r_dev), _ptr(J_dev)))
         return f.value
+
+
+def _residual_hessian_layout(fn, term):
+    off, k, n_res, total = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+    _check(runtime().tad_function_residual_hessian_layout(fn.h, term, ctypes.byref(off), ctypes.byref(k), ctypes.byref(n_res), ctypes.byref(total)))
+    return off.value, k.value, n_res.value, total.value
+
+
+def _veval_with_derivatives(fn, x_dev, r_dev, J_dev, Hb_dev):
+    _check(runtime().tad_veval_with_derivatives(fn.h, _ptr(x_dev), _ptr(r_dev), _ptr(J_dev), _ptr(Hb_dev)))
+
+
+Function.residual_hessian_layout = _residual_hessian_layout      # (offset, k, n_residuals, total doubles) of a term (term < 0: total only)
+Function.veval_with_derivatives = _veval_with_derivatives        # r, J values, one dense k x k Hessian block per residual
 
 
 def project_batch(k, hess_dev, n, stride, eps=1e-9, method=0, counts_dev=None, stream=None):

@@ -337,7 +337,7 @@ int assemble_atomic(int d, int N, const SlabMaps& m, const double* grad, const d
     if (!done)
     {
         const int K = d * N;
-        if (K > 18) return fail(TAD_NOT_SUPPORTED, "assembly supports at most 18 variables per element");
+        if (K > 32) return fail(TAD_NOT_SUPPORTED, "assembly supports at most 32 variables per element");
         SeqTable seq;
         for (int i = 0; i < K; ++i)
             for (int j = 0; j < K; ++j) seq.idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);

@@ -67,7 +67,7 @@ enum
 {
     K_SYMDIRICHLET2D = 1, K_PENALTY2D = 2, K_SYMDIRICHLET3D = 3, K_PENALTY3D = 4, K_EDGE_DIRICHLET1D = 5, K_ARAP2D = 12, K_DYN_SUM_SQR2D = 10, K_DYN_ONERING1D = 11,
     K_QUADRATIC2D = 6, K_REPEATED_HANDLE = 7, K_TRIG_MIX2D = 8, K_SQRT1D = 9, K_BRANCH_ON_X1D = 13,
-    K_SOS_SYMDIRICHLET2D = 101, K_SOS_PENALTY2D = 102, K_SOS_POLYCURL2D = 103,
+    K_SOS_SYMDIRICHLET2D = 101, K_SOS_PENALTY2D = 102, K_SOS_POLYCURL2D = 103, K_SOS_TEST1D_A = 104, K_SOS_TEST1D_B = 105,
 };
 
 struct DeviceArray
@@ -95,6 +95,7 @@ struct Problem
     std::unique_ptr<ScalarFunction<2>> s2;
     std::unique_ptr<ScalarFunction<3>> s3;
     std::unique_ptr<VectorFunction<2>> v2;
+    std::unique_ptr<VectorFunction<1>> v1;
     std::vector<std::unique_ptr<DeviceArray>> arrays;
     tad_function handle() const
     {
@@ -102,6 +103,7 @@ struct Problem
         if (s2) return s2->handle();
         if (s3) return s3->handle();
         if (v2) return v2->handle();
+        if (v1) return v1->handle();
         return nullptr;
     }
 };
@@ -131,8 +133,9 @@ int tadx_create(int d, int64_t n_vertices, int is_vector, int device, int assemb
         s.assembly = assembly;
         if (is_vector)
         {
-            if (d != 2) throw std::runtime_error("vector functions are instantiated for d = 2 only");
-            P->v2 = std::make_unique<VectorFunction<2>>(vector_function<2>(range(n_vertices), s));
+            if (d == 2) P->v2 = std::make_unique<VectorFunction<2>>(vector_function<2>(range(n_vertices), s));
+            else if (d == 1) P->v1 = std::make_unique<VectorFunction<1>>(vector_function<1>(range(n_vertices), s));
+            else throw std::runtime_error("vector functions are instantiated for d = 1, 2 only");
         }
         else if (d == 1) P->s1 = std::make_unique<ScalarFunction<1>>(scalar_function<1>(range(n_vertices), s));
         else if (d == 2) P->s2 = std::make_unique<ScalarFunction<2>>(scalar_function<2>(range(n_vertices), s));
@@ -180,6 +183,8 @@ int tadx_add_term(void* h, int kind, int64_t n_elements, const int32_t* conn, in
         case K_SOS_SYMDIRICHLET2D: need(P->v2 && valence == 3 && n_data == 5); P->v2->add_elements<3, 8>(els, SosSymDirichlet2D{C, D}); break;
         case K_SOS_PENALTY2D: need(P->v2 && valence == 1 && n_data == 2); P->v2->add_elements<1, 2>(els, SosPenalty2D{C, D}); break;
         case K_SOS_POLYCURL2D: need(P->v2 && valence == 2 && n_data == 3); P->v2->add_elements<2, 2>(els, SosPolycurl2D{C, D}); break;
+        case K_SOS_TEST1D_A: need(P->v1 && valence == 1); P->v1->add_elements<1, 2>(els, SosTest1DA{C, D}); break;
+        case K_SOS_TEST1D_B: need(P->v1 && valence == 1); P->v1->add_elements<1, 1>(els, SosTest1DB{C, D}); break;
         default: throw std::runtime_error("unknown term kind");
         }
     });
@@ -263,6 +268,36 @@ int tadx_selftest(int device)
             threw = false;
             try { newton_direction(gq, Hneg, solver); } catch (const std::runtime_error&) { threw = true; }
             if (!threw) return 19;
+        }
+        // tests/VectorFunctionTest.cc:73-172 (test_eval) through the facade, incl. eval_with_derivatives (per-residual Hessians)
+        {
+            DeviceArray ca, cb;
+            const int32_t conn_a[1] = {0}, conn_b[1] = {1};
+            if (!upload_soa(conn_a, 1, 1, 32, ca) || !upload_soa(conn_b, 1, 1, 32, cb)) return 30;
+            auto vf = vector_function<1>(range(2), es);
+            vf.add_elements<1, 2>(range(1), SosTest1DA{ConnView{static_cast<const int32_t*>(ca.p), 32}, D});
+            vf.add_elements<1, 1>(range(1), SosTest1DB{ConnView{static_cast<const int32_t*>(cb.p), 32}, D});
+            const std::vector<double> xv = {3.0, 4.0};
+            const double r_exp[3] = {6.0, 9.0, 16.0};
+            const std::vector<double> rv = vf.eval(xv);
+            for (int i = 0; i < 3; ++i) if (rv[(size_t)i] != r_exp[i]) return 31;
+            if (vf.eval_sum_of_squares(xv) != 373.0) return 32;
+            auto [r1, J1] = vf.eval_with_jacobian(xv);
+            if (J1.coeff(0, 0) != 2.0 || J1.coeff(1, 0) != 6.0 || J1.coeff(2, 1) != 8.0 || J1.coeff(2, 0) != 0.0 || J1.nonZeros() != 3) return 33;
+            auto [r2, J2, H2] = vf.eval_with_derivatives(xv);
+            for (int i = 0; i < 3; ++i) if (r2[(size_t)i] != r_exp[i]) return 34;
+            if (J2.coeff(0, 0) != 2.0 || J2.coeff(1, 0) != 6.0 || J2.coeff(2, 1) != 8.0) return 35;
+            if (H2.size() != 3) return 36;
+            // H_expected[1](0,0) = 2, H_expected[2](1,1) = 2, everything else 0 (:101-103)
+            for (int i = 0; i < 3; ++i)
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b)
+                    {
+                        const double want = ((i == 1 && a == 0 && b == 0) || (i == 2 && a == 1 && b == 1)) ? 2.0 : 0.0;
+                        if (H2[(size_t)i].coeff(a, b) != want) return 37;
+                    }
+            auto [f3, g3, r3, J3] = vf.eval_sum_of_squares_with_derivatives(xv);
+            if (f3 != 373.0 || g3[0] != 8.0 * 3.0 + 4.0 * 27.0 || g3[1] != 4.0 * 64.0) return 38;
         }
         // mesh-library handle types (Support/Common.hh; reference Support/{OpenMesh,PMP,Polymesh,GeometryCentral}.hh): handles with
         // .idx(), .idx.value or .getIndex() enumerate variables and elements on the host; the device functor sees the integer

@@ -263,6 +263,35 @@ struct SosPenalty2D  // GaussNewtonTest.cc:63-70
     }
 };
 
+// tests/VectorFunctionTest.cc:73-93 (test_eval): R^2 -> R^3, element A returns (2 x0, x0^2), element B returns (x1^2)
+struct SosTest1DA
+{
+    ConnView C; DataView D;  // D unused
+    template <class E>
+    TINYAD_HD auto operator()(E& element) const -> TINYAD_VECTOR_TYPE(element)
+    {
+        using T = TINYAD_SCALAR_TYPE(element);
+        T x0 = element.variables(C(element.handle, 0))[0];
+        Vec<T, 2> r;
+        r[0] = 2.0 * x0;
+        r[1] = sqr(x0);
+        return r;
+    }
+};
+struct SosTest1DB
+{
+    ConnView C; DataView D;  // D unused
+    template <class E>
+    TINYAD_HD auto operator()(E& element) const -> TINYAD_VECTOR_TYPE(element)
+    {
+        using T = TINYAD_SCALAR_TYPE(element);
+        T x1 = element.variables(C(element.handle, 0))[0];
+        Vec<T, 1> r;
+        r[0] = sqr(x1);
+        return r;
+    }
+};
+
 struct SosPolycurl2D  // synthetic polycurl-style complex residual (config C4 stand-in), data: ex ey w
 {
     ConnView C; DataView D;

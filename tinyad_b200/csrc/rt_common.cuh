@@ -208,7 +208,7 @@ int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps,
                      int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st);
 
 // ---- assembly (assembly.cu) ----
-struct SeqTable { int16_t idx[18 * 18]; };
+struct SeqTable { int16_t idx[32 * 32]; };   // packed (tile-order) index of entry (i, j), row-major k x k, k <= 32
 // The scatter maps of one slab: the term's maps offset to the slab's first element (leading dimension mstride).
 struct SlabMaps
 {

@@ -371,6 +371,23 @@ __global__ void scatter_jacobian(const double* grad, const int32_t* jslot, int64
     if (!finite) atomicOr(err, ERR_NONFINITE);
 }
 
+// Per-residual Hessians of a vector term: staged packed entries hess[(m * nh + s) * stride + e] -> dense row-major k x k blocks,
+// one per residual, out[((M * e + m) * k + i) * k + j] (element-local variable order).
+__global__ void __launch_bounds__(256) scatter_hess_blocks(const double* __restrict__ hess, int64_t n, int64_t stride, int M, int k, int nh, SeqTable seq,
+                                                           double* __restrict__ out, int32_t* err)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int kk = k * k;
+    if (i >= n * M * kk) return;
+    const int64_t em = i / kk;          // M * e + m
+    const int ij = (int)(i % kk);
+    const int64_t e = em / M;
+    const int m = (int)(em % M);
+    const double v = hess[(int64_t)(m * nh + seq.idx[ij]) * stride + e];
+    if (!isfinite(v)) atomicOr(err, ERR_NONFINITE);
+    out[i] = v;
+}
+
 __global__ void jt_r(const int32_t* outer, const int32_t* inner, const double* Jv, const double* r, int64_t n_vars, double* g)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -450,7 +467,7 @@ void fill_launch_args(tad_function f, const Term& t, int mode, const double* x, 
     const int rows = std::max(1, t.M);
     a.val = stage;
     a.grad = stage ? stage + (int64_t)rows * sstride : nullptr;
-    a.hess = (stage && t.M == 0) ? a.grad + (int64_t)t.k * sstride : nullptr;
+    a.hess = stage ? a.grad + (int64_t)rows * t.k * sstride : nullptr;   // scalar terms: after grad[k]; vector terms: after grad[M * k]
     a.rec_handles = t.rec_handles.p;
     a.rec_counts = t.rec_counts.p;
     a.error_flags = f->err.p;
@@ -467,7 +484,7 @@ size_t stage_doubles(const Term& t, int mode, int64_t sstride)
     const int rows = std::max(1, t.M);
     size_t per = rows;
     if (mode >= TAD_MODE_FIRST) per += (size_t)rows * t.k;
-    if (mode == TAD_MODE_SECOND && t.M == 0) per += (size_t)hess_size(t.k);
+    if (mode == TAD_MODE_SECOND) per += (size_t)rows * hess_size(t.k);   // vector terms: one packed Hessian per residual
     return per * (size_t)sstride;
 }
 size_t stage_doubles(const Term& t, int mode) { return stage_doubles(t, mode, t.stride); }
@@ -634,7 +651,7 @@ int build_pattern_scalar(tad_function f)
         for (size_t ti = 0; ti < f->terms.size(); ++ti)
         {
             const int K = f->terms[ti].k;
-            if (K > 18) continue;  // gather assembly reports TAD_NOT_SUPPORTED for such a term
+            if (K > 32) continue;  // gather assembly reports TAD_NOT_SUPPORTED for such a term
             for (int i = 0; i < K; ++i)
                 for (int j = 0; j < K; ++j) seqs[ti].idx[i * K + j] = (int16_t)hess_seq_index(K, i, j);
         }
@@ -1211,7 +1228,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     if (gather)
     {
         for (const Term& t : f->terms)
-            if (t.k > 18) return fail(TAD_NOT_SUPPORTED, "gather assembly supports at most 18 variables per element");
+            if (t.k > 32) return fail(TAD_NOT_SUPPORTED, "gather assembly supports at most 32 variables per element");
         cudaEvent_t g0 = f->lanes[0].tev[0], g1 = f->lanes[0].tev[1];
         if (f->timing) cudaEventRecord(g0, st);
         TAD_TRY(upload_terms_dev(f, true, mode));
@@ -1297,9 +1314,19 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     return es;
 }
 
-int eval_vector(tad_function f, int what, const double* x, double* f_host, double* g, double* r, double* Jv)
+// First residual-Hessian block of every term in the output of tad_veval_with_derivatives (in doubles), and the total.
+std::vector<int64_t> residual_hessian_offsets(tad_function f)
 {
-    // what: 0 eval (r), 1 jacobian (r, J), 2 sum of squares (f), 3 sum of squares with derivatives (f, g, r, J)
+    std::vector<int64_t> off(f->terms.size() + 1, 0);
+    for (size_t ti = 0; ti < f->terms.size(); ++ti)
+        off[ti + 1] = off[ti] + f->terms[ti].n * f->terms[ti].M * (int64_t)f->terms[ti].k * f->terms[ti].k;
+    return off;
+}
+
+int eval_vector(tad_function f, int what, const double* x, double* f_host, double* g, double* r, double* Jv, double* Hblocks = nullptr)
+{
+    // what: 0 eval (r), 1 jacobian (r, J), 2 sum of squares (f), 3 sum of squares with derivatives (f, g, r, J),
+    //       4 derivatives (r, J, one dense k x k Hessian block per residual)
     if (!f->is_vector) return fail(TAD_INVALID_ARGUMENT, "vector evaluation called on a scalar function");
     std::lock_guard<std::recursive_mutex> lock(f->mtx);
     DeviceGuard guard(f->device);
@@ -1308,9 +1335,10 @@ int eval_vector(tad_function f, int what, const double* x, double* f_host, doubl
     TAD_TRY(ensure_pattern(f));
     TAD_TRY(wait_for_caller(f));
     const int n_terms = (int)f->terms.size();
-    const int mode = (what == 1 || what == 3) ? TAD_MODE_FIRST : TAD_MODE_PASSIVE;
+    const int mode = what == 4 ? TAD_MODE_SECOND : ((what == 1 || what == 3) ? TAD_MODE_FIRST : TAD_MODE_PASSIVE);
     TAD_CUDA(cudaMemsetAsync(f->err.p, 0, 8 * sizeof(int32_t), st));
     TAD_CUDA(f->fterm.ensure((size_t)std::max(n_terms, 1) + 1));
+    const std::vector<int64_t> hoff = residual_hessian_offsets(f);
     for (int ti = 0; ti < n_terms; ++ti)
     {
         Term& t = f->terms[ti];
@@ -1328,10 +1356,20 @@ int eval_vector(tad_function f, int what, const double* x, double* f_host, doubl
             count_launch();
             scatter_residuals<<<blocks_for(t.n * t.M, 256), 256, 0, st>>>(a.val, t.n, t.stride, t.M, t.out_offset, r);
         }
-        if (mode == TAD_MODE_FIRST && t.n > 0)
+        if (mode >= TAD_MODE_FIRST && t.n > 0)
         {
             count_launch();
             scatter_jacobian<<<blocks_for(t.n, 128), 128, 0, st>>>(a.grad, t.jslot.p, t.n, t.stride, t.M * t.k, Jv, f->err.p);
+        }
+        if (what == 4 && t.n > 0)
+        {
+            if (t.k > 32) return fail(TAD_NOT_SUPPORTED, "per-residual Hessians support at most 32 variables per element");
+            SeqTable seq;
+            for (int i = 0; i < t.k; ++i)
+                for (int j = 0; j < t.k; ++j) seq.idx[i * t.k + j] = (int16_t)hess_seq_index(t.k, i, j);
+            count_launch();
+            scatter_hess_blocks<<<blocks_for(t.n * t.M * t.k * t.k, 256), 256, 0, st>>>(a.hess, t.n, t.stride, t.M, t.k, hess_size(t.k), seq,
+                                                                                        Hblocks + hoff[(size_t)ti], f->err.p);
         }
     }
     double fv = 0.0;
@@ -1713,6 +1751,25 @@ int tad_veval_sum_of_squares_with_derivatives(tad_function f, const double* x_de
 {
     if (!f || !g_dev || !r_dev || !J_values_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
     return eval_vector(f, 3, x_dev, f_host, g_dev, r_dev, J_values_dev);
+}
+
+int tad_veval_with_derivatives(tad_function f, const double* x_dev, double* r_dev, double* J_values_dev, double* H_blocks_dev)
+{
+    if (!f || !r_dev || !J_values_dev || !H_blocks_dev) return fail(TAD_INVALID_ARGUMENT, "null argument");
+    return eval_vector(f, 4, x_dev, nullptr, nullptr, r_dev, J_values_dev, H_blocks_dev);
+}
+
+int tad_function_residual_hessian_layout(tad_function f, int term, int64_t* offset, int* k, int64_t* n_residuals, int64_t* total)
+{
+    if (!f || !f->is_vector) return fail(TAD_INVALID_ARGUMENT, "residual Hessians belong to vector functions");
+    const std::vector<int64_t> off = residual_hessian_offsets(f);
+    if (total) *total = off.back();
+    if (term < 0) return TAD_OK;
+    if (term >= (int)f->terms.size()) return fail(TAD_INVALID_ARGUMENT, "bad term index");
+    if (offset) *offset = off[(size_t)term];
+    if (k) *k = f->terms[(size_t)term].k;
+    if (n_residuals) *n_residuals = f->terms[(size_t)term].n * f->terms[(size_t)term].M;
+    return TAD_OK;
 }
 
 int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double eps, int method, int64_t* counts_dev, void* stream)

@@ -217,6 +217,36 @@ __global__ void __launch_bounds__(128, TINYAD_FUSED_MIN_BLOCKS) second_order_fus
     if (!finite) atomicOr(a.error_flags, 1 << TAD_NONFINITE_DERIVATIVE);
 }
 
+// Per-residual second derivatives of a VectorFunction element (VectorObjectiveTerm.hh:245-324, eval_with_derivatives): every
+// residual r_m of the element comes back with its gradient (the Jacobian rows) and its packed k x k Hessian.  Staging layout:
+// val[m], grad[m * k + i], hess[m * k(k+1)/2 + s] (tile order), leading dimension stride.  One thread per element, so this is
+// for elements with few variables (NP == 1, k <= 6); larger elements report TAD_NOT_SUPPORTED.
+template <class Functor, int d, int N, int M, bool Dedup>
+__global__ void __launch_bounds__(128) second_order_vector_kernel(Functor f, tad_launch_args a)
+{
+    constexpr int k = d * N;
+    using T = Scalar<k, true, 1, 0>;
+    constexpr int nh = T::nh;
+    int64_t si;
+    if (!slab_index(a, si)) return;
+    const int64_t e = a.e_begin + si;
+    Element<d, N, M, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags, rec_column(a, e), a.rec_stride);
+    const Vec<T, M> r = f(el);
+    static_for<M>([&](auto mc) TINYAD_LAMBDA_INLINE {
+        constexpr int m = decltype(mc)::value;
+        a.val[m * a.stride + si] = r.a[m].val;
+        static_for<k>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            a.grad[(m * k + i) * a.stride + si] = r.a[m].grad[i];
+        });
+        static_for<nh>([&](auto sc) TINYAD_LAMBDA_INLINE {
+            constexpr int s = decltype(sc)::value;
+            a.hess[(int64_t)(m * nh + s) * a.stride + si] = r.a[m].hess[s];
+        });
+    });
+    if (a.rec_counts) el.check_recorded_count(a.rec_counts[e]);
+}
+
 inline int check_launch();
 
 // One kernel per Hessian part: all threads of a launch run the same instantiation
@@ -308,8 +338,10 @@ struct TermLauncher
                 });
                 return status;
             }
+            else if constexpr (NP == 1)
+                detail::second_order_vector_kernel<Functor, d, N, M, Dedup><<<g128, 128, 0, st>>>(self->f, *a);
             else
-                return TAD_NOT_SUPPORTED;  // per-residual Hessians (VectorObjectiveTerm.hh:245-324) are out of scope
+                return TAD_NOT_SUPPORTED;  // per-residual Hessians (VectorObjectiveTerm.hh:245-324) of elements with k > 6
             break;
         default:
             return TAD_INVALID_ARGUMENT;

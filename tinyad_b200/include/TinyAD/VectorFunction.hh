@@ -9,6 +9,8 @@
 // (eval_with_derivatives, VectorFunctionImpl.hh:206-252) is out of scope.
 #pragma once
 
+#include <algorithm>
+
 #include <TinyAD/ScalarFunction.hh>
 
 namespace TinyAD
@@ -47,6 +49,7 @@ struct VectorFunction
             settings = o.settings;
             n_vars = o.n_vars; n_elements = o.n_elements; n_outputs = o.n_outputs;
             variable_handles = std::move(o.variable_handles);
+            term_elements_ = std::move(o.term_elements_);
             o.n_vars = o.n_elements = o.n_outputs = 0;
         }
         return *this;
@@ -67,6 +70,7 @@ struct VectorFunction
                                             identity ? nullptr : handles.data(), &L::launch, launcher, &L::destroy));
         n_elements += (int64_t)handles.size();
         n_outputs += outputs_per_element * (int64_t)handles.size();
+        term_elements_.push_back((int64_t)handles.size());
     }
 
     std::vector<double> eval(const std::vector<double>& _x) const  // :143-159
@@ -95,6 +99,82 @@ struct VectorFunction
         SparseMatrix J;
         eval_with_jacobian(_x, r, J);
         return {std::move(r), std::move(J)};
+    }
+
+    // VectorFunctionImpl.hh:203-236 (eval_with_derivatives): residuals, Jacobian and one n_vars x n_vars Hessian per residual.
+    // The device returns one dense k x k block per residual (tad_veval_with_derivatives); the sparse matrices of the reference's
+    // signature are built from them on the host with setFromTriplets semantics (k^2 entries per residual, zeros kept, entries of a
+    // handle requested twice summed).  eval_hessians_device keeps the blocks in HBM.
+    void eval_with_derivatives(const std::vector<double>& _x, std::vector<double>& _r, SparseMatrix& _J, std::vector<SparseMatrix>& _H) const
+    {
+        _r.assign((size_t)n_outputs, 0.0);
+        _J = pattern();
+        _H.assign((size_t)n_outputs, SparseMatrix());
+        for (auto& Hm : _H) { Hm.rows = Hm.cols = n_vars; Hm.outer.assign((size_t)n_vars + 1, 0); }
+        if (!h) return;
+        Scratch s(*this, _x, true);
+        int64_t total = 0;
+        detail::check(tad_function_residual_hessian_layout(h, -1, nullptr, nullptr, nullptr, &total));
+        double* Hb = nullptr;
+        Scratch::cuda_check(cudaMalloc(&Hb, sizeof(double) * (size_t)(total + 1)));
+        const int status = tad_veval_with_derivatives(h, s.x, s.r, s.J, Hb);
+        std::vector<double> blocks((size_t)total);
+        if (status == TAD_OK && total) cudaMemcpy(blocks.data(), Hb, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost);
+        cudaFree(Hb);
+        detail::check(status);
+        s.download(nullptr, &_r, &_J.values);
+        int64_t row0 = 0;
+        for (int t = 0;; ++t)
+        {
+            int64_t off = 0, n_res = 0;
+            int k = 0;
+            if (tad_function_residual_hessian_layout(h, t, &off, &k, &n_res, nullptr) != TAD_OK) break;   // past the last term
+            const int N = k / variable_dimension;
+            const int64_t n_el = term_elements_[(size_t)t];
+            const int M = n_el ? (int)(n_res / n_el) : 0;
+            std::vector<int32_t> table((size_t)N * (size_t)n_el);
+            detail::check(tad_function_term_table(h, t, table.data()));
+            for (int64_t e = 0; e < n_el; ++e)
+                for (int m = 0; m < M; ++m)
+                {
+                    const double* B = blocks.data() + off + ((int64_t)M * e + m) * k * k;
+                    // dense accumulation over the element's global variables (columns sorted ascending, duplicates summed)
+                    std::vector<std::pair<int64_t, int>> vars;   // (global variable, local index)
+                    for (int sl = 0; sl < N; ++sl)
+                    {
+                        const int32_t vh = table[(size_t)sl * (size_t)n_el + (size_t)e];
+                        if (vh < 0) continue;
+                        for (int c = 0; c < variable_dimension; ++c) vars.push_back({(int64_t)variable_dimension * vh + c, variable_dimension * sl + c});
+                    }
+                    std::sort(vars.begin(), vars.end());
+                    SparseMatrix& Hm = _H[(size_t)(row0 + (int64_t)M * e + m)];
+                    for (size_t cj = 0; cj < vars.size(); ++cj)
+                    {
+                        for (size_t ri = 0; ri < vars.size(); ++ri)
+                        {
+                            Hm.inner.push_back((int32_t)vars[ri].first);
+                            Hm.values.push_back(B[vars[ri].second * k + vars[cj].second]);
+                        }
+                        Hm.outer[(size_t)vars[cj].first + 1] = (int32_t)vars.size();
+                    }
+                    for (int64_t c = 0; c < n_vars; ++c) Hm.outer[(size_t)c + 1] += Hm.outer[(size_t)c];
+                }
+            row0 += n_res;
+        }
+    }
+    std::tuple<std::vector<double>, SparseMatrix, std::vector<SparseMatrix>> eval_with_derivatives(const std::vector<double>& _x) const
+    {
+        std::vector<double> r;
+        SparseMatrix J;
+        std::vector<SparseMatrix> H;
+        eval_with_derivatives(_x, r, J, H);
+        return {std::move(r), std::move(J), std::move(H)};
+    }
+    // device-resident form: r (n_outputs), J values (nnz of the CSC pattern), H blocks (tad_function_residual_hessian_layout)
+    void eval_with_derivatives_device(const double* x_dev, double* r_dev, double* J_values_dev, double* H_blocks_dev) const
+    {
+        if (!h) return;
+        detail::check(tad_veval_with_derivatives(h, x_dev, r_dev, J_values_dev, H_blocks_dev));
     }
 
     double eval_sum_of_squares(const std::vector<double>& _x) const  // :254-266
@@ -179,6 +259,7 @@ private:
     };
 
     tad_function h = nullptr;
+    std::vector<int64_t> term_elements_;   // number of elements of every term (layout of the per-residual Hessian blocks)
 };
 
 // VectorFunction.hh:198-204
