@@ -368,15 +368,23 @@ __global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t
         code = TinyAD::detail::proj_select_vectors<K>(
             [&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return sl[i * bd]; }, [&](int i, double v) { sl[i * bd] = v; },
             [&](int i, double v) { wp[(int64_t)i * stride] = v; },
-            [&](int jv, int q, double v) {
-                wp[(int64_t)(L::off_vec + jv * K + q) * stride] = v;
-                if (jv < B2_SMEM_VECS) sv[(jv * K + q) * bd] = v;
+            [&](int jv, const double (&v)[K]) {
+                double* p = wp + (int64_t)(L::off_vec + jv * K) * stride;
+#pragma unroll
+                for (int q = 0; q < K; ++q) { *p = v[q]; p += stride; }
+                if (jv < B2_SMEM_VECS)
+                {
+                    double* q0 = sv + (jv * K) * bd;
+#pragma unroll
+                    for (int q = 0; q < K; ++q) q0[q * bd] = v[q];
+                }
             },
             [&](int jv, double (&v)[K]) {
                 if (jv < B2_SMEM_VECS)
                 {
+                    const double* q0 = sv + (jv * K) * bd;
 #pragma unroll
-                    for (int q = 0; q < K; ++q) v[q] = sv[(jv * K + q) * bd];
+                    for (int q = 0; q < K; ++q) v[q] = q0[q * bd];
                 }
                 else
                 {

@@ -405,13 +405,43 @@ TINYAD_HD TINYAD_INLINE void sort_ascending(double (&v)[K])
     }
 }
 
+// Dot product / sums of K entries with FOUR independent accumulators: phase B2 runs at two warps per scheduler and is bound by
+// the latency of dependent FP64 instructions, so a 12-long serial fma chain costs ~100 cycles where four chains of 3 plus a
+// 2-level combine cost ~40 (ncu: the serial dot products of the orthogonalisation passes were 12 % of the kernel's stall samples).
+template <int K>
+TINYAD_HD TINYAD_INLINE double dot4(const double (&a)[K], const double (&b)[K])
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+        constexpr int i = decltype(ic)::value;
+        if constexpr (i % 4 == 0) s0 = fma(a[i], b[i], s0);
+        else if constexpr (i % 4 == 1) s1 = fma(a[i], b[i], s1);
+        else if constexpr (i % 4 == 2) s2 = fma(a[i], b[i], s2);
+        else s3 = fma(a[i], b[i], s3);
+    });
+    return (s0 + s1) + (s2 + s3);
+}
+template <int K>
+TINYAD_HD TINYAD_INLINE double abssum4(const double (&a)[K])
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+        constexpr int i = decltype(ic)::value;
+        if constexpr (i % 4 == 0) s0 += fabs(a[i]);
+        else if constexpr (i % 4 == 1) s1 += fabs(a[i]);
+        else if constexpr (i % 4 == 2) s2 += fabs(a[i]);
+        else s3 += fabs(a[i]);
+    });
+    return (s0 + s1) + (s2 + s3);
+}
+
 // Phase B2: selection of the eigenvalues that move, their eigenvectors (of T) by inverse iteration.
 // Scalar recurrences on small arrays, written as plain loops: nvcc unrolls the fixed-trip-count ones (LU, solves)
 // so those arrays live in registers.  load_w re-reads vectors already stored through store_w; the eigenvalues are read
 // back from R at run-time indices.
 // Functors: load_r(i) reads R; load_lam(i) / store_lam(i, v), i < K: the eigenvalues (read unsorted from R[off_lam + i] by the
 // first load_lam calls, then rewritten sorted -- the kernel keeps the sorted copy in shared memory, they are read at run-time
-// indices); store_w(i, v) writes W; store_vec(jv, q, v) writes component q of vector jv (W[off_vec + jv K + q]) and load_vec(jv, v)
+// indices); store_w(i, v) writes W; store_vec(jv, v) writes the K components of vector jv (W[off_vec + jv K + q]) and load_vec(jv, v)
 // reads vector jv back (the kernel serves the first few vectors, the ones re-read most often, from shared memory).
 template <int K, class LoadRFn, class LoadLamFn, class StoreLamFn, class StoreWFn, class StoreVecFn, class LoadVecFn>
 TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam, StoreLamFn&& store_lam, StoreWFn&& store_w,
@@ -571,12 +601,10 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam,
             {
                 double v[K];
                 load_vec(i - j_begin, v);
-                double dot = 0.0;
-                for (int q = 0; q < K; ++q) dot = fma(x[q], v[q], dot);
+                const double dot = dot4<K>(x, v);
                 for (int q = 0; q < K; ++q) x[q] = fma(-dot, v[q], x[q]);
             }
-            double xabs = 0.0;
-            for (int i = 0; i < K; ++i) xabs += fabs(x[i]);
+            const double xabs = abssum4<K>(x);
             const double scl = (double)K * onenrm * fmax(macheps, fmax(a_last, tol)) / fmax(xabs, 1e-300);
             // solve (dlagts): forward with L and the interchanges (scaling folded in), back substitution
             x[0] *= scl;
@@ -605,12 +633,10 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam,
             {
                 double v[K];
                 load_vec(i - j_begin, v);
-                double dot = 0.0;
-                for (int q = 0; q < K; ++q) dot = fma(x[q], v[q], dot);
+                const double dot = dot4<K>(x, v);
                 for (int q = 0; q < K; ++q) x[q] = fma(-dot, v[q], x[q]);
             }
-            double n2 = 0.0;
-            for (int i = 0; i < K; ++i) n2 = fma(x[i], x[i], n2);
+            const double n2 = dot4<K>(x, x);
             if (!(n2 > 0.0) || !(n2 < 1e300)) break;  // NaN, zero or overflow
             inv = 1.0 / sqrt(n2);
             double res = 0.0;
@@ -634,7 +660,11 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam,
             }
         }
         if (!converged) return PROJ_FALLBACK;
-        for (int i = 0; i < K; ++i) store_vec(jv, i, x[i] * inv);
+        {
+            double xn[K];
+            for (int i = 0; i < K; ++i) xn[i] = x[i] * inv;
+            store_vec(jv, xn);   // whole vector at once: the kernel forms the address of component 0 once and steps by the stride
+        }
         store_w(L::off_wgt + jv, wj);
         xjm = xj;
     }
@@ -755,7 +785,7 @@ TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const doubl
     code = proj_eigenvalues<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; });
     if (code == PROJ_FALLBACK) return code;
     code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i) { return R[L::off_lam + i]; }, [&](int i, double v) { R[L::off_lam + i] = v; },
-                                  [&](int i, double v) { Wb[i] = v; }, [&](int jv, int q, double v) { Wb[L::off_vec + jv * K + q] = v; },
+                                  [&](int i, double v) { Wb[i] = v; }, [&](int jv, const double (&v)[K]) { for (int q = 0; q < K; ++q) Wb[L::off_vec + jv * K + q] = v[q]; },
                                   [&](int jv, double (&v)[K]) { for (int q = 0; q < K; ++q) v[q] = Wb[L::off_vec + jv * K + q]; }, eps);
     if (code != PROJ_REBUILT) return code;
     proj_apply<K>([&](int i) { return R[i]; }, [&](int i) { return Wb[i]; }, load, store, eps);

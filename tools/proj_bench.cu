@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(128, MINB) kb2(int64_t n, int64_t stride, doub
     const int code = proj_select_vectors<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return rp[(int64_t)(L::off_lam + i) * stride]; },
                                             [&](int i, double v) { rp[(int64_t)(L::off_lam + i) * stride] = v; },
                                             [&](int i, double v) { wp[(int64_t)i * stride] = v; },
-                                            [&](int jv, int q, double v) { wp[(int64_t)(L::off_vec + jv * K + q) * stride] = v; },
+                                            [&](int jv, const double (&v)[K]) {
+                                                double* p = wp + (int64_t)(L::off_vec + jv * K) * stride;
+#pragma unroll
+                                                for (int q = 0; q < K; ++q) { *p = v[q]; p += stride; }
+                                            },
                                             [&](int jv, double (&v)[K]) {
                                                 const double* p = wp + (int64_t)(L::off_vec + jv * K) * stride;
 #pragma unroll
