@@ -1,4 +1,5 @@
-"""GPU: batched PSD projection kernel (tad_project_batch) vs the oracle / numpy for every instantiated k."""
+"""GPU: batched PSD projection kernel (tad_project_batch) vs the oracle / numpy for every instantiated k, and for sizes
+without a dedicated instantiation (run-time k Jacobi kernel: any k <= 32, e.g. d = 2 with N = 7, hexahedra k = 24)."""
 import numpy as np
 import pytest
 
@@ -41,7 +42,7 @@ def make_batch(k, n, rng):
     return np.array(mats)
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 18])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 18, 11, 14, 24, 32])
 @pytest.mark.parametrize("eps", [1e-9, -1.0])
 @pytest.mark.parametrize("method", [0, 1])
 def test_project_batch(torch_cuda, k, eps, method):

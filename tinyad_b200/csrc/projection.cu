@@ -485,6 +485,112 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
 }
 
 
+#if TAD_PROJ_PART == 0
+// Any k <= 32 without a dedicated instantiation (the Hessian projection is instantiated for k in {1..10, 12, 15, 16, 18}; the
+// reference projects any k, Utils/HessianProjection.hh:48-101): cyclic Jacobi with run-time k, the k x k work matrices A and V of a
+// thread in a global scratch laid out [entry][thread] (coalesced).  Correct for every k, not tuned -- the sizes the benchmarks and
+// the usual elements use (triangles, tets, edges, quads, one-rings) have the register-resident path above.
+constexpr int kGenericBlocks = 148 * 2, kGenericThreads = 128;
+__global__ void __launch_bounds__(kGenericThreads) project_kernel_generic(int k, double* __restrict__ hess, int64_t n, int64_t stride, double eps,
+                                                                          unsigned long long* counts, double* __restrict__ work)
+{
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = hess_size(k);
+    double* A = work + tid;                              // A(i, j) = A[(i * k + j) * nthreads]
+    double* V = work + (int64_t)k * k * nthreads + tid;  // V(i, j) likewise
+#define GA(i, j) A[(int64_t)((i) * k + (j)) * nthreads]
+#define GV(i, j) V[(int64_t)((i) * k + (j)) * nthreads]
+    for (int64_t el = tid; el < n; el += nthreads)
+    {
+        double* hp = hess + el;
+        // early-out 1: positive diagonally dominant (HessianProjection.hh:23-42)
+        bool dominant = true;
+        for (int i = 0; i < k && dominant; ++i)
+        {
+            double off = 0.0;
+            for (int j = 0; j < k; ++j)
+                if (j != i) off += fabs(hp[(int64_t)hess_seq_index(k, i, j) * stride]);
+            if (hp[(int64_t)hess_seq_index(k, i, i) * stride] < off + eps) dominant = false;
+        }
+        if (dominant) continue;
+        double nrm = 0.0;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j)
+            {
+                const double v = hp[(int64_t)hess_seq_index(k, i, j) * stride];
+                GA(i, j) = v;
+                GV(i, j) = i == j ? 1.0 : 0.0;
+                nrm += v * v;
+            }
+        if (!(nrm == nrm) || nrm > 1e300) continue;     // NaN / Inf: the caller's finite check reports it
+        for (int sweep = 0; sweep < 60; ++sweep)
+        {
+            double off = 0.0;
+            for (int p = 0; p < k; ++p)
+                for (int q = p + 1; q < k; ++q) { const double v = GA(p, q); off += v * v; }
+            if (off <= 1e-32 * nrm) break;
+            for (int p = 0; p < k - 1; ++p)
+                for (int q = p + 1; q < k; ++q)
+                {
+                    const double apq = GA(p, q);
+                    if (apq == 0.0) continue;
+                    const double theta = (GA(q, q) - GA(p, p)) / (2.0 * apq);
+                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                    for (int r = 0; r < k; ++r)
+                    {
+                        const double arp = GA(r, p), arq = GA(r, q);
+                        GA(r, p) = c * arp - sn * arq;
+                        GA(r, q) = sn * arp + c * arq;
+                    }
+                    for (int r = 0; r < k; ++r)
+                    {
+                        const double apr = GA(p, r), aqr = GA(q, r);
+                        GA(p, r) = c * apr - sn * aqr;
+                        GA(q, r) = sn * apr + c * aqr;
+                    }
+                    for (int r = 0; r < k; ++r)
+                    {
+                        const double vrp = GV(r, p), vrq = GV(r, q);
+                        GV(r, p) = c * vrp - sn * vrq;
+                        GV(r, q) = sn * vrp + c * vrq;
+                    }
+                }
+        }
+        if (counts) atomicAdd(&counts[0], 1ull);
+        // H += sum over the moved eigenpairs of (target - l) v v^T: leaves H bit-unchanged when nothing moves (:94-95)
+        bool moved = false;
+        for (int j = 0; j < k; ++j)
+        {
+            const double lam = GA(j, j);
+            const bool mv = eps < 0.0 ? lam < 0.0 : lam < eps;
+            if (!mv) continue;
+            moved = true;
+            const double w = eps < 0.0 ? -2.0 * lam : eps - lam;
+            for (int s = 0; s < h; ++s)
+            {
+                const TinyAD::detail::HessRC rc = hess_seq_rc(k, s);
+                hp[(int64_t)s * stride] = fma(w * GV(rc.row, j), GV(rc.col, j), hp[(int64_t)s * stride]);
+            }
+        }
+        if (moved && counts) atomicAdd(&counts[1], 1ull);
+    }
+#undef GA
+#undef GV
+}
+
+size_t project_scratch_doubles_generic(int k) { return (size_t)2 * k * k * kGenericBlocks * kGenericThreads; }
+
+int launch_project_generic(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, cudaStream_t st)
+{
+    if (k < 1 || k > 32) return fail(TAD_NOT_SUPPORTED, "Hessian projection supports at most 32 variables per element");
+    count_launch();
+    project_kernel_generic<<<kGenericBlocks, kGenericThreads, 0, st>>>(k, hess, n, stride, eps, counts, scratch_d);
+    return cudaGetLastError() == cudaSuccess ? TAD_OK : fail(TAD_CUDA_ERROR, "project kernel launch failed");
+}
+#endif  // TAD_PROJ_PART == 0
+
 #define TAD_INST(K)                                                                                                                         \
     template size_t project_scratch_doubles<K>(int64_t);                                                                                    \
     template int launch_project<K>(double*, int64_t, int64_t, double, unsigned long long*, double*, int32_t*, int64_t*, bool, ProjScratch*, \

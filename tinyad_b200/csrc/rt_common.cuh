@@ -203,6 +203,8 @@ template <int K> size_t project_scratch_doubles(int64_t stride);
 template <int K>
 int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, int32_t* codes,
                    int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st);
+size_t project_scratch_doubles_generic(int k);   // k without a dedicated instantiation (run-time k Jacobi, projection.cu)
+int launch_project_generic(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, cudaStream_t st);
 size_t project_scratch_doubles_rt(int k, int64_t stride);
 int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d,
                      int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st);

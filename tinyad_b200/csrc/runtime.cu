@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(1024) reduce_stage2(const double* partial, int
 
 namespace tadrt
 {
+// k with a dedicated (register-resident) instantiation of the projection kernels; every other k <= 32 runs the run-time k kernel
+bool project_has_instance(int k) { return (k >= 1 && k <= 10) || k == 12 || k == 15 || k == 16 || k == 18; }
+
 size_t project_scratch_doubles_rt(int k, int64_t stride)
 {
     switch (k)
@@ -162,7 +165,7 @@ size_t project_scratch_doubles_rt(int k, int64_t stride)
     case 15: return project_scratch_doubles<15>(stride);
     case 16: return project_scratch_doubles<16>(stride);
     case 18: return project_scratch_doubles<18>(stride);
-    default: return 0;
+    default: return (k >= 1 && k <= 32) ? project_scratch_doubles_generic(k) : 0;
     }
 }
 
@@ -186,7 +189,7 @@ int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps,
     case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
     case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
     case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    default: return fail(TAD_NOT_SUPPORTED, "Hessian projection is instantiated for k in {1..10,12,15,16,18}");
+    default: return launch_project_generic(k, hess, n, stride, eps, counts, scratch_d, st);   // any other k <= 32: run-time k Jacobi
     }
 }
 }  // namespace tadrt
@@ -1159,7 +1162,8 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         {
             TAD_CUDA(L.proj_list.ensure((size_t)sstride));
             TAD_CUDA(L.proj_codes.ensure((size_t)sstride));
-            if (!f->projection_full) TAD_CUDA(L.proj_scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(t.k, sstride))));
+            if (!f->projection_full || !project_has_instance(t.k))
+                TAD_CUDA(L.proj_scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(t.k, sstride))));
             TAD_CUDA(cudaMemsetAsync(L.counts.p + 2, 0, sizeof(unsigned long long), ls));  // the list of the full solver is per slab
             TAD_TRY(project_dispatch(t.k, a.hess, sl.n, sstride, eps, L.counts.p, L.proj_scratch.p, L.proj_codes.p, L.proj_list.p,
                                      f->projection_full != 0, fuse ? &fused_sc : nullptr, fuse ? &L.side : nullptr, ls));
@@ -1790,7 +1794,7 @@ int tad_project_batch(int k, int64_t n, int64_t stride, double* hess_dev, double
     DevBuf<int32_t> codes;
     TAD_CUDA(list.ensure((size_t)std::max<int64_t>(stride, 1)));
     TAD_CUDA(codes.ensure((size_t)std::max<int64_t>(stride, 1)));
-    if (method != 1) TAD_CUDA(scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(k, stride))));
+    if (method != 1 || !project_has_instance(k)) TAD_CUDA(scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(k, stride))));
     TAD_TRY(project_dispatch(k, hess_dev, n, stride, eps, counts, scratch.p, codes.p, list.p, method == 1, nullptr, nullptr, st));
     TAD_CUDA(cudaStreamSynchronize(st));  // the scratch buffers above are locals
     return TAD_OK;

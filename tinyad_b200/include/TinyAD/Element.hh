@@ -86,10 +86,19 @@ struct Element
             detail::raise(err, TINYAD_ERR_TOO_MANY_VARIABLES);  // Element.hh:237-238
             slot = N - 1;
         }
-        // compared without a branch and reported once, after the functor (check_recorded_count): a branch here would sit between the
-        // load of the recorded handle and the loads of x, and the GPU does not speculate -- every variables() call then costs two
-        // dependent memory round trips instead of one (measured: +40 % on the first tet kernel)
-        if (rec) mismatch = mismatch || ((int64_t)rec[slot * rec_stride] != vh);
+        // The recorded handle is only LOADED here; the comparison happens after the functor (check_recorded_count).  A warp issues
+        // in order, so any instruction consuming the load right here -- a branch, or even a branch-free compare -- makes every
+        // variables() call wait for a second memory round trip before the loads of x can issue (ncu: +40 % on the first tet
+        // kernel, 35 % of its stall samples on this line).
+        if (rec)
+        {
+            if constexpr (Dedup) mismatch = mismatch || ((int64_t)rec[slot * rec_stride] != vh);   // run-time slot: compare at once
+            else
+            {
+                rec_val[slot] = rec[slot * rec_stride];
+                req_val[slot] = (int32_t)vh;
+            }
+        }
         const double* xv = x + d * vh;
         VariableVectorType v;
         detail::static_for<d>([&](auto ic) TINYAD_LAMBDA_INLINE {
@@ -133,13 +142,23 @@ struct Element
     const int32_t* rec;
     int64_t rec_stride;
     bool mismatch;  // some variables() call requested another handle than the recorded one
+    int32_t rec_val[Dedup ? 1 : N], req_val[Dedup ? 1 : N];  // recorded / requested handle of every slot, compared after the functor
     int64_t seen[Dedup ? N : 1];
 
     // after the functor ran: did it request the recorded handles, and exactly the recorded number of (distinct) handles?
     TINYAD_HD TINYAD_INLINE void check_recorded_count(int32_t recorded) const
     {
         const int want = recorded < 0 ? -recorded - 1 : recorded;  // < 0 marks "a handle was requested more than once"
-        if (mismatch || (Dedup ? (n_used != want) : (recorded >= 0 && n_used != want))) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
+        bool bad = mismatch;
+        if constexpr (!Dedup)
+        {
+            if (rec)
+                detail::static_for<N>([&](auto jc) TINYAD_LAMBDA_INLINE {
+                    constexpr int j = decltype(jc)::value;
+                    if (j < n_used && rec_val[j] != req_val[j]) bad = true;
+                });
+        }
+        if (bad || (Dedup ? (n_used != want) : (recorded >= 0 && n_used != want))) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
     }
 };
 

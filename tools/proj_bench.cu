@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(128) ka(const double* hess, int64_t n, int64_t
     double* rp = R + el;
     codes[el] = proj_tridiagonalize<K>([&](int s) { return hp[(int64_t)s * stride]; }, [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
 }
-__global__ void __launch_bounds__(128) kb1(int64_t n, int64_t stride, double* R, int* codes)
+#ifndef B1_MINB
+#define B1_MINB 1
+#endif
+__global__ void __launch_bounds__(128, B1_MINB) kb1(int64_t n, int64_t stride, double* R, int* codes)
 {
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
