@@ -437,6 +437,7 @@ SCALAR_CASES = [
     "c_mul", "c_mul_d", "c_d_mul", "c_div", "c_div_d", "c_add", "c_sub", "c_sqr", "c_conj", "c_abs", "c_arg", "symm_dirich6",
     "svd2", "closest_orthogonal2",
     "fmin", "fmax", "clamp_d", "cmp", "isnan_isinf",
+    "hess_block_issue13", "hess_block_symdir",
 ]
 
 

@@ -328,11 +328,12 @@ enum ScalarCase
     SC_C_MUL, SC_C_MUL_D, SC_C_D_MUL, SC_C_DIV, SC_C_DIV_D, SC_C_ADD, SC_C_SUB, SC_C_SQR, SC_C_CONJ, SC_C_ABS, SC_C_ARG, SC_SYMM_DIRICH6,
     SC_SVD2, SC_CLOSEST_ORTHOGONAL2,
     SC_FMIN, SC_FMAX, SC_CLAMP_D, SC_CMP, SC_ISNAN_ISINF,   // tests/ScalarTestComparison.cc
+    SC_HESS_BLOCK_ISSUE13, SC_HESS_BLOCK_SYMDIR,             // tests/ScalarTestHessianBlock.cc
     SC_COUNT
 };
 
-template <int k>
-TINYAD_HD inline void sc_put(const Scalar<k, true>& s, double*& out)
+template <int k, int NP, int P>
+TINYAD_HD inline void sc_put(const Scalar<k, true, NP, P>& s, double*& out)
 {
     *out++ = s.val;
     for (int i = 0; i < k; ++i) *out++ = s.grad[i];
@@ -481,6 +482,51 @@ TINYAD_HD inline int scalar_case_run(int id, const double* p, double* out)
         A6 E = J.squaredNorm() + J.inverse().squaredNorm();
         sc_put(E, out);
         return 1;
+    }
+    if (id == SC_HESS_BLOCK_ISSUE13)  // tests/ScalarTestHessianBlock.cc:12-45: f = y3 ((x1 - y1)^2 + (x2 - y2)^2), block d2f / dx dy = (0, 2, 2, 3)
+    {
+        auto fn = [&](auto tag) {
+            using T = typename decltype(tag)::type;
+            const T x1(p[0], 0), x2(p[1], 1), y1(p[2], 2), y2(p[3], 3), y3(p[4], 4);
+            const T r1 = x1 - y1, r2 = x2 - y2;
+            return y3 * (r1 * r1 + r2 * r2);
+        };
+        struct FullTag { using type = Scalar<5, true>; };
+        struct BlockTag { using type = ScalarHessianBlock<5, 0, 2, 2, 3>; };
+        sc_put(fn(FullTag{}), out);
+        sc_put(fn(BlockTag{}), out);
+        return 2;
+    }
+    if (id == SC_HESS_BLOCK_SYMDIR)   // tests/ScalarTestHessianBlock.cc:50-100: symmetric Dirichlet, k = 6; p[12] selects the block
+    {
+        Vec<double, 2> ar(p[6], p[7]), br(p[8], p[9]), cr(p[10], p[11]);
+        Mat<double, 2, 2> Mr = col_mat(br - ar, cr - ar);
+        auto fn = [&](auto tag) {
+            using T = typename decltype(tag)::type;
+            Vec<T, 2> va(T(p[0], 0), T(p[1], 1)), vb(T(p[2], 2), T(p[3], 3)), vc(T(p[4], 4), T(p[5], 5));
+            Mat<T, 2, 2> M = col_mat(vb - va, vc - va);
+            Mat<T, 2, 2> J = M * Mr.inverse();
+            T E = J.squaredNorm() + J.inverse().squaredNorm();
+            return E;
+        };
+        struct FullTag { using type = Scalar<6, true>; };
+        struct B0 { using type = ScalarHessianBlock<6, 0, 0, 0, 0>; };
+        struct B1 { using type = ScalarHessianBlock<6, 0, 0, 6, 6>; };
+        struct B2 { using type = ScalarHessianBlock<6, 0, 0, 3, 1>; };
+        struct B3 { using type = ScalarHessianBlock<6, 0, 0, 1, 3>; };
+        struct B4 { using type = ScalarHessianBlock<6, 2, 2, 2, 2>; };
+        struct B5 { using type = ScalarHessianBlock<6, 1, 4, 5, 2>; };
+        sc_put(fn(FullTag{}), out);
+        switch ((int)p[12])
+        {
+        case 0: sc_put(fn(B0{}), out); break;
+        case 1: sc_put(fn(B1{}), out); break;
+        case 2: sc_put(fn(B2{}), out); break;
+        case 3: sc_put(fn(B3{}), out); break;
+        case 4: sc_put(fn(B4{}), out); break;
+        default: sc_put(fn(B5{}), out); break;
+        }
+        return 2;
     }
     if (id == SC_SVD2 || id == SC_CLOSEST_ORTHOGONAL2)  // tests/SVDTest.cc:9-97, Scalar<4>: A = [[p0, p1], [p2, p3]]
     {

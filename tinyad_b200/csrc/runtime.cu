@@ -71,6 +71,7 @@ struct tad_function_s
     cudaStream_t caller_stream = nullptr;
     bool wait_caller = false;      // tad_function_set_caller_stream
     std::vector<Lane> lanes;
+    std::vector<Lane> prio_lane;           // 0 or 1 lane with high stream priority (partitioned functions: the slabs the exchange waits for)
     std::vector<cudaEvent_t> slab_events;  // one per slab of the schedule: "this slab is assembled"
     cudaStream_t copy_stream = nullptr;    // device -> host copies of finished rows (host-buffer entry points)
     // multi-GPU (tad_function_set_comm): the halo plan is built with the pattern; all NCCL calls of an evaluation go to comm_stream
@@ -79,6 +80,7 @@ struct tad_function_s
     int replicate_gradient = 0;            // TAD_OPT_REPLICATE_GRADIENT
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_comm[2] = {nullptr, nullptr};   // main stream -> comm stream, comm stream -> main stream
+    cudaEvent_t ev_trace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // TAD_COMM_TRACE=1: timeline of the exchange
     std::recursive_mutex mtx;      // eval* may be called concurrently (ScalarFunctionTest.cc:255-291): calls on one function are serialised
 };
 
@@ -1033,21 +1035,41 @@ int build_schedule(tad_function f, int mode, bool whole_terms, bool host_path, t
     return TAD_OK;
 }
 
+int create_lane(Lane& L, bool high_priority)
+{
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);   // numerically lower = higher priority
+    const int prio = high_priority ? greatest : least;
+    TAD_CUDA(cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio));
+    if (cudaStreamCreateWithPriority(&L.side.stream, cudaStreamNonBlocking, prio) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L.side.ev_b, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L.side.ev_list, cudaEventDisableTiming) != cudaSuccess)
+        L.side = ProjSide();  // no side stream: the list kernel stays on the lane's stream
+    for (auto& e : L.tev) TAD_CUDA(cudaEventCreate(&e));
+    TAD_CUDA(L.counts.ensure(4));
+    return TAD_OK;
+}
+
 int ensure_lanes(tad_function f, int n)
 {
     while ((int)f->lanes.size() < n)
     {
         f->lanes.emplace_back();
-        Lane& L = f->lanes.back();
-        TAD_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-        if (cudaStreamCreateWithFlags(&L.side.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&L.side.ev_b, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&L.side.ev_list, cudaEventDisableTiming) != cudaSuccess)
-            L.side = ProjSide();  // no side stream: the list kernel stays on the lane's stream
-        for (auto& e : L.tev) TAD_CUDA(cudaEventCreate(&e));
-        TAD_CUDA(L.counts.ensure(4));
+        TAD_TRY(create_lane(f->lanes.back(), false));
     }
     return TAD_OK;
+}
+
+// Partitioned functions: the slabs the exchange waits for (the halo slabs, at least the first slab) run on a lane of their own with
+// HIGH stream priority.  On equal-priority lanes a slab shares the GPU with the next one and finishes at ~2/3 of a three-slab step
+// (5 M tets per rank: 9.8 of 15 ms), which left the exchange little to hide behind -- and a rank with nothing to send posted its
+// receive at t = 0, whose spinning NCCL kernel then took SM resources from the assembly for 10 ms (rank 0 was 5 % slower than
+// rank 1).  With the priority lane all ranks reach the exchange after about one slab's time.
+int ensure_prio_lane(tad_function f)
+{
+    if (!f->prio_lane.empty()) return TAD_OK;
+    f->prio_lane.emplace_back();
+    return create_lane(f->prio_lane.back(), true);
 }
 
 int ensure_slab_events(tad_function f, size_t n)
@@ -1098,6 +1120,14 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     const int n_lanes = std::max(1, std::min((f->timing || gather) ? 1 : want_lanes, std::max(n_slabs, 1)));
     TAD_TRY(ensure_lanes(f, n_lanes));
     TAD_TRY(ensure_slab_events(f, (size_t)n_slabs));
+    // partitioned: the first n_first slabs (the halo slabs; at least one, so that all ranks reach the exchange together) on the priority lane
+    static const bool prio_enabled = [] { const char* e = getenv("TAD_PRIORITY_LANE"); return !e || atoi(e) != 0; }();
+    const int n_first = (partitioned && prio_enabled && !f->timing && !gather && n_slabs > 1 && mode >= TAD_MODE_FIRST)
+                            ? std::min(n_slabs - 1, std::max(1, schedule->n_halo_slabs)) : 0;
+    if (n_first > 0) TAD_TRY(ensure_prio_lane(f));
+    std::vector<Lane*> active_lanes;
+    for (int l = 0; l < n_lanes; ++l) active_lanes.push_back(&f->lanes[(size_t)l]);
+    if (n_first > 0) active_lanes.push_back(&f->prio_lane[0]);
 
     // partial sums of f: one per 256 elements, laid out term by term (independent of the slab size)
     std::vector<int64_t> part_off((size_t)n_terms + 1, 0);
@@ -1105,9 +1135,9 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     TAD_CUDA(f->fpart.ensure((size_t)std::max<int64_t>(1, part_off[(size_t)n_terms])));
 
     TAD_CUDA(cudaEventRecord(f->ev[0], st));
-    for (int l = 0; l < n_lanes; ++l)
+    for (Lane* Lp : active_lanes)
     {
-        Lane& L = f->lanes[(size_t)l];
+        Lane& L = *Lp;
         TAD_CUDA(cudaStreamWaitEvent(L.stream, f->ev[0], 0));
         if (mode == TAD_MODE_SECOND && project) TAD_CUDA(cudaMemsetAsync(L.counts.p, 0, 4 * sizeof(unsigned long long), L.stream));
     }
@@ -1116,7 +1146,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     {
         const Slab& sl = sched[(size_t)q];
         Term& t = f->terms[(size_t)sl.term];
-        Lane& L = f->lanes[(size_t)(q % n_lanes)];
+        Lane& L = q < n_first ? f->prio_lane[0] : f->lanes[(size_t)((q - n_first) % n_lanes)];
         cudaStream_t ls = L.stream;
         const int64_t sstride = ((sl.n + 31) / 32) * 32;
         DevBuf<double>& stage = gather ? t.stage : L.stage;
@@ -1189,6 +1219,11 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     // multi-GPU: as soon as the slabs that touch halo rows are assembled (scheduled first), their H values and g entries travel to
     // the owners on the communication stream, and what the peers send is added into this rank's rows -- next to the assembly of
     // the remaining slabs (atomics on both sides)
+    // TAD_COMM_TRACE=1 (development): timeline of the exchange of every partitioned second-order evaluation on stderr
+    static const bool comm_trace_env = [] { const char* e = getenv("TAD_COMM_TRACE"); return e && atoi(e) != 0; }();
+    const bool comm_trace = comm_trace_env && partitioned && mode == TAD_MODE_SECOND && !gather;
+    if (comm_trace && !f->ev_trace[0])
+        for (auto& e : f->ev_trace) TAD_CUDA(cudaEventCreate(&e));
     const bool halo_g = partitioned && mode >= TAD_MODE_FIRST && !f->replicate_gradient;
     const bool halo_h = partitioned && mode == TAD_MODE_SECOND;
     if ((halo_g || halo_h) && !gather)
@@ -1197,15 +1232,19 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         cudaStream_t cs = f->comm_stream;
         const int W = f->comm->world;
         TAD_CUDA(cudaStreamWaitEvent(cs, f->ev[0], 0));
-        for (int q = 0; q < std::min(schedule->n_halo_slabs, n_slabs); ++q) TAD_CUDA(cudaStreamWaitEvent(cs, f->slab_events[(size_t)q], 0));
+        for (int q = 0; q < std::min(std::max(schedule->n_halo_slabs, n_first), n_slabs); ++q) TAD_CUDA(cudaStreamWaitEvent(cs, f->slab_events[(size_t)q], 0));
+        if (comm_trace) cudaEventRecord(f->ev_trace[0], cs);   // halo slabs assembled
         TAD_TRY(halo_pack(halo_h ? Hv : nullptr, halo_g ? g : nullptr, P.send_base.p, P.send_rs.p, P.send_blk_off[(size_t)W], P.send_vtx.p,
                           P.send_vtx_off[(size_t)W], f->d, P.send_h.p, P.send_g.p, cs));
         TAD_TRY(comm_group_begin());
         if (halo_h) TAD_TRY(comm_exchange(f->comm, P.send_h.p, P.send_h_off.data(), P.recv_h.p, P.recv_h_off.data(), (int)sizeof(double), cs));
         if (halo_g) TAD_TRY(comm_exchange(f->comm, P.send_g.p, P.send_g_off.data(), P.recv_g.p, P.recv_g_off.data(), (int)sizeof(double), cs));
+        if (comm_trace) cudaEventRecord(f->ev_trace[1], cs);   // packed
         TAD_TRY(comm_group_end());
+        if (comm_trace) cudaEventRecord(f->ev_trace[2], cs);   // exchanged
         TAD_TRY(halo_add(halo_h ? Hv : nullptr, halo_g ? g : nullptr, P.recv_base.p, P.recv_rs.p, P.recv_blk_off[(size_t)W], P.recv_vtx.p,
                          P.recv_vtx_off[(size_t)W], f->d, P.recv_h.p, P.recv_g.p, cs));
+        if (comm_trace) cudaEventRecord(f->ev_trace[3], cs);   // added
     }
     // pipelined D2H of the rows that are final (all slabs are queued by now, so a pageable destination, whose copies block the
     // host, cannot starve the GPU)
@@ -1223,6 +1262,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         }
     // the main stream continues after the last slab of every lane
     for (int q = std::max(0, n_slabs - n_lanes); q < n_slabs; ++q) TAD_CUDA(cudaStreamWaitEvent(st, f->slab_events[(size_t)q], 0));
+    if (n_first > 0) TAD_CUDA(cudaStreamWaitEvent(st, f->slab_events[(size_t)n_first - 1], 0));   // ... and of the priority lane
     for (int ti = 0; ti < n_terms; ++ti)
     {
         const int64_t nb = part_off[(size_t)ti + 1] - part_off[(size_t)ti];
@@ -1253,6 +1293,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         cudaStream_t cs = f->comm_stream;
         const int W = f->comm->world;
         TAD_CUDA(cudaEventRecord(f->ev_comm[0], st));
+        if (comm_trace) cudaEventRecord(f->ev_trace[4], st);   // all slabs assembled, f reduced
         TAD_CUDA(cudaStreamWaitEvent(cs, f->ev_comm[0], 0));
         if ((halo_g || halo_h) && gather)
         {
@@ -1268,6 +1309,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         }
         if (n_terms) TAD_TRY(comm_allreduce_sum_f64(f->comm, f->fterm.p, n_terms, cs));
         if (mode >= TAD_MODE_FIRST && f->replicate_gradient) TAD_TRY(comm_allreduce_sum_f64(f->comm, g, f->n_vars, cs));
+        if (comm_trace) cudaEventRecord(f->ev_trace[5], cs);   // f all-reduced
         TAD_CUDA(cudaEventRecord(f->ev_comm[1], cs));
         TAD_CUDA(cudaStreamWaitEvent(st, f->ev_comm[1], 0));
     }
@@ -1285,21 +1327,29 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     std::vector<double> fterm((size_t)std::max(n_terms, 1), 0.0);
     if (n_terms)
         TAD_CUDA(cudaMemcpyAsync(fterm.data(), f->fterm.p, (size_t)n_terms * sizeof(double), cudaMemcpyDeviceToHost, st));
-    unsigned long long lane_counts[4][4] = {};
+    unsigned long long lane_counts[5][4] = {};
     if (mode == TAD_MODE_SECOND && project)
-        for (int l = 0; l < n_lanes; ++l)
-            TAD_CUDA(cudaMemcpyAsync(lane_counts[l], f->lanes[(size_t)l].counts.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        for (size_t l = 0; l < active_lanes.size(); ++l)
+            TAD_CUDA(cudaMemcpyAsync(lane_counts[l], active_lanes[l]->counts.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     TAD_CUDA(cudaStreamSynchronize(st));
     if (hc) TAD_CUDA(cudaStreamSynchronize(f->copy_stream));
     if (mode == TAD_MODE_SECOND && project)
     {
         f->last_proj[0] = f->last_proj[1] = f->last_proj[2] = 0;
-        for (int l = 0; l < n_lanes; ++l)
+        for (size_t l = 0; l < active_lanes.size(); ++l)
         {
             f->last_proj[0] += (int64_t)lane_counts[l][0];
             f->last_proj[1] += (int64_t)lane_counts[l][1];
             f->last_proj[2] += (int64_t)lane_counts[l][3];
         }
+    }
+    if (comm_trace)
+    {
+        float t[6] = {0, 0, 0, 0, 0, 0}, total = 0;
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], f->ev[0], f->ev_trace[i]);
+        cudaEventElapsedTime(&total, f->ev[0], f->ev[1]);
+        fprintf(stderr, "[tad comm trace] rank %d: halo slabs done %.3f | packed %.3f | exchanged %.3f | added %.3f | all slabs + f %.3f | f all-reduced %.3f | end %.3f ms (slabs %d, halo slabs %d)\n",
+                f->comm->rank, t[0], t[1], t[2], t[3], t[4], t[5], total, n_slabs, schedule->n_halo_slabs);
     }
     if (f->timing)
     {
@@ -1440,7 +1490,8 @@ int tad_function_create(int variable_dimension, int64_t n_handles, int is_vector
     if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess || f->err.ensure(8) != cudaSuccess ||
         cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&f->ev[0]) != cudaSuccess ||
         cudaEventCreate(&f->ev[1]) != cudaSuccess || cudaEventCreateWithFlags(&f->ev_caller, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&f->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        [&] { int least = 0, greatest = 0; cudaDeviceGetStreamPriorityRange(&least, &greatest);
+              return cudaStreamCreateWithPriority(&f->comm_stream, cudaStreamNonBlocking, greatest); }() != cudaSuccess ||   // pack / add kernels must not queue behind the assembly
         cudaEventCreateWithFlags(&f->ev_comm[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&f->ev_comm[1], cudaEventDisableTiming) != cudaSuccess)
     {
@@ -1459,7 +1510,8 @@ void tad_function_destroy(tad_function f)
     for (auto& t : f->terms)
         if (t.user_free && t.user) t.user_free(t.user);
     f->terms.clear();
-    for (auto& L : f->lanes)
+    for (auto* lanes : {&f->lanes, &f->prio_lane})
+      for (auto& L : *lanes)
     {
         if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         if (L.side.ev_b) cudaEventDestroy(L.side.ev_b);
@@ -1473,6 +1525,7 @@ void tad_function_destroy(tad_function f)
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->comm_stream) { cudaStreamSynchronize(f->comm_stream); cudaStreamDestroy(f->comm_stream); }
     for (auto& e : f->ev_comm) if (e) cudaEventDestroy(e);
+    for (auto& e : f->ev_trace) if (e) cudaEventDestroy(e);
     if (f->stream) cudaStreamDestroy(f->stream);
     delete f;  // device buffers are freed here, still under the device guard
 }

@@ -45,31 +45,83 @@ TINYAD_HD TINYAD_INLINE void acc(double& h, bool& have, double t)
     h = have ? h + t : t;
     have = true;
 }
-// (row, col) of the e-th packed entry held by part P of NP (free functions: usable inside generic lambdas of friends)
+// Which packed Hessian entries a Scalar<k, true, NP, P> carries:
+//   NP >= 1:  part P of NP, a contiguous cut of the tile order (the cooperating-thread split of the element kernels);
+//   NP == -1: the TRUNCATED HESSIAN BLOCK of the reference (Scalar.hh:24,31-38,188-196: hess_row_start, hess_col_start,
+//             hess_rows, hess_cols), P = hess_block_code(r0, c0, nr, nc): the packed entries (i, j) ~ (j, i) with one index in the
+//             row range and the other in the column range.  Entry (i, j) of a result only depends on entry (i, j) and gradient
+//             components i, j of the operands, so every operator works on any such subset unchanged.
+TINYAD_HD constexpr int hess_block_code(int r0, int c0, int nr, int nc) { return r0 | (c0 << 6) | (nr << 12) | (nc << 18); }
+TINYAD_HD constexpr bool hess_block_has(int code, int i, int j)
+{
+    const int r0 = code & 63, c0 = (code >> 6) & 63, nr = (code >> 12) & 63, nc = (code >> 18) & 63;
+    return (i >= r0 && i < r0 + nr && j >= c0 && j < c0 + nc) || (j >= r0 && j < r0 + nr && i >= c0 && i < c0 + nc);
+}
+// number of selected packed entries
+TINYAD_HD constexpr int hess_sel_count(int k, bool wh, int np, int p)
+{
+    if (!wh) return 0;
+    if (np >= 1) return hess_part_begin(k, np, p + 1) - hess_part_begin(k, np, p);
+    int n = 0;
+    for (int s = 0; s < hess_size(k); ++s) n += hess_block_has(p, hess_seq_rc(k, s).row, hess_seq_rc(k, s).col) ? 1 : 0;
+    return n;
+}
+// tile-order index of the e-th selected entry
+TINYAD_HD constexpr int hess_sel_seq(int k, bool wh, int np, int p, int e)
+{
+    if (np >= 1) return (wh ? hess_part_begin(k, np, p) : 0) + e;
+    int n = 0;
+    for (int s = 0; s < hess_size(k); ++s)
+        if (hess_block_has(p, hess_seq_rc(k, s).row, hess_seq_rc(k, s).col))
+        {
+            if (n == e) return s;
+            ++n;
+        }
+    return -1;
+}
+// position of tile-order index s among the selected entries, -1 if it is not selected
+TINYAD_HD constexpr int hess_sel_local(int k, bool wh, int np, int p, int s)
+{
+    if (!wh) return -1;
+    if (np >= 1)
+    {
+        const int b = hess_part_begin(k, np, p), e = hess_part_begin(k, np, p + 1);
+        return (s >= b && s < e) ? s - b : -1;
+    }
+    int n = 0;
+    for (int q = 0; q < hess_size(k); ++q)
+        if (hess_block_has(p, hess_seq_rc(k, q).row, hess_seq_rc(k, q).col))
+        {
+            if (q == s) return n;
+            ++n;
+        }
+    return -1;
+}
+// (row, col) of the e-th packed entry held by the scalar (free functions: usable inside generic lambdas of friends)
 template <int k, bool wh, int NP, int P>
-TINYAD_HD constexpr int part_row(int e) { return hess_seq_rc(k, (wh ? hess_part_begin(k, NP, P) : 0) + e).row; }
+TINYAD_HD constexpr int part_row(int e) { return hess_seq_rc(k, hess_sel_seq(k, wh, NP, P, e)).row; }
 template <int k, bool wh, int NP, int P>
-TINYAD_HD constexpr int part_col(int e) { return hess_seq_rc(k, (wh ? hess_part_begin(k, NP, P) : 0) + e).col; }
+TINYAD_HD constexpr int part_col(int e) { return hess_seq_rc(k, hess_sel_seq(k, wh, NP, P, e)).col; }
 }  // namespace detail
 
 template <int k, bool with_hessian = true, int NP = 1, int P = 0>
 struct Scalar
 {
     static_assert(k >= 0 && k <= 32, "static k <= 32 only (dynamic mode of Scalar.hh:30 is out of scope)");
-    static_assert(NP >= 1 && P >= 0 && P < NP, "bad Hessian partition");
+    static_assert((NP >= 1 && P >= 0 && P < NP) || (NP == -1 && with_hessian && P >= 0), "bad Hessian partition / block");
     static constexpr int k_ = k;
     static constexpr bool with_hessian_ = with_hessian;
     static constexpr int n_parts_ = NP;
     static constexpr int part_ = P;
-    static constexpr int h_begin = with_hessian ? detail::hess_part_begin(k, NP, P) : 0;
-    static constexpr int h_end = with_hessian ? detail::hess_part_begin(k, NP, P + 1) : 0;
-    static constexpr int nh = h_end - h_begin;  // packed entries held by this part
+    static constexpr bool truncated_hessian_ = NP == -1;   // Scalar.hh:34
+    static constexpr int h_begin = (with_hessian && NP >= 1) ? detail::hess_part_begin(k, NP, P) : 0;   // parts only (staging index)
+    static constexpr int nh = detail::hess_sel_count(k, with_hessian, NP, P);  // packed entries held by this scalar
     static constexpr int HW = nh > 0 ? (nh + 63) / 64 : 1;
     static constexpr uint32_t g_all = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
 
     // (row, col) of local packed entry e
-    TINYAD_HD static constexpr int row(int e) { return detail::hess_seq_rc(k, h_begin + e).row; }
-    TINYAD_HD static constexpr int col(int e) { return detail::hess_seq_rc(k, h_begin + e).col; }
+    TINYAD_HD static constexpr int row(int e) { return detail::hess_seq_rc(k, detail::hess_sel_seq(k, with_hessian, NP, P, e)).row; }
+    TINYAD_HD static constexpr int col(int e) { return detail::hess_seq_rc(k, detail::hess_sel_seq(k, with_hessian, NP, P, e)).col; }
 
     // ---- data (Scalar.hh:1341-1346) ----
     double val;
@@ -133,8 +185,14 @@ struct Scalar
     // Hessian entry (i, j); only valid for entries owned by this part (all of them for NP == 1).
     TINYAD_HD double Hess(int i, int j) const
     {
-        const int s = detail::hess_seq_index(k, i, j) - h_begin;
-        return (with_hessian && s >= 0 && s < nh) ? hess[s] : 0.0;
+        const int s = detail::hess_sel_local(k, with_hessian, NP, P, detail::hess_seq_index(k, i, j));
+        return s >= 0 ? hess[s] : 0.0;
+    }
+    // Truncated block (NP == -1): entry (i, j) of the hess_rows x hess_cols block, i.e. d^2 f / dx_{r0+i} dx_{c0+j} (Scalar.hh:188-196)
+    TINYAD_HD double HessBlock(int i, int j) const
+    {
+        static_assert(NP == -1, "HessBlock() belongs to truncated-Hessian scalars");
+        return Hess((P & 63) + i, ((P >> 6) & 63) + j);
     }
 
     // ---- chain rule (Scalar.hh:199-214) ----
@@ -543,6 +601,11 @@ using Double = Scalar<k, with_hessian>;
 
 // Utils/ToPassive.hh:15-30, Scalar.hh:1368-1369
 TINYAD_HD TINYAD_INLINE double to_passive(const double& a) { return a; }
+// Scalar<k, double, true, hess_row_start, hess_col_start, hess_rows, hess_cols> of the reference (Scalar.hh:24-38): only the
+// selected block of the Hessian is computed and stored; read it with HessBlock(i, j).
+template <int k, int hess_row_start, int hess_col_start, int hess_rows, int hess_cols>
+using ScalarHessianBlock = Scalar<k, true, -1, detail::hess_block_code(hess_row_start, hess_col_start, hess_rows, hess_cols)>;
+
 template <int k, bool wh, int NP, int P>
 TINYAD_HD TINYAD_INLINE double to_passive(const Scalar<k, wh, NP, P>& a) { return a.val; }
 TINYAD_HD TINYAD_INLINE double sqr(const double& x) { return x * x; }
