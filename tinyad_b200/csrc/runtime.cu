@@ -1060,11 +1060,9 @@ int ensure_lanes(tad_function f, int n)
     return TAD_OK;
 }
 
-// Partitioned functions: the slabs the exchange waits for (the halo slabs, at least the first slab) run on a lane of their own with
-// HIGH stream priority.  On equal-priority lanes a slab shares the GPU with the next one and finishes at ~2/3 of a three-slab step
-// (5 M tets per rank: 9.8 of 15 ms), which left the exchange little to hide behind -- and a rank with nothing to send posted its
-// receive at t = 0, whose spinning NCCL kernel then took SM resources from the assembly for 10 ms (rank 0 was 5 % slower than
-// rank 1).  With the priority lane all ranks reach the exchange after about one slab's time.
+// Partitioned functions, opt-in (TAD_PRIORITY_LANE=1): the slabs the exchange waits for (the halo slabs, at least the first slab)
+// run on a lane of their own with HIGH stream priority, so that they finish after about one slab's time instead of sharing the GPU
+// with the next slab (three slabs of 1.7 M tets: 5.3 instead of 9.8 of 15 ms).
 int ensure_prio_lane(tad_function f)
 {
     if (!f->prio_lane.empty()) return TAD_OK;
@@ -1121,7 +1119,9 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
     TAD_TRY(ensure_lanes(f, n_lanes));
     TAD_TRY(ensure_slab_events(f, (size_t)n_slabs));
     // partitioned: the first n_first slabs (the halo slabs; at least one, so that all ranks reach the exchange together) on the priority lane
-    static const bool prio_enabled = [] { const char* e = getenv("TAD_PRIORITY_LANE"); return !e || atoi(e) != 0; }();
+    // (opt-in, TAD_PRIORITY_LANE=1: it wins with three slabs per rank -- C5 on 2 GPUs 15.3 vs 16.2 ms -- but loses with two -- C5 on
+    // 8 GPUs 4.28 vs 4.11 ms: two slabs interleaved on equal-priority lanes use the GPU better than one after the other)
+    static const bool prio_enabled = [] { const char* e = getenv("TAD_PRIORITY_LANE"); return e && atoi(e) != 0; }();
     const int n_first = (partitioned && prio_enabled && !f->timing && !gather && n_slabs > 1 && mode >= TAD_MODE_FIRST)
                             ? std::min(n_slabs - 1, std::max(1, schedule->n_halo_slabs)) : 0;
     if (n_first > 0) TAD_TRY(ensure_prio_lane(f));
@@ -1232,7 +1232,9 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         cudaStream_t cs = f->comm_stream;
         const int W = f->comm->world;
         TAD_CUDA(cudaStreamWaitEvent(cs, f->ev[0], 0));
-        for (int q = 0; q < std::min(std::max(schedule->n_halo_slabs, n_first), n_slabs); ++q) TAD_CUDA(cudaStreamWaitEvent(cs, f->slab_events[(size_t)q], 0));
+        // every rank waits for its halo slabs and at least for its first slab: a rank with nothing to send would otherwise post its
+        // receive at t = 0, and the spinning NCCL kernel takes SM resources from the assembly until the sender is ready
+        for (int q = 0; q < std::min(std::max(schedule->n_halo_slabs, 1), n_slabs); ++q) TAD_CUDA(cudaStreamWaitEvent(cs, f->slab_events[(size_t)q], 0));
         if (comm_trace) cudaEventRecord(f->ev_trace[0], cs);   // halo slabs assembled
         TAD_TRY(halo_pack(halo_h ? Hv : nullptr, halo_g ? g : nullptr, P.send_base.p, P.send_rs.p, P.send_blk_off[(size_t)W], P.send_vtx.p,
                           P.send_vtx_off[(size_t)W], f->d, P.send_h.p, P.send_g.p, cs));
