@@ -56,11 +56,44 @@ struct Element
     // (a functor that branches on x before or between its variables() calls) must be reported, not silently mis-assembled.
     TINYAD_HD TINYAD_INLINE Element(int64_t _handle, const double* _x, int64_t _n_handles, int32_t* _err, const int32_t* _rec = nullptr,
                                     int64_t _rec_stride = 0)
-        : handle(_handle), x(_x), n_handles(_n_handles), err(_err), n_used(0), rec(_rec), rec_stride(_rec_stride), mismatch(false) {}
+        : handle(_handle), x(_x), n_handles(_n_handles), err(_err), n_used(0), rec(_rec), rec_stride(_rec_stride), mismatch(false)
+    {
+        // Static slots: ALL recorded handles of the element are loaded here, back to back (N coalesced int32 loads).  variables()
+        // then addresses x through the RECORDED handle of its slot and only remembers the handle the functor asked for; range and
+        // equality are checked after the functor (check_recorded_count).  A warp issues in order, so with the functor's own
+        // `element.variables(conn(e, j))` every call used to wait for its connectivity load, then for the range check on it,
+        // then for x -- N times two dependent memory round trips at 8 warps per SM (ncu: 15 % of the tet kernels' stall samples
+        // on the range checks, another 35 % of the first kernel's on the comparison with the recorded handle).  Now the loads
+        // of x depend on one round trip that starts at construction.  A functor that requests another handle than recorded
+        // computes with the recorded one and the evaluation reports TAD_PATTERN_MISMATCH / TAD_INDEX_OUT_OF_RANGE.
+        if constexpr (!Dedup)
+        {
+            if (rec)
+                detail::static_for<N>([&](auto jc) TINYAD_LAMBDA_INLINE {
+                    constexpr int j = decltype(jc)::value;
+                    rec_val[j] = rec[j * rec_stride];
+                });
+        }
+    }
     Element(const Element&) = delete;  // Element.hh:78
 
     TINYAD_HD TINYAD_INLINE VariableVectorType variables(int64_t vh)
     {
+        if constexpr (!Dedup)
+        {
+            if (rec)
+            {
+                int slot = n_used++;
+                if (slot >= N)
+                {
+                    detail::raise(err, TINYAD_ERR_TOO_MANY_VARIABLES);  // Element.hh:237-238
+                    slot = N - 1;
+                }
+                req_val[slot] = (vh < 0 || vh > 0x7fffffffll) ? -2 : (int32_t)vh;   // checked after the functor
+                const int32_t rh = rec_val[slot];
+                return load_variables(rh >= 0 ? (int64_t)rh : 0, slot);
+            }
+        }
         if (vh < 0 || vh >= n_handles)
         {
             detail::raise(err, TINYAD_ERR_INDEX_OUT_OF_RANGE);
@@ -86,19 +119,16 @@ struct Element
             detail::raise(err, TINYAD_ERR_TOO_MANY_VARIABLES);  // Element.hh:237-238
             slot = N - 1;
         }
-        // The recorded handle is only LOADED here; the comparison happens after the functor (check_recorded_count).  A warp issues
-        // in order, so any instruction consuming the load right here -- a branch, or even a branch-free compare -- makes every
-        // variables() call wait for a second memory round trip before the loads of x can issue (ncu: +40 % on the first tet
-        // kernel, 35 % of its stall samples on this line).
-        if (rec)
+        if constexpr (Dedup)
         {
-            if constexpr (Dedup) mismatch = mismatch || ((int64_t)rec[slot * rec_stride] != vh);   // run-time slot: compare at once
-            else
-            {
-                rec_val[slot] = rec[slot * rec_stride];
-                req_val[slot] = (int32_t)vh;
-            }
+            if (rec) mismatch = mismatch || ((int64_t)rec[slot * rec_stride] != vh);   // run-time slot: compare at once
         }
+        return load_variables(vh, slot);
+    }
+
+    // the d variables of handle vh as active scalars with local indices d * slot + i (or passive values)
+    TINYAD_HD TINYAD_INLINE VariableVectorType load_variables(const int64_t vh, const int slot) const
+    {
         const double* xv = x + d * vh;
         VariableVectorType v;
         detail::static_for<d>([&](auto ic) TINYAD_LAMBDA_INLINE {
@@ -149,15 +179,21 @@ struct Element
     TINYAD_HD TINYAD_INLINE void check_recorded_count(int32_t recorded) const
     {
         const int want = recorded < 0 ? -recorded - 1 : recorded;  // < 0 marks "a handle was requested more than once"
-        bool bad = mismatch;
+        bool bad = mismatch, out_of_range = false;
         if constexpr (!Dedup)
         {
             if (rec)
                 detail::static_for<N>([&](auto jc) TINYAD_LAMBDA_INLINE {
                     constexpr int j = decltype(jc)::value;
-                    if (j < n_used && rec_val[j] != req_val[j]) bad = true;
+                    if (j < n_used)
+                    {
+                        const int32_t r = req_val[j];
+                        if (r == -2 || (int64_t)r >= n_handles) out_of_range = true;   // Element.hh:159-170
+                        else if (rec_val[j] != r) bad = true;
+                    }
                 });
         }
+        if (out_of_range) detail::raise(err, TINYAD_ERR_INDEX_OUT_OF_RANGE);
         if (bad || (Dedup ? (n_used != want) : (recorded >= 0 && n_used != want))) detail::raise(err, TINYAD_ERR_PATTERN_MISMATCH);
     }
 };

@@ -120,14 +120,14 @@ __global__ void __launch_bounds__(128) first_order_kernel(Functor f, tad_launch_
     if (a.rec_counts) el.check_recorded_count(a.rec_counts[e]);
 }
 
-// si: position inside the slab (staging index), e = a.e_begin + si: the element.  Only part 0 validates the recorded handles.
+// si: position inside the slab (staging index), e = a.e_begin + si: the element.  Only part 0 validates the requested handles.
 template <class Functor, int d, int N, int NP, int P, bool Dedup>
 __device__ TINYAD_INLINE void second_order_part(const Functor& f, const tad_launch_args& a, int64_t si)
 {
     constexpr int k = d * N;
     using T = Scalar<k, true, NP, P>;
     const int64_t e = a.e_begin + si;
-    Element<d, N, 0, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags, P == 0 ? rec_column(a, e) : nullptr, a.rec_stride);
+    Element<d, N, 0, T, true, Dedup> el(elem_handle(a, e), a.x, a.n_handles, a.error_flags, rec_column(a, e), a.rec_stride);   // every part addresses x through the recorded handles
     const T r = f(el);
     if constexpr (P == 0)
     {
