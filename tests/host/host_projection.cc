@@ -30,6 +30,43 @@ extern "C" int host_project(int k, double* packed, double eps)
     }
 }
 
+// element Hessians with the translation null space of D-dimensional handles: deflated form (Projection.hh proj_tridiagonalize<K, D>)
+extern "C" int host_project_translations(int k, int d, double* packed, double eps)
+{
+    auto ld = [&](int s) { return packed[s]; };
+    auto st = [&](int s, double v) { packed[s] = v; };
+    if (k == 12 && d == 3) return TinyAD::detail::project_element<12, 3>(ld, st, eps);
+    if (k == 9 && d == 3) return TinyAD::detail::project_element<9, 3>(ld, st, eps);
+    if (k == 6 && d == 3) return TinyAD::detail::project_element<6, 3>(ld, st, eps);
+    if (k == 6 && d == 2) return TinyAD::detail::project_element<6, 2>(ld, st, eps);
+    if (k == 8 && d == 2) return TinyAD::detail::project_element<8, 2>(ld, st, eps);
+    if (k == 4 && d == 2) return TinyAD::detail::project_element<4, 2>(ld, st, eps);
+    return -1;
+}
+
+// dimension of the translation null space phase B2 deflated (0 = the plain path was taken), for the tests
+template <int K, int D>
+static int deflated_dim(const double* packed, double eps)
+{
+    using namespace TinyAD::detail;
+    using L = ProjLayout<K>;
+    double R[L::nR], Wb[L::nW] = {0};
+    int code = proj_tridiagonalize<K, D>([&](int s) { return packed[s]; }, [&](int i, double v) { R[i] = v; }, eps);
+    if (code == PROJ_DOMINANT) return -1;
+    if (proj_eigenvalues<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; }) == PROJ_FALLBACK) return -2;
+    code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i) { return R[L::off_lam + i]; }, [&](int i, double v) { R[L::off_lam + i] = v; },
+                                  [&](int i, double v) { Wb[i] = v; }, [&](int jv, const double (&v)[K]) { for (int q = 0; q < K; ++q) Wb[L::off_vec + jv * K + q] = v[q]; },
+                                  [&](int jv, double (&v)[K]) { for (int q = 0; q < K; ++q) v[q] = Wb[L::off_vec + jv * K + q]; }, eps);
+    if (code != PROJ_REBUILT) return -3;
+    return ((int)Wb[1]) >> 3;
+}
+extern "C" int host_deflated_dim(int k, int d, const double* packed, double eps)
+{
+    if (k == 12 && d == 3) return deflated_dim<12, 3>(packed, eps);
+    if (k == 6 && d == 2) return deflated_dim<6, 2>(packed, eps);
+    return -9;
+}
+
 // the in-kernel fallback of the fused small-k element kernel (cyclic Jacobi, Projection.hh project_full_jacobi)
 template <int K>
 static int run_jacobi(double* packed, double eps)

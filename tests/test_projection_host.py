@@ -24,6 +24,8 @@ def hostlib():
     L = ctypes.CDLL(so)
     L.host_project.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
     L.host_project_jacobi.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
+    L.host_project_translations.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
+    L.host_deflated_dim.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
     return L
 
 
@@ -140,3 +142,74 @@ def test_projection_host_element_hessians(hostlib):
             assert code == 2
             ref = reference_projection(A, 1e-9)
             assert np.abs(unpack(hostlib, pk, k) - ref).max() <= 1e-11 * np.abs(A).max()
+
+
+def translation_projector(k, d):
+    """Orthogonal projector onto the complement of the d translations of k / d handles (local index = d * handle + component)."""
+    n = k // d
+    U = np.zeros((k, d))
+    for a in range(d):
+        U[a::d, a] = 1.0 / np.sqrt(n)
+    return np.eye(k) - U @ U.T
+
+
+@pytest.mark.parametrize("k,d", [(12, 3), (9, 3), (6, 3), (6, 2), (8, 2), (4, 2)])
+@pytest.mark.parametrize("eps", [1e-9, 0.0, -1.0, 1e-3])
+def test_translation_null_space_deflation_host(hostlib, k, d, eps):
+    """proj_tridiagonalize<K, D> + the deflated phases B2 / C: matrices WITH the translation null space (random, with negative
+    eigenvalues, with an additional null vector, scaled, zero) and WITHOUT it (generic: the test must say no) against numpy."""
+    rng = np.random.default_rng(3000 + 10 * k + d)
+    P = translation_projector(k, d)
+    mats = []
+    for scale in (1.0, 1e-5, 1e4):
+        for _ in range(6):
+            A = rng.standard_normal((k, k)); A = P @ (A + A.T) @ P * scale            # indefinite, translation invariant
+            mats.append(A)
+        B = rng.standard_normal((k, k)); mats.append(P @ (B @ B.T) @ P * scale)      # PSD, exactly the translation null space
+        B = rng.standard_normal((k, max(1, k - d - 1))); mats.append(P @ (B @ B.T) @ P * scale)   # one more null vector
+        A = rng.standard_normal((k, k)); mats.append((A + A.T) * scale)              # not translation invariant
+        A = rng.standard_normal((k, k)); A = P @ (A + A.T) @ P
+        mats.append((A + 1e-9 * rng.standard_normal((k, k))) * scale)                # invariance violated at 1e-9: must not be deflated
+    mats.append(np.zeros((k, k)))
+    mats.append(-P)
+    n_fallback = 0
+    for idx, A in enumerate(mats):
+        A = 0.5 * (A + A.T)
+        p = pack(hostlib, A)
+        code = hostlib.host_project_translations(k, d, p.ctypes.data, eps)
+        assert code in (0, 1, 2, 3), (k, d, idx, code)
+        got = unpack(hostlib, p, k)
+        if code == 3:
+            n_fallback += 1
+            assert np.array_equal(got, A)
+            continue
+        ora, ocode = oracle.project(A, eps)
+        ref = A if ocode == 0 else reference_projection(A, eps)
+        scale = max(np.abs(A).max(), abs(eps), 1e-300)
+        assert np.abs(got - ref).max() / scale <= 5e-12, (k, d, idx, code, np.abs(got - ref).max() / scale)
+        assert np.abs(got - ora).max() / scale <= 5e-12
+        if code < 2:
+            assert np.array_equal(got, A)
+    assert n_fallback <= 2, n_fallback
+
+
+def test_translation_deflation_on_element_hessians(hostlib):
+    """Real element Hessians of the tet / triangle deformation energies through the deflated path (what the kernels run)."""
+    from problems import tet_problem, grid_problem
+    import scipy.sparse as sp
+    for (p, x), k in ((tet_problem(3, seed=4), 12), (grid_problem(6, seed=4), 6)):
+        kind, conn, data = p.terms[0]
+        for e in range(0, len(conn), 5):
+            loc = np.arange(conn.shape[1], dtype=np.int32)[None, :]
+            xe = x.reshape(-1, p.d)[conn[e]].reshape(-1)
+            r = oracle.scalar_eval(p.d, conn.shape[1], [oracle.Term(kind, loc, data[e:e + 1])], oracle.DERIVATIVES, xe)
+            A = sp.csc_matrix((r.values, r.inner, r.outer), shape=(k, k)).toarray()
+            A = 0.5 * (A + A.T)
+            for eps in (1e-9, 1e-6):
+                pk = pack(hostlib, A)
+                if np.abs(A).max() > 0:                                                        # (an inverted element has a zero Hessian)
+                    assert hostlib.host_deflated_dim(k, p.d, pk.ctypes.data, eps) == p.d      # the deflated path really runs on them
+                code = hostlib.host_project_translations(k, p.d, pk.ctypes.data, eps)
+                assert code == 2
+                ref = reference_projection(A, eps)
+                assert np.abs(unpack(hostlib, pk, k) - ref).max() <= 1e-11 * np.abs(A).max()

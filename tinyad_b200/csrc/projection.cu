@@ -318,14 +318,15 @@ __global__ void __launch_bounds__(kListThreads) project_kernel_list(double* __re
 //   C  apply           -- back-transform through the reflectors, H += low-rank term (register-heavy)
 // Scratch between them is structure-of-arrays over the elements (coalesced 256-byte rows).
 
-template <int K>
+// D: variable dimension of the term when its K = D * N local variables are ordered handle by handle (translation null-space test), else 0
+template <int K, int D>
 __global__ void __launch_bounds__(128) project_kernel_a(const double* __restrict__ hess, int64_t n, int64_t stride, double eps, ProjScratch sc)
 {
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
     const double* hp = hess + el;
     double* rp = sc.R + el;
-    sc.codes[el] = TinyAD::detail::proj_tridiagonalize<K>([&](int s) { return hp[(int64_t)s * stride]; },
+    sc.codes[el] = TinyAD::detail::proj_tridiagonalize<K, D>([&](int s) { return hp[(int64_t)s * stride]; },
                                                           [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
 }
 
@@ -429,7 +430,7 @@ size_t project_scratch_doubles(int64_t stride)
 // doubles, scratch_i: stride int32 + n int64 (see project_scratch_bytes).
 template <int K>
 int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, int32_t* codes,
-                   int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st)
+                   int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st, int tdim)
 {
     using L = TinyAD::detail::ProjLayout<K>;
     constexpr size_t smem = (size_t)ProjSmem<K>::doubles_per_warp * sizeof(double);
@@ -451,7 +452,17 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         sc.list = list;
         const unsigned g = (unsigned)((n + 127) / 128);
         count_launch(4 + (fuse_out ? 0 : 1));
-        project_kernel_a<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+        // translation null-space test for the element shapes of the fused path (d <= 3 variables per handle, <= 4 handles)
+        if constexpr (K % 3 == 0 && K / 3 >= 2 && K / 3 <= 4)
+        {
+            if (tdim == 3) project_kernel_a<K, 3><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+        }
+        if constexpr (K % 2 == 0 && K / 2 >= 2 && K / 2 <= 4)
+        {
+            if (tdim == 2) project_kernel_a<K, 2><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+        }
+        if (!((tdim == 3 && K % 3 == 0 && K / 3 >= 2 && K / 3 <= 4) || (tdim == 2 && K % 2 == 0 && K / 2 >= 2 && K / 2 <= 4)))
+            project_kernel_a<K, 0><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
         project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
         {
             static PerDeviceOnce b2_configured;
@@ -594,7 +605,7 @@ int launch_project_generic(int k, double* hess, int64_t n, int64_t stride, doubl
 #define TAD_INST(K)                                                                                                                         \
     template size_t project_scratch_doubles<K>(int64_t);                                                                                    \
     template int launch_project<K>(double*, int64_t, int64_t, double, unsigned long long*, double*, int32_t*, int64_t*, bool, ProjScratch*, \
-                                   const ProjSide*, cudaStream_t);
+                                   const ProjSide*, cudaStream_t, int);
 #if TAD_PROJ_PART == 0
 TAD_INST(1) TAD_INST(2) TAD_INST(3) TAD_INST(4) TAD_INST(5) TAD_INST(6)
 #elif TAD_PROJ_PART == 1

@@ -202,12 +202,13 @@ constexpr int kListBlocks = 148, kListThreads = 32;
 template <int K> size_t project_scratch_doubles(int64_t stride);
 template <int K>
 int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, int32_t* codes,
-                   int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st);
+                   int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st, int tdim);
 size_t project_scratch_doubles_generic(int k);   // k without a dedicated instantiation (run-time k Jacobi, projection.cu)
 int launch_project_generic(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d, cudaStream_t st);
 size_t project_scratch_doubles_rt(int k, int64_t stride);
 int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d,
-                     int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st);
+                     int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st,
+                     int tdim = 0);   // tdim: variable dimension of the term (translation null-space deflation), 0 = none
 
 // ---- assembly (assembly.cu) ----
 struct SeqTable { int16_t idx[32 * 32]; };   // packed (tile-order) index of entry (i, j), row-major k x k, k <= 32

@@ -172,25 +172,25 @@ size_t project_scratch_doubles_rt(int k, int64_t stride)
 }
 
 int project_dispatch(int k, double* hess, int64_t n, int64_t stride, double eps, unsigned long long* counts, double* scratch_d,
-                     int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st)
+                     int32_t* codes, int64_t* list, bool full_only, ProjScratch* fuse_out, const ProjSide* side, cudaStream_t st, int tdim)
 {
     if (n <= 0 || k <= 0) return TAD_OK;
     switch (k)
     {
-    case 1: return launch_project<1>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 2: return launch_project<2>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 3: return launch_project<3>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 4: return launch_project<4>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 5: return launch_project<5>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 6: return launch_project<6>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 7: return launch_project<7>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 8: return launch_project<8>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 9: return launch_project<9>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 10: return launch_project<10>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 12: return launch_project<12>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
-    case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st);
+    case 1: return launch_project<1>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 2: return launch_project<2>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 3: return launch_project<3>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 4: return launch_project<4>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 5: return launch_project<5>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 6: return launch_project<6>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 7: return launch_project<7>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 8: return launch_project<8>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 9: return launch_project<9>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 10: return launch_project<10>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 12: return launch_project<12>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 15: return launch_project<15>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 16: return launch_project<16>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
+    case 18: return launch_project<18>(hess, n, stride, eps, counts, scratch_d, codes, list, full_only, fuse_out, side, st, tdim);
     default: return launch_project_generic(k, hess, n, stride, eps, counts, scratch_d, st);   // any other k <= 32: run-time k Jacobi
     }
 }
@@ -1186,6 +1186,7 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
         count_launch();
         reduce_stage1<false><<<(unsigned)((sl.n + 255) / 256), 256, 0, ls>>>(a.val, sl.n, sstride, 1, f->fpart.p + part_off[(size_t)sl.term] + sl.e_begin / 256);
         // atomic mode + fast projection: the last projection phase (low-rank update) is fused with the scatter
+        static const bool deflate_translations = [] { const char* e = getenv("TAD_DEFLATE_TRANSLATIONS"); return !e || atoi(e) != 0; }();
         const bool fuse = !fused_done && mode == TAD_MODE_SECOND && project && !gather && !f->projection_full && fused_c_assemble_supported(f->d, t.N);
         ProjScratch fused_sc;
         if (mode == TAD_MODE_SECOND && project && !fused_done)
@@ -1196,7 +1197,8 @@ int eval_scalar(tad_function f, int mode, const double* x, double* f_host, doubl
                 TAD_CUDA(L.proj_scratch.ensure(std::max<size_t>(1, project_scratch_doubles_rt(t.k, sstride))));
             TAD_CUDA(cudaMemsetAsync(L.counts.p + 2, 0, sizeof(unsigned long long), ls));  // the list of the full solver is per slab
             TAD_TRY(project_dispatch(t.k, a.hess, sl.n, sstride, eps, L.counts.p, L.proj_scratch.p, L.proj_codes.p, L.proj_list.p,
-                                     f->projection_full != 0, fuse ? &fused_sc : nullptr, fuse ? &L.side : nullptr, ls));
+                                     f->projection_full != 0, fuse ? &fused_sc : nullptr, fuse ? &L.side : nullptr, ls,
+                                     (deflate_translations && t.k == f->d * t.N) ? f->d : 0));
         }
         if (f->timing) cudaEventRecord(L.tev[2], ls);
         const SlabMaps maps{t.rec_handles.p + sl.e_begin, t.blockbase.p ? t.blockbase.p + sl.e_begin : nullptr,

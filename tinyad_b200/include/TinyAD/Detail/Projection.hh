@@ -72,7 +72,8 @@ struct ProjLayout
     static constexpr int n_v = n_refl * (n_refl + 1) / 2;  // sum_{k} (K-k-2)
     static constexpr int off_amax = off_v + n_v;  // max |H_ij| of the element (scale of the accuracy target)
     static constexpr int off_lam = off_amax + 1;  // eigenvalues of T, ascending (written by proj_eigenvalues)
-    static constexpr int nR = off_lam + K;
+    static constexpr int off_tnull = off_lam + K; // D if the D translations (1,0,..,1,0,..), ... are null vectors of H, else 0 (proj_tridiagonalize<K, D>)
+    static constexpr int nR = off_tnull + 1;
     static constexpr int off_wgt = 2, off_vec = 2 + MAXV;
     static constexpr int nW = off_vec + MAXV * K;
     // offset of v_k(2 + i), i < K-k-2
@@ -86,7 +87,11 @@ struct ProjLayout
 
 // Phase A: early-out 1 and Householder tridiagonalisation; the packed matrix lives in registers.
 // Returns PROJ_DOMINANT (nothing stored) or PROJ_UNCHANGED (R stored, continue with phase B).
-template <int K, class LoadFn, class StoreRFn>
+// D > 0 (variable dimension of a term whose K = D * N local variables are ordered handle by handle): also tests whether the D
+// TRANSLATIONS t_a (1 on component a of every handle) are null vectors of H, |H t_a|_inf <= 1e-13 max|H|, and stores the answer.
+// Every translation-invariant element energy has them (the tet / triangle deformation energies: 3 of the ~4.5 eigenpairs phase B2
+// would compute per tet); phase B2 then skips them and phase C adds their exactly known term, eps * (projector onto the translations).
+template <int K, int D = 0, class LoadFn, class StoreRFn>
 TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, const double eps)
 {
     using L = ProjLayout<K>;
@@ -121,6 +126,27 @@ TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, cons
         });
         if (dominant) return PROJ_DOMINANT;
     }
+
+    if constexpr (D > 0 && K % (D > 0 ? D : 1) == 0 && K > D)
+    {
+        // row sums over the handles, per component: S(i, a) = sum_s H(i, D s + a)
+        double worst = 0.0;
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            static_for<D>([&](auto ac) TINYAD_LAMBDA_INLINE {
+                constexpr int a_ = decltype(ac)::value;
+                double sum = 0.0;
+                static_for<K / D>([&](auto sc) TINYAD_LAMBDA_INLINE {
+                    constexpr int j = D * decltype(sc)::value + a_;
+                    sum += a[hess_seq_index(K, i, j)];
+                });
+                worst = fmax(worst, fabs(sum));
+            });
+        });
+        store_r(L::off_tnull, (worst <= 1e-13 * amax) ? (double)D : 0.0);
+    }
+    else
+        store_r(L::off_tnull, 0.0);
 
     double d0[K], e0[K];  // tridiagonal T: d0[i] = T(i,i), e0[i] = T(i+1,i); e0[K-1] = 0
     double tau[K > 2 ? K - 2 : 1];
@@ -492,7 +518,26 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam,
     // form A: H + sum_{j<r} delta_j v_j v_j^T with delta_j = target_j - l_j           (r <= K/2)
     // form B: base + sum_{j>=r} gamma_j v_j v_j^T, base = eps I (clamp) or -H (abs)     (otherwise: fewer vectors)
     const bool form_b = 2 * r > K;
-    const int j_begin = form_b ? r : 0, j_end = form_b ? K : r;
+    // Translation null space (proj_tridiagonalize<K, D> found the D translations to be null vectors of H): if the moved eigenvalues
+    // are exactly some clearly negative ones plus D eigenvalues that are zero to rounding, the latter ARE the translations -- no
+    // inverse iteration for them; phase C adds eps * (projector onto the translations) (the reference adds (eps - l_j) v_j v_j^T
+    // over an arbitrary orthonormal basis v_j of that eigenspace, l_j = O(macheps |H|)).
+    int tn = (int)load_r(L::off_tnull);
+    int n_neg = 0;
+    if (tn > 0)
+    {
+        const double tolz = 1e-11 * load_r(L::off_amax);
+        int n_tiny = 0;
+        for (int i = 0; i < K; ++i)
+        {
+            const double li = lam_at(i);
+            n_neg += (li < -tolz) ? 1 : 0;
+            n_tiny += (fabs(li) <= tolz) ? 1 : 0;
+        }
+        // exactly D tiny eigenvalues, all moved eigenvalues accounted for, form A
+        if (n_tiny != tn || r != n_neg + tn || form_b) tn = 0;
+    }
+    const int j_begin = form_b ? r : 0, j_end = form_b ? K : (tn > 0 ? n_neg : r);
 
     // ---- 4. inverse iteration on T (LAPACK dstein scheme: dlagtf / dlagts, re-orthogonalisation in clusters) ----
     const double ortol = 1e-3 * onenrm;
@@ -669,7 +714,7 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam,
         xjm = xj;
     }
     store_w(0, (double)(j_end - j_begin));
-    store_w(1, !form_b ? 0.0 : (abs_mode ? 2.0 : 1.0));
+    store_w(1, (!form_b ? 0.0 : (abs_mode ? 2.0 : 1.0)) + 8.0 * tn);   // form + 8 * (dimension of the deflated translation null space)
     return PROJ_REBUILT;
 }
 
@@ -688,7 +733,8 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
     using L = ProjLayout<K>;
     constexpr int H = L::H;
     const int nv = (int)load_w(0);
-    const int form = (int)load_w(1);
+    const int form_code = (int)load_w(1);
+    const int form = form_code & 7, tn = form_code >> 3;
     const bool preloaded = preload(nv);
     {
         // reflectors in registers; each vector goes v = H_0 H_1 ... H_{K-3} y
@@ -762,6 +808,20 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
             acc[s] = fma(wv[hess_seq_rc(K, s).row], v[hess_seq_rc(K, s).col], acc[s]);
         });
     }
+    if (tn > 0 && eps > 0.0)
+    {
+        // + eps * (projector onto the tn translations of the K / tn handles): eps / N on the entries (i, j) with equal component
+        const double w0 = eps * (double)tn / (double)K;
+        static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+            constexpr int s = decltype(sc)::value;
+            constexpr int r_ = hess_seq_rc(K, s).row, c_ = hess_seq_rc(K, s).col;
+            bool same = false;
+            if (tn == 3) same = (K % 3 == 0) && (r_ % 3 == c_ % 3);
+            else if (tn == 2) same = (K % 2 == 0) && (r_ % 2 == c_ % 2);
+            else same = true;
+            if (same) acc[s] += w0;
+        });
+    }
     static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE { constexpr int s = decltype(sc)::value; store(s, acc[s]); });
 }
 
@@ -775,12 +835,13 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
 }
 
 // All three phases on one element through local scratch (host tests; the kernels run the phases separately).
-template <int K, class LoadFn, class StoreFn>
+// D: variable dimension of the term (translation null-space deflation, see proj_tridiagonalize); 0 = none.
+template <int K, int D = 0, class LoadFn, class StoreFn>
 TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const double eps)
 {
     using L = ProjLayout<K>;
     double R[L::nR > 0 ? L::nR : 1], Wb[L::nW];
-    int code = proj_tridiagonalize<K>(load, [&](int i, double v) { R[i] = v; }, eps);
+    int code = proj_tridiagonalize<K, D>(load, [&](int i, double v) { R[i] = v; }, eps);
     if (code == PROJ_DOMINANT) return code;
     code = proj_eigenvalues<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; });
     if (code == PROJ_FALLBACK) return code;

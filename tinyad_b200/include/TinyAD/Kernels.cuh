@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128, TINYAD_FUSED_MIN_BLOCKS) second_order_fus
     static_for<nh>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int s = decltype(ic)::value; finite = finite && isfinite(h[s]); });
     if (a.project && finite)
     {
-        int code = project_element<k>([&](int s) { return h[s]; }, [&](int s, double v) { h[s] = v; }, a.eps);
+        int code = project_element<k, d>([&](int s) { return h[s]; }, [&](int s, double v) { h[s] = v; }, a.eps);
         if (code == PROJ_FALLBACK)
         {
             code = project_full_jacobi<k>([&](int s) { return h[s]; }, [&](int s, double v) { h[s] = v; }, a.eps);

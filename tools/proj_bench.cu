@@ -10,6 +10,9 @@
 
 using namespace TinyAD::detail;
 constexpr int K = 12;
+#ifndef TDIM
+#define TDIM 3   // translation null-space deflation (0 = off)
+#endif
 using L = ProjLayout<K>;
 
 __device__ double rnd(uint64_t& s)
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(128) ka(const double* hess, int64_t n, int64_t
     if (el >= n) return;
     const double* hp = hess + el;
     double* rp = R + el;
-    codes[el] = proj_tridiagonalize<K>([&](int s) { return hp[(int64_t)s * stride]; }, [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
+    codes[el] = proj_tridiagonalize<K, TDIM>([&](int s) { return hp[(int64_t)s * stride]; }, [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
 }
 #ifndef B1_MINB
 #define B1_MINB 1
