@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- projected-Hessian assembly throughput of the tet Double<12> path (BASELINE.json metric).
 
-  python bench.py --gpus 1 --steps K --warmup W            # this framework, one B200
-  torchrun ... bench.py --gpus N ...                        # N ranks, weak scaling over z-slabs
-  python bench.py --impl reference ...                      # the reference's CPU/OpenMP algorithm (oracle port)
+  python bench.py --gpus 1 --steps K --warmup W            # this framework, one B200: C5 (10.1 M tets), the north-star configuration
+  torchrun ... bench.py --gpus N ...                        # N ranks: C5 split in N z-slabs (strong scaling), exchange inside the runtime
+  python bench.py --impl reference ...                      # the reference's CPU/OpenMP algorithm (oracle port) on the same workload
 
 A "step" is one eval_with_hessian_proj over the whole mesh: x is resident in HBM, f / g / CSR values are
 left in HBM (`value`); `e2e` times the same call through the host-buffer C ABI (pinned host x, g, H values;
 H2D + D2H inside the timed region).  Pattern / scatter-map construction is one-time setup and reported apart.
-Prints ONE JSON line on rank 0.
+Every line carries a `check` (against the CPU oracle at N = 1, against a single-rank evaluation of the whole mesh at N > 1);
+the C2 (and, at N = 1, C1) lines ride along under `also`.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json

@@ -44,6 +44,17 @@ extern "C" int host_project_translations(int k, int d, double* packed, double ep
     return -1;
 }
 
+// the reduced pipeline (four handles: the complement of the translations through a Hadamard transform, K - D instead of K)
+extern "C" int host_project_reduced(int k, int d, double* packed, double eps)
+{
+    auto ld = [&](int s) { return packed[s]; };
+    auto st = [&](int s, double v) { packed[s] = v; };
+    if (k == 12 && d == 3) return TinyAD::detail::project_element_reduced<12, 3>(ld, st, eps);
+    if (k == 8 && d == 2) return TinyAD::detail::project_element_reduced<8, 2>(ld, st, eps);
+    if (k == 4 && d == 1) return TinyAD::detail::project_element_reduced<4, 1>(ld, st, eps);
+    return -1;
+}
+
 // dimension of the translation null space phase B2 deflated (0 = the plain path was taken), for the tests
 template <int K, int D>
 static int deflated_dim(const double* packed, double eps)

@@ -6,6 +6,8 @@ really are concurrent at the C ABI (the runtime serialises the evaluations of ON
 objects run on their own streams)."""
 import threading
 
+import os
+
 import numpy as np
 import pytest
 
@@ -163,8 +165,9 @@ def test_launch_count_and_caller_stream(torch_cuda):
     n0 = fn.launch_count()
     f_ref = fn.eval_with_hessian_proj(xd, g, H)
     n1 = fn.launch_count()
-    # 4 element kernels (Hessian parts) + 2 reductions + A, B1, B2, list + 2 fused phase-C / assembly kernels
-    assert n1 - n0 == 12
+    # 4 element kernels (Hessian parts) + 2 reductions + A, B1, B2, list + 2 fused phase-C / assembly kernels = 12; with the reduced
+    # pipeline of four-handle elements (default): B1 and B2 once per pipeline and one more fused phase-C / assembly launch = 15
+    assert n1 - n0 == (12 if os.environ.get("TAD_REDUCED_PIPELINE", "1") == "0" else 15)
     side = torch.cuda.Stream()
     fn.set_caller_stream(side.cuda_stream)
     big = torch.randn(1 << 24, device="cuda")

@@ -26,6 +26,7 @@ def hostlib():
     L.host_project_jacobi.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
     L.host_project_translations.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
     L.host_deflated_dim.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
+    L.host_project_reduced.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
     return L
 
 
@@ -213,3 +214,63 @@ def test_translation_deflation_on_element_hessians(hostlib):
                 assert code == 2
                 ref = reference_projection(A, eps)
                 assert np.abs(unpack(hostlib, pk, k) - ref).max() <= 1e-11 * np.abs(A).max()
+
+
+@pytest.mark.parametrize("k,d", [(12, 3), (8, 2), (4, 1)])
+@pytest.mark.parametrize("eps", [1e-9, 0.0, -1.0, 1e-3])
+def test_reduced_pipeline_host(hostlib, k, d, eps):
+    """proj_tridiagonalize<K, D, true> (Hadamard reduction to the complement of the translations) + phases B1 / B2 on K - D +
+    proj_apply<K, K - D>: translation-invariant matrices take the reduced path (code bit 16), all others the general one."""
+    rng = np.random.default_rng(4000 + 10 * k + d)
+    P = translation_projector(k, d)
+    mats, invariant = [], []
+    for scale in (1.0, 1e-5, 1e4):
+        for _ in range(8):
+            A = rng.standard_normal((k, k)); mats.append(P @ (A + A.T) @ P * scale); invariant.append(True)
+        B = rng.standard_normal((k, k)); mats.append(P @ (B @ B.T) @ P * scale); invariant.append(True)          # PSD on the complement
+        B = rng.standard_normal((k, max(1, k - d - 1))); mats.append(P @ (B @ B.T) @ P * scale); invariant.append(True)
+        B = rng.standard_normal((k, k)); mats.append(-P @ (B @ B.T) @ P * scale); invariant.append(True)         # everything moves: form B
+        A = rng.standard_normal((k, k)); mats.append((A + A.T) * scale); invariant.append(False)
+    mats.append(np.zeros((k, k))); invariant.append(False)
+    mats.append(-P); invariant.append(True)
+    n_fallback = 0
+    for idx, (A, inv) in enumerate(zip(mats, invariant)):
+        A = 0.5 * (A + A.T)
+        p = pack(hostlib, A)
+        code = hostlib.host_project_reduced(k, d, p.ctypes.data, eps)
+        got = unpack(hostlib, p, k)
+        if code == 3:
+            n_fallback += 1
+            assert np.array_equal(got, A)
+            continue
+        ora, ocode = oracle.project(A, eps)
+        ref = A if ocode == 0 else reference_projection(A, eps)
+        scale = max(np.abs(A).max(), abs(eps), 1e-300)
+        assert np.abs(got - ref).max() / scale <= 5e-12, (k, d, idx, code, np.abs(got - ref).max() / scale)
+        assert np.abs(got - ora).max() / scale <= 5e-12
+        if code & 15 >= 2 and ocode != 0:
+            assert bool(code & 16) == inv, (k, d, idx, code)       # invariant matrices went through the reduced pipeline
+        if code & 15 < 2:
+            assert np.array_equal(got, A)
+    assert n_fallback <= 2, n_fallback
+
+
+def test_reduced_pipeline_on_tet_hessians(hostlib):
+    from problems import tet_problem
+    import scipy.sparse as sp
+    p, x = tet_problem(3, seed=4)
+    kind, conn, data = p.terms[0]
+    for e in range(0, len(conn), 3):
+        loc = np.arange(4, dtype=np.int32)[None, :]
+        xe = x.reshape(-1, 3)[conn[e]].reshape(-1)
+        r = oracle.scalar_eval(3, 4, [oracle.Term(kind, loc, data[e:e + 1])], oracle.DERIVATIVES, xe)
+        A = sp.csc_matrix((r.values, r.inner, r.outer), shape=(12, 12)).toarray()
+        A = 0.5 * (A + A.T)
+        if np.abs(A).max() == 0:
+            continue
+        for eps in (1e-9, 1e-6):
+            pk = pack(hostlib, A)
+            code = hostlib.host_project_reduced(12, 3, pk.ctypes.data, eps)
+            assert code == 2 | 16
+            ref = reference_projection(A, eps)
+            assert np.abs(unpack(hostlib, pk, 12) - ref).max() <= 1e-11 * np.abs(A).max()

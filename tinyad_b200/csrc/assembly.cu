@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(128) assemble_atomic_kernel(const int32_t* __r
 // Projection phase C fused with the atomic assembly: the projected Hessian of an element is formed in registers
 // (low-rank update of H, Detail/Projection.hh proj_apply) and scattered from there, instead of being written back to
 // the staging buffer and read again by the assembly kernel (saves 1.35 KB of HBM traffic per tet and one launch).
-template <int D, int N>
+// REDUCED: the element went through the reduced pipeline (four handles; R / W in ProjLayout<K - D> order, proj_apply<K, K - D>)
+template <int D, int N, bool REDUCED = false>
 __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __restrict__ hess, int64_t stride, double eps, const ProjScratch& sc,
                                                const int32_t* __restrict__ rec, const int32_t* __restrict__ blockbase,
                                                const int32_t* __restrict__ rstride, const int64_t mstride, const double* __restrict__ grad,
@@ -92,29 +93,31 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
         for (int bj = 0; bj < N; ++bj) m_base[bi * N + bj] = blockbase[(int64_t)(bi * N + bj) * mstride + e];
     }
     double acc[H];
-    if (code == TinyAD::detail::PROJ_REBUILT)
+    if ((code & 15) == TinyAD::detail::PROJ_REBUILT)
     {
+        constexpr int KR = REDUCED ? K - D : K;
         const double* rp = sc.R + e;
         const double* wp = sc.W + e;
         // scratch of proj_apply in shared memory: [slot][thread of the block], conflict-free
         extern __shared__ double casm_tmp[];
         double* tp = casm_tmp + threadIdx.x;
         const int bd = blockDim.x;
-        TinyAD::detail::proj_apply<K>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
+        TinyAD::detail::proj_apply<K, KR>([&](int i) { return rp[(int64_t)i * stride]; }, [&](int i) { return wp[(int64_t)i * stride]; },
                                       [&](int s) { return hp[(int64_t)s * stride]; }, [&](int s, double v) { acc[s] = v; }, eps,
                                       [&](int i, double v) { tp[i * bd] = v; }, [&](int i) { return tp[i * bd]; },
                                       [&](int nv) {
                                           // asynchronous global -> shared copies of the nv vectors and their weights (cp.async, 8 bytes
                                           // each): no registers, and they overlap the reflector loads that follow
-                                          using L = TinyAD::detail::ProjLayout<K>;
+                                          using L = TinyAD::detail::ProjLayout<KR>;
                                           const unsigned dst0 = (unsigned)__cvta_generic_to_shared(tp);
                                           for (int jv = 0; jv < nv; ++jv)
                                           {
 #pragma unroll
-                                              for (int i = 0; i <= K; ++i)
+                                              for (int i = 0; i <= KR; ++i)
                                               {
-                                                  const double* src = wp + (int64_t)(i < K ? L::off_vec + jv * K + i : L::off_wgt + jv) * stride;
-                                                  const unsigned dst = dst0 + (unsigned)((jv * (K + 1) + i) * bd) * 8u;
+                                                  // components i < KR to slots jv (K + 1) + i, the weight to slot jv (K + 1) + K
+                                                  const double* src = wp + (int64_t)(i < KR ? L::off_vec + jv * KR + i : L::off_wgt + jv) * stride;
+                                                  const unsigned dst = dst0 + (unsigned)((jv * (K + 1) + (i < KR ? i : K)) * bd) * 8u;
                                                   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
                                               }
                                           }
@@ -166,7 +169,8 @@ __device__ __forceinline__ void c_assemble_one(const int64_t e, const double* __
 
 // LIST = false: all elements except those handed to the full solver (code PROJ_FALLBACK) when `skip_listed`;
 // LIST = true: the listed elements (their staged Hessian was projected in place by project_kernel_list).
-template <int D, int N, bool LIST>
+// REDUCED (non-LIST only): the launch for the elements of the reduced pipeline (code bit PROJ_REDUCED_BIT); the plain launch skips them.
+template <int D, int N, bool LIST, bool REDUCED = false>
 __global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* __restrict__ hess, int64_t n, int64_t stride, double eps,
                                                                  ProjScratch sc, const int32_t* __restrict__ rec,
                                                                  const int32_t* __restrict__ blockbase, const int32_t* __restrict__ rstride,
@@ -186,7 +190,8 @@ __global__ void __launch_bounds__(128) project_c_assemble_kernel(const double* _
         if (e >= n) return;
         const int code = sc.codes[e];
         if (skip_listed && code == TinyAD::detail::PROJ_FALLBACK) return;
-        c_assemble_one<D, N>(e, hess, stride, eps, sc, rec, blockbase, rstride, mstride, grad, g, Hv, err, code);
+        if (((code & TinyAD::detail::PROJ_REDUCED_BIT) != 0) != REDUCED) return;
+        c_assemble_one<D, N, REDUCED>(e, hess, stride, eps, sc, rec, blockbase, rstride, mstride, grad, g, Hv, err, code);
     }
 }
 
@@ -211,6 +216,22 @@ int launch_c_assemble(const SlabMaps& m, const double* grad, const double* hess,
     });
     if (!ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the fused projection/assembly kernel");
     count_launch(split ? 2 : 1);
+    if constexpr (N == 4)
+    {
+        if (sc.reduced)
+        {
+            // the elements of the reduced pipeline (normally all of them) first; the plain launch below skips them
+            static PerDeviceOnce configured_r;
+            configured_r.run([&] {
+                ok = cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * tmp_thread)) == cudaSuccess &&
+                     cudaFuncSetAttribute(project_c_assemble_kernel<D, N, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+            });
+            if (!ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the fused projection/assembly kernel");
+            count_launch();
+            project_c_assemble_kernel<D, N, false, true><<<(unsigned)((n + bs - 1) / bs), bs, bs * tmp_thread, st>>>(
+                hess, n, stride, eps, sc, m.rec, m.blockbase, m.rstride, m.mstride, grad, g, Hv, err, counts, split);
+        }
+    }
     project_c_assemble_kernel<D, N, false><<<(unsigned)((n + bs - 1) / bs), bs, bs * tmp_thread, st>>>(
         hess, n, stride, eps, sc, m.rec, m.blockbase, m.rstride, m.mstride, grad, g, Hv, err, counts, split);
     if (split)

@@ -319,24 +319,34 @@ __global__ void __launch_bounds__(kListThreads) project_kernel_list(double* __re
 // Scratch between them is structure-of-arrays over the elements (coalesced 256-byte rows).
 
 // D: variable dimension of the term when its K = D * N local variables are ordered handle by handle (translation null-space test), else 0
-template <int K, int D>
+// REDUCE: elements whose Hessian has the translation null space continue in the reduced pipeline (K - D; code bit PROJ_REDUCED_BIT)
+template <int K, int D, bool REDUCE = false>
 __global__ void __launch_bounds__(128) project_kernel_a(const double* __restrict__ hess, int64_t n, int64_t stride, double eps, ProjScratch sc)
 {
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
     const double* hp = hess + el;
     double* rp = sc.R + el;
-    sc.codes[el] = TinyAD::detail::proj_tridiagonalize<K, D>([&](int s) { return hp[(int64_t)s * stride]; },
+    sc.codes[el] = TinyAD::detail::proj_tridiagonalize<K, D, REDUCE>([&](int s) { return hp[(int64_t)s * stride]; },
                                                           [&](int i, double v) { rp[(int64_t)i * stride] = v; }, eps);
+}
+
+// Which elements a phase-B kernel works on.  filter < 0: all decomposed ones; 0 / 1: those of the general / of the reduced pipeline
+// (code bit PROJ_REDUCED_BIT, set by phase A).
+__device__ __forceinline__ bool proj_skip(int code, int filter)
+{
+    if ((code & 15) == TinyAD::detail::PROJ_DOMINANT || (code & 15) == TinyAD::detail::PROJ_FALLBACK) return true;
+    if (filter < 0) return false;
+    return ((code & TinyAD::detail::PROJ_REDUCED_BIT) != 0) != (filter == 1);
 }
 
 // B1: eigenvalues of T (register-resident QL, Detail/Projection.hh proj_eigenvalues); few registers, high occupancy
 template <int K>
-__global__ void __launch_bounds__(128) project_kernel_b1(int64_t n, int64_t stride, ProjScratch sc)
+__global__ void __launch_bounds__(128) project_kernel_b1(int64_t n, int64_t stride, ProjScratch sc, int filter)
 {
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
-    if (sc.codes[el] == TinyAD::detail::PROJ_DOMINANT) return;
+    if (proj_skip(sc.codes[el], filter)) return;
     double* rp = sc.R + el;
     const int code = TinyAD::detail::proj_eigenvalues<K>([&](int i) { return rp[(int64_t)i * stride]; },
                                                          [&](int i, double v) { rp[(int64_t)i * stride] = v; });
@@ -352,14 +362,18 @@ template <int K>
 constexpr size_t b2_smem_bytes(int threads) { return (size_t)(K + B2_SMEM_VECS * K) * threads * sizeof(double); }
 
 template <int K, int MINB>
-__global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc)
+__global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc,
+                                                              int filter)
 {
     using L = TinyAD::detail::ProjLayout<K>;
     extern __shared__ double b2_smem[];
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
     int code = sc.codes[el];
-    if (code == TinyAD::detail::PROJ_DOMINANT) return;
+    if ((code & 15) == TinyAD::detail::PROJ_DOMINANT) return;
+    if (filter >= 0 && (code & 15) != TinyAD::detail::PROJ_FALLBACK && ((code & TinyAD::detail::PROJ_REDUCED_BIT) != 0) != (filter == 1)) return;
+    if (filter == 1 && (code & 15) == TinyAD::detail::PROJ_FALLBACK) return;   // failed in the reduced B1: counted by the general B2 launch
+    code &= 15;
     double* rp = sc.R + el;
     double* wp = sc.W + el;
     const int bd = blockDim.x;
@@ -395,7 +409,25 @@ __global__ void __launch_bounds__(128, MINB) project_kernel_b(int64_t n, int64_t
                 }
             },
             eps);
-    sc.codes[el] = code;
+    if (filter == 1)
+    {
+        if (code == TinyAD::detail::PROJ_FALLBACK)
+        {
+            sc.codes[el] = code;   // counted and listed by the general launch that follows (the full solver works on H itself)
+            return;
+        }
+        // reduced pipeline: the matrix on the complement of the translations.  Nothing to move there still leaves the translations'
+        // own eigenvalue 0 < eps: an update with no vectors.  The bit stays on rebuilt elements only (phase C picks the layout by it).
+        if (code == TinyAD::detail::PROJ_UNCHANGED && eps > 0.0)
+        {
+            wp[0] = 0.0;
+            wp[stride] = 0.0;
+            code = TinyAD::detail::PROJ_REBUILT;
+        }
+        sc.codes[el] = code == TinyAD::detail::PROJ_REBUILT ? (code | TinyAD::detail::PROJ_REDUCED_BIT) : code;
+    }
+    else
+        sc.codes[el] = code;
     if (counts) atomicAdd(&counts[0], 1ull);
     if (code == TinyAD::detail::PROJ_REBUILT && counts) atomicAdd(&counts[1], 1ull);
     if (code == TinyAD::detail::PROJ_FALLBACK)
@@ -411,7 +443,7 @@ __global__ void __launch_bounds__(128) project_kernel_c(double* __restrict__ hes
 {
     const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= n) return;
-    if (sc.codes[el] != TinyAD::detail::PROJ_REBUILT) return;
+    if (sc.codes[el] != TinyAD::detail::PROJ_REBUILT) return;   // (the reduced pipeline only exists on the fused path)
     double* hp = hess + el;
     const double* rp = sc.R + el;
     const double* wp = sc.W + el;
@@ -424,6 +456,24 @@ size_t project_scratch_doubles(int64_t stride)
 {
     using L = TinyAD::detail::ProjLayout<K>;
     return (size_t)(L::nR + L::nW) * (size_t)stride + (size_t)(K * K + 2 * K) * kListBlocks * kListThreads;
+}
+
+// Phase B2.  2 blocks per SM at 255 registers (no spills) beat 3 blocks at 168 registers with ~400 B of spills by 3-6 %
+// (tools/proj_bench.cu); K <= 12: 128-thread blocks (61 KB of shared memory each at K = 12); larger K: smaller blocks keep the
+// footprint per SM.
+template <int K>
+int launch_b2(int64_t n, int64_t stride, double eps, unsigned long long* counts, ProjScratch sc, int filter, cudaStream_t st)
+{
+    static PerDeviceOnce b2_configured;
+    bool config_ok = true;
+    b2_configured.run([&] {
+        config_ok = cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128)) == cudaSuccess &&
+                    cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+    });
+    if (!config_ok) return TAD_CUDA_ERROR;
+    const int bt = K <= 12 ? 128 : 64;
+    project_kernel_b<K, 2><<<(unsigned)((n + bt - 1) / bt), bt, b2_smem_bytes<K>(bt), st>>>(n, stride, eps, counts, sc, filter);
+    return TAD_OK;
 }
 
 // counts: device uint64[4] = {#decomposed, #rebuilt, #full solver, unused}.  scratch_d: project_scratch_doubles<K>(stride)
@@ -451,30 +501,42 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         sc.codes = codes;
         sc.list = list;
         const unsigned g = (unsigned)((n + 127) / 128);
-        count_launch(4 + (fuse_out ? 0 : 1));
-        // translation null-space test for the element shapes of the fused path (d <= 3 variables per handle, <= 4 handles)
-        if constexpr (K % 3 == 0 && K / 3 >= 2 && K / 3 <= 4)
+        // tdim: variable dimension of the term (translation null-space test of phase A), | 64: reduced pipeline wanted -- for
+        // four handles (K = 4 tdim) on the fused path: elements with the translation null space run phases B1 / B2 / C on K - tdim
+        const bool want_reduce = (tdim & 64) != 0 && fuse_out != nullptr;
+        tdim &= 63;
+        bool reduced = false;
+        if constexpr (K == 12 || K == 8)
         {
-            if (tdim == 3) project_kernel_a<K, 3><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+            constexpr int D = K / 4;
+            if (want_reduce && tdim == D)
+            {
+                reduced = true;
+                count_launch(6);   // A, B1 and B2 of both pipelines, the full-solver list kernel
+                project_kernel_a<K, D, true><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+                project_kernel_b1<K - D><<<g, 128, 0, st>>>(n, stride, sc, 1);
+                project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc, 0);
+                if (launch_b2<K - D>(n, stride, eps, counts, sc, 1, st) != TAD_OK || launch_b2<K>(n, stride, eps, counts, sc, 0, st) != TAD_OK)
+                    return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel B2");
+            }
         }
-        if constexpr (K % 2 == 0 && K / 2 >= 2 && K / 2 <= 4)
+        if (!reduced)
         {
-            if (tdim == 2) project_kernel_a<K, 2><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
-        }
-        if (!((tdim == 3 && K % 3 == 0 && K / 3 >= 2 && K / 3 <= 4) || (tdim == 2 && K % 2 == 0 && K / 2 >= 2 && K / 2 <= 4)))
-            project_kernel_a<K, 0><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
-        project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc);
-        {
-            static PerDeviceOnce b2_configured;
-            b2_configured.run([&] {
-                config_ok = cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem_bytes<K>(128)) == cudaSuccess &&
-                            cudaFuncSetAttribute(project_kernel_b<K, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-            });
-            if (!config_ok) return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel B2");
-            // 2 blocks per SM at 255 registers (no spills) beat 3 blocks at 168 registers with ~400 B of spills by 3-6 % (tools/proj_bench.cu);
-            // K <= 12: 128-thread blocks (61 KB of shared memory each at K = 12); larger K: smaller blocks keep the footprint per SM
-            const int bt = K <= 12 ? 128 : 64;
-            project_kernel_b<K, 2><<<(unsigned)((n + bt - 1) / bt), bt, b2_smem_bytes<K>(bt), st>>>(n, stride, eps, counts, sc);
+            count_launch(4 + (fuse_out ? 0 : 1));
+            // translation null-space test for the element shapes of the fused path (d <= 3 variables per handle, <= 4 handles)
+            if constexpr (K % 3 == 0 && K / 3 >= 2 && K / 3 <= 4)
+            {
+                if (tdim == 3) project_kernel_a<K, 3><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+            }
+            if constexpr (K % 2 == 0 && K / 2 >= 2 && K / 2 <= 4)
+            {
+                if (tdim == 2) project_kernel_a<K, 2><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+            }
+            if (!((tdim == 3 && K % 3 == 0 && K / 3 >= 2 && K / 3 <= 4) || (tdim == 2 && K % 2 == 0 && K / 2 >= 2 && K / 2 <= 4)))
+                project_kernel_a<K, 0><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
+            project_kernel_b1<K><<<g, 128, 0, st>>>(n, stride, sc, -1);
+            if (launch_b2<K>(n, stride, eps, counts, sc, -1, st) != TAD_OK)
+                return fail(TAD_CUDA_ERROR, "cannot configure shared memory of the projection kernel B2");
         }
         // elements whose inverse iteration did not converge (code PROJ_FALLBACK, listed in `list`): full eigensolver
         double* work = scratch_d + (size_t)(L::nR + L::nW) * stride;
@@ -489,6 +551,7 @@ int launch_project(double* hess, int64_t n, int64_t stride, double eps, unsigned
         }
         else
             project_kernel_list<K><<<kListBlocks, kListThreads, 0, st>>>(hess, stride, eps, counts, list, work);
+        sc.reduced = reduced ? 1 : 0;
         if (fuse_out) *fuse_out = sc;  // phase C is fused with the assembly by the caller
         else project_kernel_c<K><<<g, 128, 0, st>>>(hess, n, stride, eps, sc);
     }

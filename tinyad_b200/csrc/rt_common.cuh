@@ -197,6 +197,7 @@ struct ProjScratch
     double* W;       // [ProjLayout<K>::nW][stride]
     int32_t* codes;  // [stride] ProjectCode per element
     int64_t* list;   // elements handed to the full solver
+    int reduced = 0; // 1: elements with code bit PROJ_REDUCED_BIT went through the reduced pipeline (R / W in ProjLayout<K - D> order)
 };
 constexpr int kListBlocks = 148, kListThreads = 32;
 template <int K> size_t project_scratch_doubles(int64_t stride);

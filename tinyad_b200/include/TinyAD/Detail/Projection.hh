@@ -85,69 +85,20 @@ struct ProjLayout
     }
 };
 
-// Phase A: early-out 1 and Householder tridiagonalisation; the packed matrix lives in registers.
-// Returns PROJ_DOMINANT (nothing stored) or PROJ_UNCHANGED (R stored, continue with phase B).
-// D > 0 (variable dimension of a term whose K = D * N local variables are ordered handle by handle): also tests whether the D
-// TRANSLATIONS t_a (1 on component a of every handle) are null vectors of H, |H t_a|_inf <= 1e-13 max|H|, and stores the answer.
-// Every translation-invariant element energy has them (the tet / triangle deformation energies: 3 of the ~4.5 eigenpairs phase B2
-// would compute per tet); phase B2 then skips them and phase C adds their exactly known term, eps * (projector onto the translations).
-template <int K, int D = 0, class LoadFn, class StoreRFn>
-TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, const double eps)
+// Row p of the 4 x 4 Hadamard matrix (+-1/2 each): row 0 = (1,1,1,1)/2 spans the translation of four handles, rows 1..3 its complement
+TINYAD_HD constexpr int hadamard_sign(int p, int s)
+{
+    // p = 1: + + - -,  p = 2: + - + -,  p = 3: + - - +
+    return p == 0 ? 1 : (p == 1 ? (s < 2 ? 1 : -1) : (p == 2 ? ((s % 2 == 0) ? 1 : -1) : ((s == 0 || s == 3) ? 1 : -1)));
+}
+
+// Householder tridiagonalisation of the packed symmetric K x K matrix a (tile order, in registers, overwritten) and the stores of
+// phase A: d, e, taus, reflectors, max|H| into R (ProjLayout<K>).
+template <int K, class StoreRFn>
+TINYAD_HD TINYAD_INLINE void proj_tridiag_core(double (&a)[K * (K + 1) / 2], const double amax, StoreRFn&& store_r)
 {
     using L = ProjLayout<K>;
-    constexpr int H = L::H;
-    double a[H];
-    double amax = 0.0;
-    static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
-        constexpr int s = decltype(sc)::value;
-        a[s] = load(s);
-        amax = fmax(amax, fabs(a[s]));
-    });
 #define TAD_A(i, j) a[hess_seq_index(K, (i), (j))]
-
-    // ---- early-out 1: positive diagonally dominant (HessianProjection.hh:23-42, :62-63) ----
-    {
-        double offsum[K];
-        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { offsum[decltype(ic)::value] = 0.0; });
-        static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
-            constexpr int s = decltype(sc)::value;
-            constexpr int r = hess_seq_rc(K, s).row, c = hess_seq_rc(K, s).col;
-            if constexpr (r != c)
-            {
-                const double v = fabs(a[s]);
-                offsum[r] += v;
-                offsum[c] += v;
-            }
-        });
-        bool dominant = true;
-        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
-            constexpr int i = decltype(ic)::value;
-            if (TAD_A(i, i) < offsum[i] + eps) dominant = false;
-        });
-        if (dominant) return PROJ_DOMINANT;
-    }
-
-    if constexpr (D > 0 && K % (D > 0 ? D : 1) == 0 && K > D)
-    {
-        // row sums over the handles, per component: S(i, a) = sum_s H(i, D s + a)
-        double worst = 0.0;
-        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
-            constexpr int i = decltype(ic)::value;
-            static_for<D>([&](auto ac) TINYAD_LAMBDA_INLINE {
-                constexpr int a_ = decltype(ac)::value;
-                double sum = 0.0;
-                static_for<K / D>([&](auto sc) TINYAD_LAMBDA_INLINE {
-                    constexpr int j = D * decltype(sc)::value + a_;
-                    sum += a[hess_seq_index(K, i, j)];
-                });
-                worst = fmax(worst, fabs(sum));
-            });
-        });
-        store_r(L::off_tnull, (worst <= 1e-13 * amax) ? (double)D : 0.0);
-    }
-    else
-        store_r(L::off_tnull, 0.0);
-
     double d0[K], e0[K];  // tridiagonal T: d0[i] = T(i,i), e0[i] = T(i+1,i); e0[K-1] = 0
     double tau[K > 2 ? K - 2 : 1];
 
@@ -241,6 +192,132 @@ TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, cons
         });
     });
 #undef TAD_A
+}
+
+// PROJ_* code bit: the element goes through the REDUCED pipeline (proj_tridiagonalize<K, D, true>): phases B1 / B2 / C on K - D
+constexpr int PROJ_REDUCED_BIT = 16;
+
+// Phase A: early-out 1 and Householder tridiagonalisation; the packed matrix lives in registers.
+// Returns PROJ_DOMINANT (nothing stored) or PROJ_UNCHANGED (R stored, continue with phase B).
+// D > 0 (variable dimension of a term whose K = D * N local variables are ordered handle by handle): also tests whether the D
+// TRANSLATIONS t_a (1 on component a of every handle) are null vectors of H, |H t_a|_inf <= 1e-13 max|H|, and stores the answer.
+// Every translation-invariant element energy has them (the tet / triangle deformation energies: 3 of the ~4.5 eigenpairs phase B2
+// would compute per tet); phase B2 then skips them and phase C adds their exactly known term, eps * (projector onto the translations).
+// REDUCE (needs D > 0 and four handles, K = 4 D): when the translations are null vectors, H is mapped to the (K - D) x (K - D)
+// matrix of its action on their orthogonal complement -- for four handles a 2-D Hadamard transform over the 4 x 4 grid of D x D
+// blocks, additions and one scale -- and THAT matrix is tridiagonalised (stored in ProjLayout<K - D> order; the returned code
+// carries PROJ_REDUCED_BIT).  Phases B1 / B2 then run on K - D = 9 instead of 12 (QL ~ K^2) without the null cluster, and phase C
+// (proj_apply<K, K - D>) maps the eigenvectors back.  Elements that fail the translation test take the general path.
+template <int K, int D = 0, bool REDUCE = false, class LoadFn, class StoreRFn>
+TINYAD_HD inline int proj_tridiagonalize(LoadFn&& load, StoreRFn&& store_r, const double eps)
+{
+    using L = ProjLayout<K>;
+    constexpr int H = L::H;
+    double a[H];
+    double amax = 0.0;
+    static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+        constexpr int s = decltype(sc)::value;
+        a[s] = load(s);
+        amax = fmax(amax, fabs(a[s]));
+    });
+#define TAD_A(i, j) a[hess_seq_index(K, (i), (j))]
+
+    // ---- early-out 1: positive diagonally dominant (HessianProjection.hh:23-42, :62-63) ----
+    {
+        double offsum[K];
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { offsum[decltype(ic)::value] = 0.0; });
+        static_for<H>([&](auto sc) TINYAD_LAMBDA_INLINE {
+            constexpr int s = decltype(sc)::value;
+            constexpr int r = hess_seq_rc(K, s).row, c = hess_seq_rc(K, s).col;
+            if constexpr (r != c)
+            {
+                const double v = fabs(a[s]);
+                offsum[r] += v;
+                offsum[c] += v;
+            }
+        });
+        bool dominant = true;
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            if (TAD_A(i, i) < offsum[i] + eps) dominant = false;
+        });
+        if (dominant) return PROJ_DOMINANT;
+    }
+
+    bool tnull = false;
+    if constexpr (D > 0 && K % (D > 0 ? D : 1) == 0 && K > D)
+    {
+        // row sums over the handles, per component: S(i, a) = sum_s H(i, D s + a)
+        double worst = 0.0;
+        static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+            constexpr int i = decltype(ic)::value;
+            static_for<D>([&](auto ac) TINYAD_LAMBDA_INLINE {
+                constexpr int a_ = decltype(ac)::value;
+                double sum = 0.0;
+                static_for<K / D>([&](auto sc) TINYAD_LAMBDA_INLINE {
+                    constexpr int j = D * decltype(sc)::value + a_;
+                    sum += a[hess_seq_index(K, i, j)];
+                });
+                worst = fmax(worst, fabs(sum));
+            });
+        });
+        tnull = worst <= 1e-13 * amax && amax > 0.0;
+    }
+    if constexpr (REDUCE && D > 0 && K == 4 * (D > 0 ? D : 1))
+    {
+        if (tnull)
+        {
+            // H~_pq = 1/4 sum_s sum_t sg(p, s) sg(q, t) B_st for the Hadamard rows p, q = 1..3 (row 0 = the translations): first over
+            // s (G_pt = sum_s sg(p, s) B_st), then over t; only the lower block triangle p >= q of the symmetric result is formed
+            constexpr int KR = K - D;
+            double ar[KR * (KR + 1) / 2];
+            static_for<3>([&](auto pc) TINYAD_LAMBDA_INLINE {
+                constexpr int p = decltype(pc)::value + 1;
+                static_for<D>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    constexpr int i = decltype(ic)::value;
+                    double g[4][D];   // G_pt(i, j), t = 0..3
+                    static_for<4>([&](auto tc) TINYAD_LAMBDA_INLINE {
+                        constexpr int t = decltype(tc)::value;
+                        static_for<D>([&](auto jc) TINYAD_LAMBDA_INLINE {
+                            constexpr int j = decltype(jc)::value;
+                            double sum = 0.0;
+                            static_for<4>([&](auto sc) TINYAD_LAMBDA_INLINE {
+                                constexpr int s_ = decltype(sc)::value;
+                                const double v = a[hess_seq_index(K, s_ * D + i, t * D + j)];
+                                if constexpr (hadamard_sign(p, s_) > 0) sum += v; else sum -= v;
+                            });
+                            g[t][j] = sum;
+                        });
+                    });
+                    static_for<p>([&](auto qc) TINYAD_LAMBDA_INLINE {
+                        constexpr int q = decltype(qc)::value + 1;   // q <= p
+                        static_for<D>([&](auto jc) TINYAD_LAMBDA_INLINE {
+                            constexpr int j = decltype(jc)::value;
+                            if constexpr (q < p || j <= i)
+                            {
+                                double sum = 0.0;
+                                static_for<4>([&](auto tc) TINYAD_LAMBDA_INLINE {
+                                    constexpr int t = decltype(tc)::value;
+                                    if constexpr (hadamard_sign(q, t) > 0) sum += g[t][j]; else sum -= g[t][j];
+                                });
+                                ar[hess_seq_index(KR, (p - 1) * D + i, (q - 1) * D + j)] = 0.25 * sum;
+                            }
+                        });
+                    });
+                });
+            });
+            // max|H| stays the scale of the accuracy targets (the transform is orthogonal)
+            proj_tridiag_core<KR>(ar, amax, store_r);
+            store_r(ProjLayout<KR>::off_tnull, 0.0);   // nothing left to deflate in the reduced matrix
+            return PROJ_UNCHANGED | PROJ_REDUCED_BIT;
+        }
+        store_r(L::off_tnull, 0.0);
+    }
+    else
+        store_r(L::off_tnull, tnull ? (double)D : 0.0);
+
+#undef TAD_A
+    proj_tridiag_core<K>(a, amax, store_r);
     return PROJ_UNCHANGED;
 }
 
@@ -726,49 +803,55 @@ TINYAD_HD inline int proj_select_vectors(LoadRFn&& load_r, LoadLamFn&& load_lam,
 // preload(nv): optional asynchronous copy of the nv vectors and weights from W straight into the scratch (slot jv (K+1) + i <-
 // W[off_vec + jv K + i], slot jv (K+1) + K <- W[off_wgt + jv]); returns true if it did so.  preload_wait() completes it.  The
 // fused kernel uses cp.async here, so these loads overlap the reflector loads and cost no registers.
-template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn, class TmpStoreFn, class TmpLoadFn, class PreloadFn, class PreloadWaitFn>
+// KR < K (reduced pipeline, proj_tridiagonalize<K, D, true>, D = K - KR, four handles): R and W are in ProjLayout<KR> order, the
+// eigenvectors are those of the KR x KR matrix on the complement of the translations; after the reflectors they are mapped back
+// with the Hadamard rows 1..3, v[s D + i] = 1/2 sum_p sg(p, s) y[(p - 1) D + i], and the translations' own term eps * projector is
+// added in closed form (form 0 only: the bases of the other forms contain it).  preload(nv) then fills slots jv (K + 1) + i, i < KR.
+template <int K, int KR = K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn, class TmpStoreFn, class TmpLoadFn, class PreloadFn, class PreloadWaitFn>
 TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps, TmpStoreFn&& tmp_store,
                                  TmpLoadFn&& tmp_load, PreloadFn&& preload, PreloadWaitFn&& preload_wait)
 {
-    using L = ProjLayout<K>;
-    constexpr int H = L::H;
+    using L = ProjLayout<KR>;          // layout of R / W: the matrix that was decomposed
+    constexpr int H = K * (K + 1) / 2;
+    constexpr int DR = K - KR;         // dimension of the translation space removed by the reduction (0: none)
+    static_assert(KR == K || (DR > 0 && K == 4 * DR), "the reduced pipeline is for four handles");
     const int nv = (int)load_w(0);
     const int form_code = (int)load_w(1);
-    const int form = form_code & 7, tn = form_code >> 3;
+    const int form = form_code & 7, tn = (KR == K) ? (form_code >> 3) : ((form == 0) ? DR : 0);
     const bool preloaded = preload(nv);
     {
         // reflectors in registers; each vector goes v = H_0 H_1 ... H_{K-3} y
         double refl[L::n_v > 0 ? L::n_v : 1], tau[L::n_refl > 0 ? L::n_refl : 1];
         static_for<L::n_v>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; refl[i] = load_r(L::off_v + i); });
         static_for<L::n_refl>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tau[i] = load_r(L::off_tau + i); });
-        double ynext[K], wnext = 0.0;
+        double ynext[KR], wnext = 0.0;
         if (preloaded) preload_wait();
         else if (nv > 0)
         {
-            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; ynext[i] = load_w(L::off_vec + i); });
+            static_for<KR>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; ynext[i] = load_w(L::off_vec + i); });
             wnext = load_w(L::off_wgt);
         }
         for (int jv = 0; jv < nv; ++jv)
         {
-            double y[K];
+            double y[KR];
             double wj = wnext;
             if (preloaded)
-                static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = tmp_load(jv * (K + 1) + i); });
+                static_for<KR>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = tmp_load(jv * (K + 1) + i); });
             else
             {
-                static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = ynext[i]; });
+                static_for<KR>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; y[i] = ynext[i]; });
                 if (jv + 1 < nv)
                 {
-                    static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                    static_for<KR>([&](auto ic) TINYAD_LAMBDA_INLINE {
                         constexpr int i = decltype(ic)::value;
-                        ynext[i] = load_w(L::off_vec + (jv + 1) * K + i);
+                        ynext[i] = load_w(L::off_vec + (jv + 1) * KR + i);
                     });
                     wnext = load_w(L::off_wgt + jv + 1);
                 }
             }
             static_for<L::n_refl>([&](auto kc) TINYAD_LAMBDA_INLINE {
-                constexpr int k = K - 3 - decltype(kc)::value;
-                constexpr int n = K - k - 1;
+                constexpr int k = KR - 3 - decltype(kc)::value;
+                constexpr int n = KR - k - 1;
                 constexpr int vo = L::v_index(k, 0) - L::off_v;
                 double s = y[k + 1];
                 static_for<n - 1>([&](auto ic) TINYAD_LAMBDA_INLINE {
@@ -782,7 +865,21 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
                     y[k + 2 + i] = fma(-s, refl[vo + i], y[k + 2 + i]);
                 });
             });
-            static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tmp_store(jv * (K + 1) + i, y[i]); });
+            if constexpr (KR == K)
+                static_for<K>([&](auto ic) TINYAD_LAMBDA_INLINE { constexpr int i = decltype(ic)::value; tmp_store(jv * (K + 1) + i, y[i]); });
+            else
+                static_for<4>([&](auto sc) TINYAD_LAMBDA_INLINE {   // back to the K variables of the four handles
+                    constexpr int s_ = decltype(sc)::value;
+                    static_for<DR>([&](auto ic) TINYAD_LAMBDA_INLINE {
+                        constexpr int i = decltype(ic)::value;
+                        double v = 0.0;
+                        static_for<3>([&](auto pc) TINYAD_LAMBDA_INLINE {
+                            constexpr int p = decltype(pc)::value + 1;
+                            if constexpr (hadamard_sign(p, s_) > 0) v += y[(p - 1) * DR + i]; else v -= y[(p - 1) * DR + i];
+                        });
+                        tmp_store(jv * (K + 1) + s_ * DR + i, 0.5 * v);
+                    });
+                });
             if (!preloaded) tmp_store(jv * (K + 1) + K, wj);
         }
     }
@@ -826,12 +923,12 @@ TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& lo
 }
 
 // with a thread-local scratch array (host; kernels without shared memory)
-template <int K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn>
+template <int K, int KR = K, class LoadRFn, class LoadWFn, class LoadFn, class StoreFn>
 TINYAD_HD inline void proj_apply(LoadRFn&& load_r, LoadWFn&& load_w, LoadFn&& load, StoreFn&& store, const double eps)
 {
     double tmp[ProjLayout<K>::MAXV * (K + 1)];
-    proj_apply<K>(load_r, load_w, load, store, eps, [&](int i, double v) { tmp[i] = v; }, [&](int i) { return tmp[i]; },
-                  [](int) { return false; }, [] {});
+    proj_apply<K, KR>(load_r, load_w, load, store, eps, [&](int i, double v) { tmp[i] = v; }, [&](int i) { return tmp[i]; },
+                      [](int) { return false; }, [] {});
 }
 
 // All three phases on one element through local scratch (host tests; the kernels run the phases separately).
@@ -853,6 +950,45 @@ TINYAD_HD inline int project_element(LoadFn&& load, StoreFn&& store, const doubl
     return PROJ_REBUILT;
 }
 
+
+// The reduced pipeline on one element (host tests; the kernels run its phases separately): four handles of D variables each.
+template <int K, int D, class LoadFn, class StoreFn>
+TINYAD_HD inline int project_element_reduced(LoadFn&& load, StoreFn&& store, const double eps)
+{
+    static_assert(D > 0 && K == 4 * D, "four handles");
+    constexpr int KR = K - D;
+    using L = ProjLayout<K>;
+    using LR = ProjLayout<KR>;
+    double R[L::nR], Wb[L::nW];
+    int code = proj_tridiagonalize<K, D, true>(load, [&](int i, double v) { R[i] = v; }, eps);
+    if (code == PROJ_DOMINANT) return code;
+    if (code & PROJ_REDUCED_BIT)
+    {
+        code = proj_eigenvalues<KR>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; });
+        if (code == PROJ_FALLBACK) return code;
+        code = proj_select_vectors<KR>([&](int i) { return R[i]; }, [&](int i) { return R[LR::off_lam + i]; }, [&](int i, double v) { R[LR::off_lam + i] = v; },
+                                       [&](int i, double v) { Wb[i] = v; }, [&](int jv, const double (&v)[KR]) { for (int q = 0; q < KR; ++q) Wb[LR::off_vec + jv * KR + q] = v[q]; },
+                                       [&](int jv, double (&v)[KR]) { for (int q = 0; q < KR; ++q) v[q] = Wb[LR::off_vec + jv * KR + q]; }, eps);
+        if (code == PROJ_FALLBACK) return code;
+        if (code == PROJ_UNCHANGED)
+        {
+            // nothing moves in the complement: only the translations' own eigenvalue 0 is below eps > 0
+            if (!(eps > 0.0)) return PROJ_UNCHANGED;
+            Wb[0] = 0.0;
+            Wb[1] = 0.0;
+        }
+        proj_apply<K, KR>([&](int i) { return R[i]; }, [&](int i) { return Wb[i]; }, load, store, eps);
+        return PROJ_REBUILT | PROJ_REDUCED_BIT;
+    }
+    code = proj_eigenvalues<K>([&](int i) { return R[i]; }, [&](int i, double v) { R[i] = v; });
+    if (code == PROJ_FALLBACK) return code;
+    code = proj_select_vectors<K>([&](int i) { return R[i]; }, [&](int i) { return R[L::off_lam + i]; }, [&](int i, double v) { R[L::off_lam + i] = v; },
+                                  [&](int i, double v) { Wb[i] = v; }, [&](int jv, const double (&v)[K]) { for (int q = 0; q < K; ++q) Wb[L::off_vec + jv * K + q] = v[q]; },
+                                  [&](int jv, double (&v)[K]) { for (int q = 0; q < K; ++q) v[q] = Wb[L::off_vec + jv * K + q]; }, eps);
+    if (code != PROJ_REBUILT) return code;
+    proj_apply<K>([&](int i) { return R[i]; }, [&](int i) { return Wb[i]; }, load, store, eps);
+    return PROJ_REBUILT;
+}
 
 // Full eigendecomposition of one packed matrix by cyclic Jacobi rotations, all in thread-local arrays: the in-kernel fallback of
 // the fused small-k element kernel (TinyAD/Kernels.cuh) for the few elements per million whose inverse iteration does not converge

@@ -235,9 +235,12 @@ private:
     {
         double *x = nullptr, *g = nullptr, *r = nullptr, *J = nullptr;
         int64_t nv, no, nnz = 0;
+        int prev_device = -1;   // the scratch lives on the function's device (settings.device), whatever the caller's current device is
         Scratch(const VectorFunction& fn, const std::vector<double>& _x, bool jac) : nv(fn.n_vars), no(fn.n_outputs)
         {
             if ((int64_t)_x.size() != nv) throw std::runtime_error("[TinyAD-B200] x.size() != n_vars");
+            cuda_check(cudaGetDevice(&prev_device));
+            if (prev_device != fn.settings.device) cuda_check(cudaSetDevice(fn.settings.device));
             if (jac) detail::check(tad_function_pattern(fn.h, nullptr, &nnz));
             cuda_check(cudaMalloc(&x, sizeof(double) * (size_t)(nv + 1)));
             cuda_check(cudaMalloc(&g, sizeof(double) * (size_t)(nv + 1)));
@@ -245,7 +248,11 @@ private:
             cuda_check(cudaMalloc(&J, sizeof(double) * (size_t)(nnz + 1)));
             cuda_check(cudaMemcpy(x, _x.data(), sizeof(double) * (size_t)nv, cudaMemcpyHostToDevice));
         }
-        ~Scratch() { cudaFree(x); cudaFree(g); cudaFree(r); cudaFree(J); }
+        ~Scratch()
+        {
+            cudaFree(x); cudaFree(g); cudaFree(r); cudaFree(J);
+            if (prev_device >= 0) cudaSetDevice(prev_device);
+        }
         void download(std::vector<double>* _g, std::vector<double>* _r, std::vector<double>* _J)
         {
             if (_g) { _g->resize((size_t)nv); cuda_check(cudaMemcpy(_g->data(), g, sizeof(double) * (size_t)nv, cudaMemcpyDeviceToHost)); }
