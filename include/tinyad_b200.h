@@ -166,7 +166,7 @@ int tad_function_add_pattern_blocks(tad_function f, int64_t n_blocks, const int6
 int tad_comm_unique_id(void* id_out /* TAD_COMM_ID_BYTES */);
 int tad_comm_create(const void* id, int rank, int world, int device, tad_comm* out);
 int tad_comm_adopt(void* nccl_comm, int rank, int world, int device, tad_comm* out);
-void tad_comm_destroy(tad_comm c);
+void tad_comm_destroy(tad_comm c);   /* after the functions that use it have been destroyed or detached (tad_function_set_comm(f, NULL)) */
 int tad_comm_rank(tad_comm c);
 int tad_comm_world(tad_comm c);
 int tad_function_set_comm(tad_function f, tad_comm c);                 /* c = NULL detaches; the pattern is rebuilt on next use */
