@@ -3,7 +3,7 @@
 
   python bench.py --gpus 1 --steps K --warmup W            # this framework, one B200: C5 (10.1 M tets), the north-star configuration
   torchrun ... bench.py --gpus N ...                        # N ranks: C5 split in N z-slabs (strong scaling), exchange inside the runtime
-  python bench.py --impl reference ...                      # the reference's CPU/OpenMP algorithm (oracle port) on the same workload
+  python bench.py --impl reference ...                      # the reference's own CPU/OpenMP code (oracle/_ref; else the oracle port) on the same workload
 
 A "step" is one eval_with_hessian_proj over the whole mesh: x is resident in HBM, f / g / CSR values are
 left in HBM (`value`); `e2e` times the same call through the host-buffer C ABI (pinned host x, g, H values;
@@ -163,44 +163,62 @@ class CpuSample:
             self.what = f"first {layers} of {n} grid rows of the {n}x{n} grid ({len(F):,} triangles)"
         self.x = meshes.deform(V, 1.0 / n, seed=0).reshape(-1)
 
-    def step(self, threads):
+    def step(self, threads, engine="port"):
+        """engine "reference": oracle/_ref (the unmodified TinyAD headers over oracle/eigen_shim); "port": the oracle restatement."""
         import oracle
+        fn = oracle.ref_scalar_eval if engine == "reference" else oracle.scalar_eval
         t0 = time.perf_counter()
-        r = oracle.scalar_eval(self.d, self.nv, self.terms, oracle.HESSIAN_PROJ, self.x, n_threads=threads)
+        r = fn(self.d, self.nv, self.terms, oracle.HESSIAN_PROJ, self.x, n_threads=threads)
         return time.perf_counter() - t0, r.phases
 
 
-def cpu_sample_for(workload, budget_s, threads):
+def cpu_engine():
+    """("reference", description) when oracle/_ref/libtinyad_ref.so exists (built in the build container from /root/reference, shipped
+    prebuilt to the GPU box), else ("port", description)."""
+    import oracle
+    if oracle.ref_available():
+        return "reference", ("oracle/_ref = the reference's own headers (TinyAD::ScalarFunction::eval_with_hessian_proj, unmodified, compiled "
+                             "in place) over oracle/eigen_shim, a minimal eager stand-in for the Eigen API (Eigen is not in the image; real "
+                             "Eigen would vectorise the fixed-size Hessian updates)")
+    return "port", "oracle = C++/OpenMP restatement of the reference path (oracle/_ref is not built on this machine)"
+
+
+def cpu_sample_for(workload, budget_s, threads, engine="port"):
     """Chooses the number of layers so that one step takes about budget_s seconds on `threads` threads (calibrated on one layer)."""
     probe = CpuSample(workload, 1)
-    probe.step(threads)                         # warm-up (OpenMP pool, page faults)
-    t1, _ = probe.step(threads)
+    probe.step(threads, engine)                 # warm-up (OpenMP pool, page faults)
+    t1, _ = probe.step(threads, engine)
     layers = int(max(1, min(probe.n, budget_s / max(t1, 1e-4))))
     return probe if layers == 1 else CpuSample(workload, layers)
 
 
 def cpu_baseline(workload, budget_s=4.0):
-    """cpu_baseline leg of the product line: the CPU oracle (port of the reference's OpenMP eval_with_hessian_proj) on a bounded
+    """cpu_baseline leg of the product line: the reference's OpenMP eval_with_hessian_proj (oracle/_ref, else the oracle port) on a bounded
     sample of the same workload, all host threads and the reference's default (max - 1, Detail/Parallel.hh:27)."""
     threads = host_threads()
-    smp = cpu_sample_for(workload, budget_s, threads)
+    engine, what = cpu_engine()
+    smp = cpu_sample_for(workload, budget_s, threads, engine)
     times, phases = [], None
     for _ in range(3):
-        t, phases = smp.step(threads)
+        t, phases = smp.step(threads, engine)
         times.append(t)
     t = float(np.median(times))
-    out = {"value": smp.n_el / t, "unit": UNIT, "cores": threads, "kind": "port",
-           "sample": f"{smp.what}, same x / energy / eps as the GPU arm, median of 3 steps after warm-up; oracle = C++/OpenMP restatement of the "
-                     f"reference path (the reference itself needs Eigen, which is not installed)",
-           "phases_s": {k: phases[k] for k in ("eval_s", "accumulate_s", "compress_s")}, "seconds_per_step": t}
+    out = {"value": smp.n_el / t, "unit": UNIT, "cores": threads, "kind": engine,
+           "sample": f"{smp.what}, same x / energy / eps as the GPU arm, median of 3 steps after warm-up; {what}",
+           "phases_s": phases, "seconds_per_step": t}
     if threads > 1:
-        td, _ = smp.step(threads - 1)
+        td, _ = smp.step(threads - 1, engine)
         out["reference_default_threads"] = {"cores": threads - 1, "value": smp.n_el / td, "note": "Detail/Parallel.hh:27: omp_get_max_threads() - 1"}
+    if engine == "reference":
+        tp, pp = smp.step(threads, "port")
+        out["oracle_port"] = {"value": smp.n_el / tp, "cores": threads, "phases_s": {k: pp[k] for k in ("eval_s", "accumulate_s", "compress_s")},
+                              "note": "the oracle restatement (the checker of the parity tests) on the same sample"}
     return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; TinyAD + Eigen cannot be built here) on the box's host cores,
+    """--impl reference: the reference's own CPU path (oracle/_ref: the unmodified TinyAD headers over an Eigen-API shim; the oracle
+    port where that library is absent) on the box's host cores,
     thread count set explicitly (torchrun exports OMP_NUM_THREADS=1), on the SAME workload as the product arm.  Each step is a
     bounded sample of that workload (whole cube layers of the same mesh, same x) sized so that warm-up + steps end within minutes."""
     rank = int(os.environ.get("RANK", "0"))
@@ -209,21 +227,26 @@ def run_reference(args):
     import oracle
     oracle.lib()
     threads = host_threads()
+    engine, what = cpu_engine()
     workload = args.workload if args.workload in WORKLOADS else "c5"
     total = max(1, args.steps + args.warmup)
     budget = min(6.0, max(0.5, 150.0 / total))          # seconds per step: the whole run stays below ~3 minutes
-    smp = cpu_sample_for(workload, budget, threads)
+    smp = cpu_sample_for(workload, budget, threads, engine)
     times = []
     for i in range(args.warmup + args.steps):
-        t, phases = smp.step(threads)
+        t, phases = smp.step(threads, engine)
         if i >= args.warmup:
             times.append(t)
     t = float(np.mean(times))
     value = smp.n_el / t
     extra = {}
     if threads > 1:
-        td, _ = smp.step(threads - 1)
+        td, _ = smp.step(threads - 1, engine)
         extra = {"reference_default_threads": {"cores": threads - 1, "value": smp.n_el / td, "note": "Detail/Parallel.hh:27: omp_get_max_threads() - 1"}}
+    if engine == "reference":
+        tp, pp = smp.step(threads, "port")
+        extra["oracle_port"] = {"value": smp.n_el / tp, "cores": threads, "phases_s": {k: pp[k] for k in ("eval_s", "accumulate_s", "compress_s")},
+                                "note": "the oracle restatement (the checker of the parity tests) on the same sample"}
     full_n = {"c5": 10110954, "c2": 998250, "small": 24576, "c1": 524288}[workload]
     line = {"metric": METRIC if WORKLOADS[workload][0] == "tet" else METRIC_TRI, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup,
@@ -231,10 +254,9 @@ def run_reference(args):
             "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOADS[workload][2], "elements_total": full_n, "eps": 1e-9,
                        "elements_per_step": smp.n_el, "seconds_full_workload_extrapolated": full_n / value},
-            "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                                  "sample": f"each step: {smp.what} of the same workload (same x, energy, eps); oracle port of the reference's OpenMP "
-                                            f"path (the reference itself needs Eigen, absent here); {threads} threads set explicitly",
-                                  "phases_s": {k: phases[k] for k in ("eval_s", "accumulate_s", "compress_s")}}, **extra),
+            "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": threads, "kind": engine,
+                                  "sample": f"each step: {smp.what} of the same workload (same x, energy, eps); {what}; {threads} threads set explicitly",
+                                  "phases_s": phases}, **extra),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -178,5 +178,112 @@ def default_threads():
     return lib().oracle_default_threads()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the UNMODIFIED reference headers compiled over oracle/eigen_shim (ref_driver.cc).  Used to check the
+# restatement above (tests/test_oracle_vs_reference.py) and as the `--impl reference` arm of bench.py.
+# ---------------------------------------------------------------------------------------------------------------------
+_REF = None
+REFERENCE_ROOT = "/root/reference"
+
+
+def ref_path():
+    return os.path.join(_HERE, "_ref", "libtinyad_ref.so")
+
+
+def build_ref(force=False):
+    """Compile oracle/_ref/libtinyad_ref.so from the reference headers where they lie; needs /root/reference
+    (the build container).  Elsewhere the prebuilt file is used as is.  Returns the path or None."""
+    so = ref_path()
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "include", "TinyAD")):
+        srcs = [os.path.join(_HERE, f) for f in ("ref_driver.cc", "eigen_shim/Eigen/src/Shim.h", "Makefile")]
+        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["make", "-C", _HERE, "_ref/libtinyad_ref.so"], check=True, capture_output=True)
+    return so if os.path.exists(so) else None
+
+
+def ref_available():
+    return os.path.exists(ref_path())
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        so = build_ref()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libtinyad_ref.so is not built (make -C oracle _ref, needs /root/reference)")
+        L = ctypes.CDLL(so)
+        L.ref_scalar_eval.restype = ctypes.c_void_p
+        L.ref_scalar_eval.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+        L.ref_vector_eval.restype = ctypes.c_void_p
+        L.ref_vector_eval.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_int]
+        L.ref_last_error.restype = ctypes.c_char_p
+        L.ref_description.restype = ctypes.c_char_p
+        for n in ("f", "seconds"):
+            f = getattr(L, "ref_result_" + n)
+            f.restype = ctypes.c_double
+            f.argtypes = [ctypes.c_void_p]
+        for n in ("nnz", "rows", "cols", "g_size", "r_size"):
+            f = getattr(L, "ref_result_" + n)
+            f.restype = ctypes.c_int64
+            f.argtypes = [ctypes.c_void_p]
+        L.ref_result_copy.argtypes = [ctypes.c_void_p] * 6
+        L.ref_result_free.argtypes = [ctypes.c_void_p]
+        L.ref_project.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
+        _REF = L
+    return _REF
+
+
+def _ref_collect(L, h, want_matrix):
+    if not h:
+        raise RuntimeError(L.ref_last_error().decode())
+    try:
+        res = Result(f=L.ref_result_f(h))
+        res.g = np.empty(L.ref_result_g_size(h))
+        res.r = np.empty(L.ref_result_r_size(h))
+        rows, cols, nnz = L.ref_result_rows(h), L.ref_result_cols(h), L.ref_result_nnz(h)
+        res.shape = (rows, cols)
+        if want_matrix:
+            res.outer = np.empty(cols + 1, dtype=np.int32)
+            res.inner = np.empty(nnz, dtype=np.int32)
+            res.values = np.empty(nnz)
+        L.ref_result_copy(h, res.g.ctypes.data, res.r.ctypes.data,
+                          res.outer.ctypes.data if want_matrix else None,
+                          res.inner.ctypes.data if want_matrix else None,
+                          res.values.ctypes.data if want_matrix else None)
+        res.phases = {"total_s": L.ref_result_seconds(h)}
+        return res
+    finally:
+        L.ref_result_free(h)
+
+
+def ref_scalar_eval(d, n_vertices, terms, mode, x, eps=1e-9, n_threads=-1):
+    """TinyAD::ScalarFunction::eval* of the reference itself (same arguments as scalar_eval)."""
+    L = ref_lib()
+    arr, keep = _terms_array(terms)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    assert x.size == d * n_vertices
+    h = L.ref_scalar_eval(d, n_vertices, len(terms), ctypes.addressof(arr), mode, x.ctypes.data, eps, n_threads)
+    return _ref_collect(L, h, mode >= 2)
+
+
+def ref_vector_eval(d, n_vertices, terms, mode, x, n_threads=-1):
+    """TinyAD::VectorFunction::eval* of the reference itself (same arguments as vector_eval)."""
+    L = ref_lib()
+    arr, keep = _terms_array(terms)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    h = L.ref_vector_eval(d, n_vertices, len(terms), ctypes.addressof(arr), mode, x.ctypes.data, n_threads)
+    return _ref_collect(L, h, mode in (1, 3))
+
+
+def ref_project(H, eps=1e-9):
+    """TinyAD::project_positive_definite of the reference on one dense symmetric matrix."""
+    A = np.array(H, dtype=np.float64, order="C")
+    if ref_lib().ref_project(A.shape[0], A.ctypes.data, eps) < 0:
+        raise RuntimeError(ref_lib().ref_last_error().decode())
+    return A
+
+
 def max_threads():
     return lib().oracle_max_threads()
