@@ -21,7 +21,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <iostream>
 #include <limits>
+#include <list>
+#include <map>
+#include <numeric>
+#include <sstream>
 #include <string>
 #include <ostream>
 #include <stdexcept>
@@ -393,6 +398,20 @@ public:
             if (!(lin_rc(i) == lin_rc(i))) return true;
         return false;
     }
+    bool isZero(double prec = 1e-12) const
+    {
+        using std::abs;
+        for (Index i = 0; i < size(); ++i)
+            if ((double)abs(lin_rc(i)) > prec) return false;
+        return true;
+    }
+    Matrix<Scalar, Dynamic, Dynamic> replicate(Index rf, Index cf) const
+    {
+        Matrix<Scalar, Dynamic, Dynamic> r(rows() * rf, cols() * cf);
+        for (Index j = 0; j < r.cols(); ++j)
+            for (Index i = 0; i < r.rows(); ++i) r(i, j) = (*this)(i % rows(), j % cols());
+        return r;
+    }
     template <typename O>
     bool isApprox(const MatrixBase<O>& o, double prec = 1e-12) const
     {
@@ -741,6 +760,15 @@ public:
         s_.data()[3] = T(d);
     }
 
+    // { a, b, c, ... }: the coefficients of a vector
+    Matrix(std::initializer_list<T> l)
+    {
+        if constexpr (!fixed) resize_vec((Index)l.size());
+        if ((Index)l.size() != this->size()) throw std::logic_error("eigen shim: initializer list of the wrong length");
+        Index i = 0;
+        for (const T& v : l) s_.data()[i++] = v;
+    }
+
     template <typename D>
     Matrix& operator=(const MatrixBase<D>& o)
     {
@@ -818,6 +846,21 @@ public:
         m.setConstant(v);
         return m;
     }
+    // uniform in [-1, 1] from a fixed-seed generator (tests only ask for "some" matrix)
+    static Matrix Random() { return Matrix().randomize(); }
+    static Matrix Random(Index n)
+    {
+        Matrix m;
+        m.resize_vec(n);
+        return m.randomize();
+    }
+    static Matrix Random(Index r, Index c)
+    {
+        Matrix m;
+        m.resize(r, c);
+        return m.randomize();
+    }
+    Matrix& setRandom() { return randomize(); }
     static Matrix Ones() { return Constant(T(1)); }
     static Matrix Ones(Index n) { return Constant(n, T(1)); }
     static Matrix Ones(Index r, Index c) { return Constant(r, c, T(1)); }
@@ -845,6 +888,16 @@ public:
     static Matrix UnitZ() { return Unit(2); }
 
 private:
+    Matrix& randomize()
+    {
+        static thread_local unsigned long long state = 0x9E3779B97F4A7C15ull;
+        for (Index i = 0; i < this->size(); ++i)
+        {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            s_.data()[i] = T((double)(state >> 11) / 9007199254740992.0 * 2.0 - 1.0);
+        }
+        return *this;
+    }
     void resize_vec(Index n)
     {
         if constexpr (fixed)
@@ -1205,6 +1258,29 @@ TINYAD_SHIM_TYPEDEFS(float, f)
 TINYAD_SHIM_TYPEDEFS(int, i)
 #undef TINYAD_SHIM_TYPEDEFS
 
+// the alias templates of Eigen 3.4 (the reference's tests/Meshes.hh uses them after including only <Eigen/Core>);
+// Detail/EigenVectorTypedefs.hh declares the same aliases again, which is a valid redeclaration
+template <typename Type> using Matrix2 = Matrix<Type, 2, 2>;
+template <typename Type> using Vector2 = Matrix<Type, 2, 1>;
+template <typename Type> using RowVector2 = Matrix<Type, 1, 2>;
+template <typename Type> using Matrix3 = Matrix<Type, 3, 3>;
+template <typename Type> using Vector3 = Matrix<Type, 3, 1>;
+template <typename Type> using RowVector3 = Matrix<Type, 1, 3>;
+template <typename Type> using Matrix4 = Matrix<Type, 4, 4>;
+template <typename Type> using Vector4 = Matrix<Type, 4, 1>;
+template <typename Type> using RowVector4 = Matrix<Type, 1, 4>;
+template <typename Type> using MatrixX = Matrix<Type, Dynamic, Dynamic>;
+template <typename Type> using VectorX = Matrix<Type, Dynamic, 1>;
+template <typename Type> using RowVectorX = Matrix<Type, 1, Dynamic>;
+template <typename Type> using Matrix2X = Matrix<Type, 2, Dynamic>;
+template <typename Type> using MatrixX2 = Matrix<Type, Dynamic, 2>;
+template <typename Type> using Matrix3X = Matrix<Type, 3, Dynamic>;
+template <typename Type> using MatrixX3 = Matrix<Type, Dynamic, 3>;
+template <typename Type> using Matrix4X = Matrix<Type, 4, Dynamic>;
+template <typename Type> using MatrixX4 = Matrix<Type, Dynamic, 4>;
+template <typename Type, int Size> using Vector = Matrix<Type, Size, 1>;
+template <typename Type, int Size> using RowVector = Matrix<Type, 1, Size>;
+
 // --------------------------------------------------------------------------------------------------------------------
 // SelfAdjointEigenSolver: Householder tridiagonalisation of the lower triangle, implicit-shift QL on the tridiagonal
 // matrix with accumulation of the transformations; eigenvalues ascending, eigenvectors in the columns.
@@ -1411,6 +1487,100 @@ private:
 };
 
 // --------------------------------------------------------------------------------------------------------------------
+// JacobiSVD: one-sided Jacobi (Hestenes) on the columns, generic in the scalar type (works on TinyAD::Scalar as the
+// reference's tests/SVDTest.cc asks); singular values descending, full U and V for square matrices.
+// --------------------------------------------------------------------------------------------------------------------
+enum { ComputeFullU = 0x04, ComputeThinU = 0x08, ComputeFullV = 0x10, ComputeThinV = 0x20 };
+
+template <typename MatT, int QRPreconditioner = 0>
+class JacobiSVD
+{
+public:
+    using Scalar = typename MatT::Scalar;
+    using SingularValuesType = Matrix<Scalar, MatT::ColsAtCompileTime, 1>;
+
+    JacobiSVD() = default;
+    template <typename D>
+    explicit JacobiSVD(const MatrixBase<D>& m, unsigned int options = 0)
+    {
+        compute(m, options);
+    }
+    template <typename D>
+    JacobiSVD& compute(const MatrixBase<D>& m, unsigned int = 0)
+    {
+        using std::abs;
+        using std::sqrt;
+        const Index r = m.rows(), c = m.cols();
+        if (r != c) throw std::logic_error("eigen shim: JacobiSVD is implemented for square matrices");
+        MatT a = m;  // columns converge to U * diag(S)
+        v_.resize(c, c);
+        v_.setIdentity();
+        for (int sweep = 0; sweep < 60; ++sweep)
+        {
+            bool rotated = false;
+            for (Index p = 0; p < c - 1; ++p)
+                for (Index q = p + 1; q < c; ++q)
+                {
+                    Scalar alpha = Scalar(0), beta = Scalar(0), gamma = Scalar(0);
+                    for (Index i = 0; i < r; ++i)
+                    {
+                        alpha = alpha + a(i, p) * a(i, p);
+                        beta = beta + a(i, q) * a(i, q);
+                        gamma = gamma + a(i, p) * a(i, q);
+                    }
+                    if (abs(gamma) <= 1e-16 * sqrt(alpha * beta) || gamma == Scalar(0)) continue;
+                    rotated = true;
+                    const Scalar zeta = (beta - alpha) / (Scalar(2) * gamma);
+                    const Scalar t = (zeta >= Scalar(0) ? Scalar(1) : Scalar(-1)) / (abs(zeta) + sqrt(Scalar(1) + zeta * zeta));
+                    const Scalar cs = Scalar(1) / sqrt(Scalar(1) + t * t), sn = cs * t;
+                    for (Index i = 0; i < r; ++i)
+                    {
+                        const Scalar x = a(i, p), y = a(i, q);
+                        a(i, p) = cs * x - sn * y;
+                        a(i, q) = sn * x + cs * y;
+                    }
+                    for (Index i = 0; i < c; ++i)
+                    {
+                        const Scalar x = v_(i, p), y = v_(i, q);
+                        v_(i, p) = cs * x - sn * y;
+                        v_(i, q) = sn * x + cs * y;
+                    }
+                }
+            if (!rotated) break;
+        }
+        s_.resize(c, 1);
+        u_.resize(r, c);
+        for (Index j = 0; j < c; ++j)
+        {
+            Scalar n2 = Scalar(0);
+            for (Index i = 0; i < r; ++i) n2 = n2 + a(i, j) * a(i, j);
+            s_[j] = sqrt(n2);
+            for (Index i = 0; i < r; ++i) u_(i, j) = a(i, j) / s_[j];
+        }
+        for (Index i = 0; i < c - 1; ++i)  // descending
+        {
+            Index k = i;
+            for (Index j = i + 1; j < c; ++j)
+                if (s_[k] < s_[j]) k = j;
+            if (k != i)
+            {
+                std::swap(s_[i], s_[k]);
+                for (Index rr = 0; rr < r; ++rr) std::swap(u_(rr, i), u_(rr, k));
+                for (Index rr = 0; rr < c; ++rr) std::swap(v_(rr, i), v_(rr, k));
+            }
+        }
+        return *this;
+    }
+    const MatT& matrixU() const { return u_; }
+    const MatT& matrixV() const { return v_; }
+    const SingularValuesType& singularValues() const { return s_; }
+
+private:
+    MatT u_, v_;
+    SingularValuesType s_;
+};
+
+// --------------------------------------------------------------------------------------------------------------------
 // Sparse: Triplet and a compressed column-major SparseMatrix
 // --------------------------------------------------------------------------------------------------------------------
 template <typename T, typename StorageIndex_ = int>
@@ -1538,6 +1708,128 @@ public:
             if (inner_[p] == i) return values_[p];
         return T(0);
     }
+    // reference to entry (i, j), inserted as an explicit zero when absent (keeps the columns sorted)
+    T& coeffRef(Index i, Index j)
+    {
+        StorageIndex p = outer_[j];
+        while (p < outer_[j + 1] && inner_[p] < i) ++p;
+        if (p < outer_[j + 1] && inner_[p] == i) return values_[p];
+        inner_.insert(inner_.begin() + p, (StorageIndex)i);
+        values_.insert(values_.begin() + p, T(0));
+        for (Index c = j + 1; c <= cols_; ++c) ++outer_[c];
+        return values_[p];
+    }
+    T& insert(Index i, Index j) { return coeffRef(i, j); }
+    void reserve(Index) {}
+    template <typename X>
+    void reserve(const X&) {}
+
+    // a*A + b*B on the union pattern
+    static SparseMatrix combine(const T& a, const SparseMatrix& A, const T& b, const SparseMatrix& B)
+    {
+        if (A.rows_ != B.rows_ || A.cols_ != B.cols_) throw std::logic_error("eigen shim: sparse operands of different shapes");
+        SparseMatrix r(A.rows_, A.cols_);
+        for (Index j = 0; j < A.cols_; ++j)
+        {
+            StorageIndex p = A.outer_[j], q = B.outer_[j];
+            const StorageIndex pe = A.outer_[j + 1], qe = B.outer_[j + 1];
+            while (p < pe || q < qe)
+            {
+                if (q >= qe || (p < pe && A.inner_[p] < B.inner_[q]))
+                {
+                    r.inner_.push_back(A.inner_[p]);
+                    r.values_.push_back(a * A.values_[p]);
+                    ++p;
+                }
+                else if (p >= pe || B.inner_[q] < A.inner_[p])
+                {
+                    r.inner_.push_back(B.inner_[q]);
+                    r.values_.push_back(b * B.values_[q]);
+                    ++q;
+                }
+                else
+                {
+                    r.inner_.push_back(A.inner_[p]);
+                    r.values_.push_back(a * A.values_[p] + b * B.values_[q]);
+                    ++p;
+                    ++q;
+                }
+            }
+            r.outer_[j + 1] = (StorageIndex)r.inner_.size();
+        }
+        return r;
+    }
+    friend SparseMatrix operator+(const SparseMatrix& A, const SparseMatrix& B) { return combine(T(1), A, T(1), B); }
+    friend SparseMatrix operator-(const SparseMatrix& A, const SparseMatrix& B) { return combine(T(1), A, T(-1), B); }
+    SparseMatrix operator-() const
+    {
+        SparseMatrix r = *this;
+        for (auto& v : r.values_) v = -v;
+        return r;
+    }
+    friend SparseMatrix operator*(const SparseMatrix& A, const SparseMatrix& B)
+    {
+        if (A.cols_ != B.rows_) throw std::logic_error("eigen shim: sparse product of incompatible shapes");
+        SparseMatrix r(A.rows_, B.cols_);
+        std::vector<T> acc((std::size_t)A.rows_, T(0));
+        std::vector<char> used((std::size_t)A.rows_, 0);
+        std::vector<StorageIndex> idx;
+        for (Index j = 0; j < B.cols_; ++j)
+        {
+            idx.clear();
+            for (StorageIndex q = B.outer_[j]; q < B.outer_[j + 1]; ++q)
+            {
+                const StorageIndex k = B.inner_[q];
+                for (StorageIndex p = A.outer_[k]; p < A.outer_[k + 1]; ++p)
+                {
+                    const StorageIndex i = A.inner_[p];
+                    if (!used[i])
+                    {
+                        used[i] = 1;
+                        idx.push_back(i);
+                    }
+                    acc[i] += A.values_[p] * B.values_[q];
+                }
+            }
+            std::sort(idx.begin(), idx.end());
+            for (StorageIndex i : idx)
+            {
+                r.inner_.push_back(i);
+                r.values_.push_back(acc[i]);
+                acc[i] = T(0);
+                used[i] = 0;
+            }
+            r.outer_[j + 1] = (StorageIndex)r.inner_.size();
+        }
+        return r;
+    }
+    T squaredNorm() const
+    {
+        T s = T(0);
+        for (const auto& v : values_) s += v * v;
+        return s;
+    }
+    T norm() const
+    {
+        using std::sqrt;
+        return sqrt(squaredNorm());
+    }
+    T sum() const
+    {
+        T s = T(0);
+        for (const auto& v : values_) s += v;
+        return s;
+    }
+    template <typename U>
+    SparseMatrix<U, Options, StorageIndex_> cast() const
+    {
+        SparseMatrix<U, Options, StorageIndex_> r(rows_, cols_);
+        std::vector<Triplet<U, StorageIndex_>> t;
+        for (Index j = 0; j < cols_; ++j)
+            for (StorageIndex p = outer_[j]; p < outer_[j + 1]; ++p) t.emplace_back(inner_[p], (StorageIndex_)j, (U)values_[p]);
+        r.setFromTriplets(t.begin(), t.end());
+        return r;
+    }
 
     SparseMatrix transpose() const
     {
@@ -1615,6 +1907,128 @@ private:
     Index rows_ = 0, cols_ = 0;
     std::vector<StorageIndex> outer_, inner_;
     std::vector<T> values_;
+};
+
+// --------------------------------------------------------------------------------------------------------------------
+// Linear solvers of Eigen/SparseCholesky, SparseLU, SparseQR: ONE dense LU with partial pivoting under all of those names
+// (only the reference's small test systems are ever solved with it; the solver is outside the path under test)
+// --------------------------------------------------------------------------------------------------------------------
+template <typename MatT>
+class DenseFallbackSolver
+{
+public:
+    using Scalar = typename MatT::Scalar;
+    DenseFallbackSolver() = default;
+    explicit DenseFallbackSolver(const MatT& A) { compute(A); }
+    void analyzePattern(const MatT&) {}
+    void factorize(const MatT& A)
+    {
+        using std::abs;
+        n_ = A.rows();
+        info_ = Success;
+        if (A.rows() != A.cols())
+        {
+            info_ = InvalidInput;
+            return;
+        }
+        lu_ = A.toDense();
+        perm_.resize((std::size_t)n_);
+        for (Index i = 0; i < n_; ++i) perm_[i] = i;
+        for (Index c = 0; c < n_; ++c)
+        {
+            Index p = c;
+            for (Index i = c + 1; i < n_; ++i)
+                if (abs(lu_(i, c)) > abs(lu_(p, c))) p = i;
+            if (!(abs(lu_(p, c)) > Scalar(0)) || !std::isfinite((double)lu_(p, c)))
+            {
+                info_ = NumericalIssue;
+                return;
+            }
+            if (p != c)
+            {
+                std::swap(perm_[p], perm_[c]);
+                for (Index j = 0; j < n_; ++j) std::swap(lu_(p, j), lu_(c, j));
+            }
+            for (Index i = c + 1; i < n_; ++i)
+            {
+                lu_(i, c) /= lu_(c, c);
+                for (Index j = c + 1; j < n_; ++j) lu_(i, j) -= lu_(i, c) * lu_(c, j);
+            }
+        }
+    }
+    DenseFallbackSolver& compute(const MatT& A)
+    {
+        analyzePattern(A);
+        factorize(A);
+        return *this;
+    }
+    template <typename D>
+    Matrix<Scalar, Dynamic, 1> solve(const MatrixBase<D>& b) const
+    {
+        Matrix<Scalar, Dynamic, 1> x(n_);
+        if (info_ != Success || b.size() != n_)
+        {
+            x.setConstant(std::numeric_limits<Scalar>::quiet_NaN());
+            return x;
+        }
+        for (Index i = 0; i < n_; ++i)
+        {
+            Scalar s = b[perm_[i]];
+            for (Index j = 0; j < i; ++j) s -= lu_(i, j) * x[j];
+            x[i] = s;
+        }
+        for (Index i = n_ - 1; i >= 0; --i)
+        {
+            Scalar s = x[i];
+            for (Index j = i + 1; j < n_; ++j) s -= lu_(i, j) * x[j];
+            x[i] = s / lu_(i, i);
+        }
+        return x;
+    }
+    ComputationInfo info() const { return info_; }
+
+private:
+    Matrix<Scalar, Dynamic, Dynamic> lu_;
+    std::vector<Index> perm_;
+    Index n_ = 0;
+    ComputationInfo info_ = InvalidInput;
+};
+
+template <typename I>
+struct COLAMDOrdering
+{
+};
+template <typename I>
+struct AMDOrdering
+{
+};
+template <typename I>
+struct NaturalOrdering
+{
+};
+template <typename MatT, int UpLo = Lower, typename Ordering = AMDOrdering<int>>
+class SimplicialLDLT : public DenseFallbackSolver<MatT>
+{
+public:
+    using DenseFallbackSolver<MatT>::DenseFallbackSolver;
+};
+template <typename MatT, int UpLo = Lower, typename Ordering = AMDOrdering<int>>
+class SimplicialLLT : public DenseFallbackSolver<MatT>
+{
+public:
+    using DenseFallbackSolver<MatT>::DenseFallbackSolver;
+};
+template <typename MatT, typename Ordering = COLAMDOrdering<int>>
+class SparseLU : public DenseFallbackSolver<MatT>
+{
+public:
+    using DenseFallbackSolver<MatT>::DenseFallbackSolver;
+};
+template <typename MatT, typename Ordering>
+class SparseQR : public DenseFallbackSolver<MatT>
+{
+public:
+    using DenseFallbackSolver<MatT>::DenseFallbackSolver;
 };
 
 }  // namespace Eigen
