@@ -189,6 +189,10 @@ def cpu_sample_for(workload, budget_s, threads, engine="port"):
     probe.step(threads, engine)                 # warm-up (OpenMP pool, page faults)
     t1, _ = probe.step(threads, engine)
     layers = int(max(1, min(probe.n, budget_s / max(t1, 1e-4))))
+    if engine == "reference":
+        # the reference keeps every element's Scalar (1.3 kB for Double<12>) and 144 triplets (2.3 kB) alive until setFromTriplets:
+        # bound one step to ~600 k elements (~6 GB of host memory)
+        layers = max(1, min(layers, 600000 // probe.per_layer))
     return probe if layers == 1 else CpuSample(workload, layers)
 
 

@@ -87,3 +87,23 @@ def one_ring_table(n_vertices, F, width=9):
         assert len(lst) <= width
         tab[v, :len(lst)] = lst
     return tab
+
+
+def load_reference_fixtures():
+    """tests/golden/reference_fixtures.npz (made by tests/golden/make_reference_fixtures.py from the reference itself):
+    returns {name: dict} with name like "s/tet_cube3/" (scalar functions) or "v/sos_planar/" (vector functions); every dict holds
+    d, n_vertices, terms [(kind, conn, data)], x and the reference's outputs."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_fixtures.npz"))
+    cases = {}
+    for key in z.files:
+        if key.endswith("/meta"):
+            p = key[:-4]
+            d, nv, nt = (int(v) for v in z[key])
+            c = {"d": d, "n_vertices": nv, "x": z[p + "x"],
+                 "terms": [(int(z[p + f"kind{i}"][0]), z[p + f"conn{i}"], z[p + f"data{i}"]) for i in range(nt)]}
+            for field in ("f", "g", "r", "outer", "inner", "H", "H_proj", "J"):
+                if p + field in z.files:
+                    c[field] = z[p + field]
+            cases[p] = c
+    return cases
