@@ -265,6 +265,9 @@ def ref_lib():
             f.restype = ctypes.c_int64
             f.argtypes = [ctypes.c_void_p]
         L.ref_result_copy.argtypes = [ctypes.c_void_p] * 6
+        L.ref_result_hess_count.restype = ctypes.c_int64
+        L.ref_result_hess_count.argtypes = [ctypes.c_void_p]
+        L.ref_result_hess_copy.argtypes = [ctypes.c_void_p] * 5
         L.ref_result_free.argtypes = [ctypes.c_void_p]
         L.ref_project.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
         _REF = L
@@ -289,6 +292,12 @@ def _ref_collect(L, h, want_matrix):
                           res.inner.ctypes.data if want_matrix else None,
                           res.values.ctypes.data if want_matrix else None)
         res.phases = {"total_s": L.ref_result_seconds(h)}
+        nh = L.ref_result_hess_count(h)
+        if nh:
+            hr, hi, hj = (np.empty(nh, dtype=np.int32) for _ in range(3))
+            hv = np.empty(nh)
+            L.ref_result_hess_copy(h, hr.ctypes.data, hi.ctypes.data, hj.ctypes.data, hv.ctypes.data)
+            res.phases["residual_hessians"] = (hr, hi, hj, hv)      # (residual, row, col, value) of every stored entry
         return res
     finally:
         L.ref_result_free(h)
@@ -310,7 +319,10 @@ def ref_vector_eval(d, n_vertices, terms, mode, x, n_threads=-1):
     arr, keep = _terms_array(terms)
     x = np.ascontiguousarray(x, dtype=np.float64)
     h = L.ref_vector_eval(d, n_vertices, len(terms), ctypes.addressof(arr), mode, x.ctypes.data, n_threads)
-    return _ref_collect(L, h, mode in (1, 3))
+    return _ref_collect(L, h, mode in (1, 3, 4))
+
+
+V_DERIVATIVES = 4   # ref_vector_eval only: VectorFunction::eval_with_derivatives (r, J, Hessian of every residual)
 
 
 def ref_project(H, eps=1e-9):

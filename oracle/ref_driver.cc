@@ -292,6 +292,9 @@ struct Result
     Eigen::VectorXd g, r;
     Eigen::SparseMatrix<double> H;  // Hessian or Jacobian
     double seconds = 0.0;           // the eval* call alone
+    // VectorFunction::eval_with_derivatives: the Hessian of every residual as (residual, row, col, value) entries
+    std::vector<std::int32_t> hess_res, hess_row, hess_col;
+    std::vector<double> hess_val;
 };
 
 template <int d>
@@ -356,7 +359,8 @@ void* ref_scalar_eval(int d, std::int64_t n_vertices, int n_terms, const ref_ter
     return res.release();
 }
 
-// mode: 0 eval, 1 eval_with_jacobian, 2 eval_sum_of_squares, 3 eval_sum_of_squares_with_derivatives (Detail/VectorFunctionImpl.hh:143-301)
+// mode: 0 eval, 1 eval_with_jacobian, 2 eval_sum_of_squares, 3 eval_sum_of_squares_with_derivatives, 4 eval_with_derivatives
+// (Detail/VectorFunctionImpl.hh:143-301)
 void* ref_vector_eval(int d, std::int64_t n_vertices, int n_terms, const ref_term* terms, int mode, const double* x_in, int n_threads)
 {
     auto res = std::make_unique<Result>();
@@ -375,6 +379,21 @@ void* ref_vector_eval(int d, std::int64_t n_vertices, int n_terms, const ref_ter
         case 1: func.eval_with_jacobian(x, res->r, res->H); break;
         case 2: res->f = func.eval_sum_of_squares(x); break;
         case 3: func.eval_sum_of_squares_with_derivatives(x, res->f, res->g, res->r, res->H); break;
+        case 4:  // Detail/VectorFunctionImpl.hh:207-235: r, J and one n x n sparse Hessian per residual
+        {
+            std::vector<Eigen::SparseMatrix<double>> H;
+            func.eval_with_derivatives(x, res->r, res->H, H);
+            for (std::size_t i = 0; i < H.size(); ++i)
+                for (Eigen::Index j = 0; j < H[i].cols(); ++j)
+                    for (Eigen::SparseMatrix<double>::InnerIterator it(H[i], j); it; ++it)
+                    {
+                        res->hess_res.push_back((std::int32_t)i);
+                        res->hess_row.push_back((std::int32_t)it.row());
+                        res->hess_col.push_back((std::int32_t)it.col());
+                        res->hess_val.push_back(it.value());
+                    }
+            break;
+        }
         default: throw std::runtime_error("ref: bad mode");
         }
         res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -402,6 +421,15 @@ void ref_result_copy(void* rp, double* g, double* rvec, std::int32_t* outer, std
     if (outer) std::copy(r->H.outerIndexPtr(), r->H.outerIndexPtr() + r->H.cols() + 1, outer);
     if (inner) std::copy(r->H.innerIndexPtr(), r->H.innerIndexPtr() + r->H.nonZeros(), inner);
     if (values) std::copy(r->H.valuePtr(), r->H.valuePtr() + r->H.nonZeros(), values);
+}
+std::int64_t ref_result_hess_count(void* r) { return (std::int64_t)((Result*)r)->hess_val.size(); }
+void ref_result_hess_copy(void* rp, std::int32_t* res, std::int32_t* row, std::int32_t* col, double* val)
+{
+    Result* r = (Result*)rp;
+    std::copy(r->hess_res.begin(), r->hess_res.end(), res);
+    std::copy(r->hess_row.begin(), r->hess_row.end(), row);
+    std::copy(r->hess_col.begin(), r->hess_col.end(), col);
+    std::copy(r->hess_val.begin(), r->hess_val.end(), val);
 }
 void ref_result_free(void* r) { delete (Result*)r; }
 

@@ -5,7 +5,7 @@ Run in the build container (needs oracle/_ref/libtinyad_ref.so, i.e. /root/refer
 Each case stores the inputs (term kinds, connectivity, per-element data, x) and what TinyAD::ScalarFunction /
 VectorFunction of the unmodified reference (oracle/ref_driver.cc over oracle/eigen_shim) returned for them:
 f, g, the sparsity pattern and values of H (eval_with_derivatives) and of the projected H (eval_with_hessian_proj, eps = 1e-9),
-or r, J (pattern + values), f = r.r and g = 2 J^T r for vector functions.  tests/test_reference_fixtures.py (CPU: oracle) and
+or r, J (pattern + values), f = r.r, g = 2 J^T r and the Hessian of every residual (eval_with_derivatives) for vector functions.  tests/test_reference_fixtures.py (CPU: oracle) and
 tests/test_reference_fixtures_gpu.py (B200: the product through the C ABI) consume the file; neither needs the reference.
 """
 import os
@@ -97,6 +97,12 @@ def main():
         out[p + "f"] = np.array([r.f])
         out[p + "g"], out[p + "r"] = r.g, r.r
         out[p + "outer"], out[p + "inner"], out[p + "J"] = r.outer, r.inner, r.values
+        # VectorFunction::eval_with_derivatives: every stored entry of every residual's n x n Hessian
+        rd = oracle.ref_vector_eval(2, nv, ot, oracle.V_DERIVATIVES, x)
+        for u, v in ((rd.r, r.r), (rd.values, r.values)):          # last-bit differences only (FMA contraction differs per instantiation)
+            assert np.abs(u - v).max() <= 1e-15 * np.abs(v).max()
+        hr, hi, hj, hv = rd.phases["residual_hessians"]
+        out[p + "hess_res"], out[p + "hess_row"], out[p + "hess_col"], out[p + "hess_val"] = hr, hi, hj, hv
         names.append(p)
     path = os.path.join(HERE, "reference_fixtures.npz")
     np.savez_compressed(path, **out)

@@ -102,7 +102,7 @@ def load_reference_fixtures():
             d, nv, nt = (int(v) for v in z[key])
             c = {"d": d, "n_vertices": nv, "x": z[p + "x"],
                  "terms": [(int(z[p + f"kind{i}"][0]), z[p + f"conn{i}"], z[p + f"data{i}"]) for i in range(nt)]}
-            for field in ("f", "g", "r", "outer", "inner", "H", "H_proj", "J"):
+            for field in ("f", "g", "r", "outer", "inner", "H", "H_proj", "J", "hess_res", "hess_row", "hess_col", "hess_val"):
                 if p + field in z.files:
                     c[field] = z[p + field]
             cases[p] = c

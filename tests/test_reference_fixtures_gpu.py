@@ -69,6 +69,50 @@ def test_vector_functions_match_the_reference(torch_cuda, name):
         fn.close()
 
 
+VALENCE_OUTPUTS = {tad.SOS_SYMDIRICHLET2D: (3, 8), tad.SOS_PENALTY2D: (1, 2), tad.SOS_POLYCURL2D: (2, 2)}
+
+
+@pytest.mark.parametrize("name", sorted(k for k in CASES if k.startswith("v/")))
+def test_per_residual_hessians_match_the_reference(torch_cuda, name):
+    """VectorFunction::eval_with_derivatives (Detail/VectorFunctionImpl.hh:207-235): the reference returns one n x n sparse Hessian
+    per residual; the product returns the dense k x k block of every residual (tad_veval_with_derivatives).  Scattered through the
+    term tables, the blocks must reproduce the reference's matrices entry by entry."""
+    torch = torch_cuda
+    c = CASES[name]
+    fn = Problem(2, c["n_vertices"], c["terms"], is_vector=True).gpu()
+    try:
+        n, m = fn.n_vars, fn.n_outputs
+        outer, inner = fn.pattern()
+        total = fn.residual_hessian_layout(-1)[3]
+        xd = torch.from_numpy(c["x"]).cuda()
+        r = torch.empty(m, dtype=torch.float64, device="cuda")
+        J = torch.empty(len(inner), dtype=torch.float64, device="cuda")
+        Hb = torch.empty(total, dtype=torch.float64, device="cuda")
+        fn.veval_with_derivatives(xd, r, J, Hb)
+        assert_vec(r.cpu().numpy(), c["r"])
+        assert_vec(J.cpu().numpy(), c["J"])
+        Hbh = Hb.cpu().numpy()
+        mine = np.zeros((m, n, n))
+        row0 = 0
+        for term, (kind, conn, _) in enumerate(c["terms"]):
+            valence, M = VALENCE_OUTPUTS[kind]
+            off, k, n_res, _ = fn.residual_hessian_layout(term)
+            assert k == 2 * valence and n_res == M * len(conn)
+            table = fn.term_table(term, valence, len(conn))
+            blocks = Hbh[off:off + n_res * k * k].reshape(len(conn), M, k, k)
+            for e in range(len(conn)):
+                gv = (2 * table[:, e][:, None] + np.arange(2)[None, :]).reshape(-1)
+                for q in range(M):
+                    np.add.at(mine[row0 + M * e + q], np.ix_(gv, gv), blocks[e, q])
+            row0 += n_res
+        ref = np.zeros((m, n, n))
+        np.add.at(ref, (c["hess_res"], c["hess_row"], c["hess_col"]), c["hess_val"])
+        assert np.abs(ref).max() > 0.0
+        assert np.abs(mine - ref).max() <= 1e-12 * np.abs(ref).max()
+    finally:
+        fn.close()
+
+
 @pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref/libtinyad_ref.so did not travel with this snapshot")
 @pytest.mark.parametrize("make", [lambda: tet_problem(17, seed=6, with_penalty=True), lambda: grid_problem(100, seed=2, with_penalty=True)])
 def test_live_against_the_reference_library(torch_cuda, make):
