@@ -337,7 +337,14 @@ extern "C" {
 const char* ref_last_error() { return g_last_error.c_str(); }
 
 // which reference tree and which linear-algebra layer this library was built from
-const char* ref_description() { return "TinyAD headers (unmodified, compiled in place) over oracle/eigen_shim (not Eigen)"; }
+const char* ref_description()
+{
+#ifdef TINYAD_EIGEN_SHIM
+    return "TinyAD headers (unmodified, compiled in place) over oracle/eigen_shim (not Eigen)";
+#else
+    return "TinyAD headers (unmodified, compiled in place) over Eigen";
+#endif
+}
 
 // mode: 0 eval, 1 eval_with_gradient, 2 eval_with_derivatives, 3 eval_with_hessian_proj (Detail/ScalarFunctionImpl.hh:256-416)
 void* ref_scalar_eval(int d, std::int64_t n_vertices, int n_terms, const ref_term* terms, int mode, const double* x, double eps,
