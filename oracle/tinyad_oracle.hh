@@ -31,7 +31,10 @@
 // Pinning: tests/test_oracle_golden.py checks this file against the reference's
 // own known-answer tests (tests/ScalarTest*.cc, ComplexTest.cc,
 // ScalarFunctionTest.cc, VectorFunctionTest.cc, NewtonTest.cc, GaussNewtonTest.cc,
-// DynamicElementsTest.cc) -- see oracle/README.md for the list.
+// DynamicElementsTest.cc) -- see oracle/README.md for the list -- and
+// tests/test_oracle_vs_reference.py checks it against the reference itself: oracle/_ref
+// (ref_driver.cc = the unmodified TinyAD headers compiled in place over oracle/eigen_shim)
+// on the same inputs: patterns bit-exact, f / g / H 1e-13, projected H 1e-10.
 #pragma once
 
 #include <algorithm>
