@@ -205,13 +205,10 @@ def ref_available():
     return os.path.exists(ref_path())
 
 
-# The two reference tests that do not pass over the shim, with the reason (everything else must pass):
-#  * NewtonTest.2DDeformationDouble asserts |g|_inf < 1e-15 ABSOLUTE after 10 projected-Newton steps on its 4-triangle mesh
-#    (tests/NewtonTest.cc:87); over the shim the converged gradient is 1.39e-15 -- a few ulps of cancellation noise that depends
-#    on Eigen's exact summation order and on SimplicialLDLT (the shim solves with a dense LU).  f == 4 and f == eval(x) to 1e-15
-#    hold, and the float / long double instances of the same test pass.
-#  * NewtonTest.Deterministic calls that same function from four OpenMP threads (tests/NewtonTest.cc:96-110).
-REF_TESTS_SKIPPED = ("NewtonTest.2DDeformationDouble", "NewtonTest.Deterministic")
+# Reference tests excluded from the run (none: all 404 pass over the shim).  History: while the shim solved SimplicialLDLT's
+# systems with a dense LU, NewtonTest.2DDeformationDouble missed its absolute 1e-15 bound on the converged gradient by rounding
+# (1.39e-15); with an actual L D L^T (what that solver computes) it passes.
+REF_TESTS_SKIPPED = ()
 
 
 def ref_tests_path():

@@ -1910,8 +1910,9 @@ private:
 };
 
 // --------------------------------------------------------------------------------------------------------------------
-// Linear solvers of Eigen/SparseCholesky, SparseLU, SparseQR: ONE dense LU with partial pivoting under all of those names
-// (only the reference's small test systems are ever solved with it; the solver is outside the path under test)
+// Linear solvers of Eigen/SparseCholesky, SparseLU, SparseQR: a dense L D L^T for SimplicialLDLT (further down) and ONE dense LU
+// with partial pivoting under the other names (only the reference's small test systems are ever solved with them; the solver is
+// outside the path under test)
 // --------------------------------------------------------------------------------------------------------------------
 template <typename MatT>
 class DenseFallbackSolver
@@ -2006,11 +2007,80 @@ template <typename I>
 struct NaturalOrdering
 {
 };
+// symmetric L D L^T without pivoting on the lower triangle (what a simplicial factorisation computes, here densely)
 template <typename MatT, int UpLo = Lower, typename Ordering = AMDOrdering<int>>
-class SimplicialLDLT : public DenseFallbackSolver<MatT>
+class SimplicialLDLT
 {
 public:
-    using DenseFallbackSolver<MatT>::DenseFallbackSolver;
+    using Scalar = typename MatT::Scalar;
+    SimplicialLDLT() = default;
+    explicit SimplicialLDLT(const MatT& A) { compute(A); }
+    void analyzePattern(const MatT&) {}
+    void factorize(const MatT& A)
+    {
+        n_ = A.rows();
+        info_ = Success;
+        if (A.rows() != A.cols())
+        {
+            info_ = InvalidInput;
+            return;
+        }
+        l_ = A.toDense();
+        d_.resize((std::size_t)n_);
+        for (Index j = 0; j < n_; ++j)
+        {
+            Scalar dj = l_(j, j);
+            for (Index k = 0; k < j; ++k) dj -= l_(j, k) * l_(j, k) * d_[k];
+            d_[j] = dj;
+            if (dj == Scalar(0) || !std::isfinite((double)dj))
+            {
+                info_ = NumericalIssue;
+                return;
+            }
+            for (Index i = j + 1; i < n_; ++i)
+            {
+                Scalar v = l_(i, j);
+                for (Index k = 0; k < j; ++k) v -= l_(i, k) * l_(j, k) * d_[k];
+                l_(i, j) = v / dj;
+            }
+        }
+    }
+    SimplicialLDLT& compute(const MatT& A)
+    {
+        factorize(A);
+        return *this;
+    }
+    template <typename D>
+    Matrix<Scalar, Dynamic, 1> solve(const MatrixBase<D>& b) const
+    {
+        Matrix<Scalar, Dynamic, 1> x(n_);
+        if (info_ != Success || b.size() != n_)
+        {
+            x.setConstant(std::numeric_limits<Scalar>::quiet_NaN());
+            return x;
+        }
+        for (Index i = 0; i < n_; ++i)
+        {
+            Scalar s = b[i];
+            for (Index k = 0; k < i; ++k) s -= l_(i, k) * x[k];
+            x[i] = s;
+        }
+        for (Index i = 0; i < n_; ++i) x[i] /= d_[i];
+        for (Index i = n_ - 1; i >= 0; --i)
+        {
+            Scalar s = x[i];
+            for (Index k = i + 1; k < n_; ++k) s -= l_(k, i) * x[k];
+            x[i] = s;
+        }
+        return x;
+    }
+    ComputationInfo info() const { return info_; }
+
+private:
+    Matrix<Scalar, Dynamic, Dynamic> l_;
+    std::vector<Scalar> d_;
+    Index n_ = 0;
+    ComputationInfo info_ = InvalidInput;
 };
 template <typename MatT, int UpLo = Lower, typename Ordering = AMDOrdering<int>>
 class SimplicialLLT : public DenseFallbackSolver<MatT>
