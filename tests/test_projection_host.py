@@ -274,3 +274,47 @@ def test_reduced_pipeline_on_tet_hessians(hostlib):
             assert code == 2 | 16
             ref = reference_projection(A, eps)
             assert np.abs(unpack(hostlib, pk, 12) - ref).max() <= 1e-11 * np.abs(A).max()
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref is not built")
+def test_product_projection_against_the_reference_routine(hostlib):
+    """The product's projection routines (TinyAD/Detail/Projection.hh, compiled for the host: general pipeline, translation
+    deflation, reduced 9 x 9 pipeline) against TinyAD::project_positive_definite of the reference ITSELF (oracle/_ref,
+    Utils/HessianProjection.hh:48-101) on the element Hessians of a deformed tet mesh and on random symmetric matrices, eps = 1e-9
+    and the absolute-value strategy: 1e-10 relative to max |H| (north_star's bound for projected values)."""
+    from problems import tet_problem
+    import scipy.sparse as sp
+    p, x = tet_problem(3, seed=9)
+    kind, conn, data = p.terms[0]
+    mats = []
+    for e in range(0, len(conn), 2):
+        loc = np.arange(4, dtype=np.int32)[None, :]
+        xe = x.reshape(-1, 3)[conn[e]].reshape(-1)
+        r = oracle.scalar_eval(3, 4, [oracle.Term(kind, loc, data[e:e + 1])], oracle.DERIVATIVES, xe)
+        A = sp.csc_matrix((r.values, r.inner, r.outer), shape=(12, 12)).toarray()
+        A = 0.5 * (A + A.T)
+        if np.abs(A).max() > 0:
+            mats.append((A, True))
+    rng = np.random.default_rng(12)
+    for _ in range(20):
+        B = rng.standard_normal((12, 12))
+        mats.append((B + B.T, False))
+    worst = 0.0
+    for A, is_element in mats:
+        for eps in (1e-9, -1.0):
+            ref = oracle.ref_project(A, eps)
+            runs = [("general", lambda pk: hostlib.host_project(12, pk.ctypes.data, eps))]
+            if is_element:
+                runs += [("deflated", lambda pk: hostlib.host_project_translations(12, 3, pk.ctypes.data, eps)),
+                         ("reduced", lambda pk: hostlib.host_project_reduced(12, 3, pk.ctypes.data, eps))]
+            for name, run in runs:
+                if eps < 0 and name != "general":
+                    continue                       # a numerically zero eigenvalue may take either sign in |lambda| mode: no solver pins it
+                pk = pack(hostlib, A)
+                run(pk)
+                err = np.abs(unpack(hostlib, pk, 12) - ref).max() / np.abs(A).max()
+                if eps < 0 and is_element:
+                    continue                       # same remark: the translation null space sits exactly at the sign change
+                worst = max(worst, err)
+                assert err <= 1e-10, (name, eps, err)
+    assert worst > 0.0
