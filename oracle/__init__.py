@@ -322,6 +322,23 @@ def ref_vector_eval(d, n_vertices, terms, mode, x, n_threads=-1):
 V_DERIVATIVES = 4   # ref_vector_eval only: VectorFunction::eval_with_derivatives (r, J, Hessian of every residual)
 
 
+def ref_scalar_case(name, params, k, n_out_max=3):
+    """The scalar case `name` of the shared vocabulary on the reference's TinyAD::Scalar; same return value as scalar_case."""
+    L = ref_lib()
+    L.ref_scalar_case.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p]
+    p = np.zeros(16)
+    p[:len(params)] = params
+    out = np.zeros(n_out_max * (1 + k + k * k) + 64)
+    n = L.ref_scalar_case(name.encode(), p.ctypes.data, out.ctypes.data)
+    if n < 0:
+        raise RuntimeError(f"reference scalar case {name}: code {n} {L.ref_last_error().decode()}")
+    res, o = [], 0
+    for _ in range(n):
+        res.append((out[o], out[o + 1:o + 1 + k].copy(), out[o + 1 + k:o + 1 + k + k * k].reshape(k, k).copy()))
+        o += 1 + k + k * k
+    return res
+
+
 def ref_project(H, eps=1e-9):
     """TinyAD::project_positive_definite of the reference on one dense symmetric matrix."""
     A = np.array(H, dtype=np.float64, order="C")

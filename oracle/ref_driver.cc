@@ -22,6 +22,8 @@
 #include <complex>
 #include <cstdint>
 #include <cstring>
+#include <functional>
+#include <map>
 #include <memory>
 #include <string>
 
@@ -468,3 +470,169 @@ int ref_project(int k, double* H, double eps)
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Scalar cases on the reference's TinyAD::Scalar: the case vocabulary of oracle_capi.cc / tests/golden/scalar_cases.json
+// (tests/ScalarTest*.cc, ComplexTest.cc of the reference), so that the oracle's and the product's Scalar can be compared
+// with the reference's on arbitrary parameters, not only on the transcribed golden ones.
+// out = [val, grad(k), Hess(k*k) row-major] per returned scalar.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace
+{
+
+template <int k>
+void put(const TinyAD::Double<k>& s, double*& out)
+{
+    *out++ = s.val;
+    for (int i = 0; i < k; ++i) *out++ = s.grad(i);
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) *out++ = s.Hess(i, j);
+}
+
+int scalar_case_impl(const std::string& name, const double* p, double* out)
+{
+    using A1 = TinyAD::Double<1>;
+    using A2 = TinyAD::Double<2>;
+    auto kd = [&](int o) { return A1::known_derivatives(p[o], p[o + 1], p[o + 2]); };
+    static const std::map<std::string, std::function<A1(const A1&)>> unary = {
+        {"neg", [](const A1& a) { return -a; }}, {"sqrt", [](const A1& a) { return sqrt(a); }},
+        {"sqr", [](const A1& a) { return sqr(a); }}, {"fabs", [](const A1& a) { return fabs(a); }},
+        {"abs", [](const A1& a) { return abs(a); }}, {"exp", [](const A1& a) { return exp(a); }},
+        {"log", [](const A1& a) { return log(a); }}, {"log2", [](const A1& a) { return log2(a); }},
+        {"log10", [](const A1& a) { return log10(a); }}, {"sin", [](const A1& a) { return sin(a); }},
+        {"cos", [](const A1& a) { return cos(a); }}, {"tan", [](const A1& a) { return tan(a); }},
+        {"asin", [](const A1& a) { return asin(a); }}, {"acos", [](const A1& a) { return acos(a); }},
+        {"atan", [](const A1& a) { return atan(a); }}, {"sinh", [](const A1& a) { return sinh(a); }},
+        {"cosh", [](const A1& a) { return cosh(a); }}, {"tanh", [](const A1& a) { return tanh(a); }},
+        {"asinh", [](const A1& a) { return asinh(a); }}, {"acosh", [](const A1& a) { return acosh(a); }},
+        {"atanh", [](const A1& a) { return atanh(a); }},
+    };
+    if (auto it = unary.find(name); it != unary.end()) { put(it->second(kd(0)), out); return 1; }
+    if (name == "pow_int") { put(pow(kd(0), (int)p[3]), out); return 1; }
+    if (name == "pow_real") { put(pow(kd(0), p[3]), out); return 1; }
+    if (name == "add") { put(kd(0) + kd(3), out); return 1; }
+    if (name == "sub") { put(kd(0) - kd(3), out); return 1; }
+    if (name == "mul") { put(kd(0) * kd(3), out); return 1; }
+    if (name == "div") { put(kd(0) / kd(3), out); return 1; }
+    if (name == "add_s") { put(kd(0) + p[6], out); return 1; }
+    if (name == "s_add") { put(p[6] + kd(0), out); return 1; }
+    if (name == "sub_s") { put(kd(0) - p[6], out); return 1; }
+    if (name == "s_sub") { put(p[6] - kd(0), out); return 1; }
+    if (name == "mul_s") { put(kd(0) * p[6], out); return 1; }
+    if (name == "s_mul") { put(p[6] * kd(0), out); return 1; }
+    if (name == "div_s") { put(kd(0) / p[6], out); return 1; }
+    if (name == "s_div") { put(p[6] / kd(0), out); return 1; }
+    if (name == "iadd") { A1 a = kd(0); a += kd(3); put(a, out); return 1; }
+    if (name == "isub") { A1 a = kd(0); a -= kd(3); put(a, out); return 1; }
+    if (name == "imul") { A1 a = kd(0); a *= kd(3); put(a, out); return 1; }
+    if (name == "idiv") { A1 a = kd(0); a /= kd(3); put(a, out); return 1; }
+    if (name == "iadd_s") { A1 a = kd(0); a += p[6]; put(a, out); return 1; }
+    if (name == "isub_s") { A1 a = kd(0); a -= p[6]; put(a, out); return 1; }
+    if (name == "imul_s") { A1 a = kd(0); a *= p[6]; put(a, out); return 1; }
+    if (name == "idiv_s") { A1 a = kd(0); a /= p[6]; put(a, out); return 1; }
+    if (name == "min") { put(min(kd(0), kd(3)), out); return 1; }
+    if (name == "max") { put(max(kd(0), kd(3)), out); return 1; }
+    if (name == "clamp") { put(clamp(kd(0), kd(3), kd(6)), out); return 1; }
+    if (name == "fmin") { put(fmin(kd(0), kd(3)), out); return 1; }
+    if (name == "fmax") { put(fmax(kd(0), kd(3)), out); return 1; }
+    if (name == "clamp_d") { put(clamp(kd(0), p[3], p[4]), out); return 1; }
+    if (name == "cmp")
+    {
+        const A1 a = kd(0), b = kd(3);
+        const double sc = p[6];
+        unsigned m = 0;
+        int bit = 0;
+        auto put_bit = [&](bool v) { if (v) m |= 1u << bit; ++bit; };
+        put_bit(a == b); put_bit(a != b); put_bit(a < b); put_bit(a <= b); put_bit(a > b); put_bit(a >= b);
+        put_bit(a == sc); put_bit(a != sc); put_bit(a < sc); put_bit(a <= sc); put_bit(a > sc); put_bit(a >= sc);
+        put_bit(sc == a); put_bit(sc != a); put_bit(sc < a); put_bit(sc <= a); put_bit(sc > a); put_bit(sc >= a);
+        put(A1((double)m), out);
+        return 1;
+    }
+    if (name == "isnan_isinf")
+    {
+        const A1 v(p[0]);
+        put(A1((double)((isnan(v) ? 1 : 0) | (isinf(v) ? 2 : 0) | (isfinite(v) ? 4 : 0))), out);
+        return 1;
+    }
+    if (name == "quadratic") { A1 a(p[0], 0); put(sqr(a) + a + 2.0, out); return 1; }
+    if (name == "atan2_1")
+    {
+        A1 x(p[0], 0);
+        A1 y = sqr(x) - x - 1.0;
+        put(atan2(y, x), out);
+        return 1;
+    }
+    A2 x(p[0], 0), y(p[1], 1);
+    if (name == "sqr_pow_mul")
+    {
+        A2 a = x * x + 7.0 * y * y - 3.0 * x * 3.0 + x + 2 * y;
+        put(sqr(a), out); put(pow(a, 2), out); put(a * a, out);
+        return 3;
+    }
+    if (name == "atan2_const") { put(atan2(y, x), out); return 1; }
+    if (name == "atan2_2")
+    {
+        A2 a = 0.5 * sqr(x) - sqr(y) - y;
+        A2 b = -sqr(x - 2) - sqr(y - 3) + 1;
+        put(atan2(b, a), out); put(atan(b / a), out);
+        return 2;
+    }
+    if (name == "hypot") { put(hypot(x, y), out); return 1; }
+    if (name == "div2d") { put(sqr(x) / y, out); return 1; }
+    if (name == "div2d_2")
+    {
+        A2 a = 0.5 * sqr(x) - sqr(y) + 2.0 * x - y;
+        A2 b = -sqr(x - 2.0) - sqr(y - 3.0) + 1.0;
+        put(a / b, out);
+        return 1;
+    }
+    if (name == "plus_minus_mult_div_2d") { put((sqr(x) + x) * (sqr(y) - y) / (y - 1.0), out); return 1; }
+    if (name == "sphere")
+    {
+        put(sin(x) * cos(y), out); put(sin(x) * sin(y), out); put(cos(x), out);
+        return 3;
+    }
+    {
+        using C = std::complex<A2>;
+        C a(x, y);
+        std::complex<double> bd(p[2], p[3]);
+        C b(A2(p[2]) + 0.5 * x, A2(p[3]) - 0.25 * y);
+        auto putc = [&](const C& c) { put(c.real(), out); put(c.imag(), out); };
+        if (name == "c_mul") { putc(a * b); return 2; }
+        if (name == "c_mul_d") { putc(a * bd); return 2; }
+        if (name == "c_d_mul") { putc(bd * a); return 2; }
+        if (name == "c_div") { putc(a / b); return 2; }
+        if (name == "c_div_d") { putc(a / bd); return 2; }
+        if (name == "c_add") { putc(a + b); return 2; }
+        if (name == "c_sub") { putc(a - b); return 2; }
+        if (name == "c_sqr") { putc(sqr(a)); return 2; }
+        if (name == "c_conj") { putc(conj(a)); return 2; }
+        if (name == "c_abs") { put(abs(a), out); return 1; }
+        if (name == "c_arg") { put(arg(a), out); return 1; }
+    }
+    if (name == "symm_dirich6")  // tests/ScalarTestHessianBlock.cc:50-90
+    {
+        using A6 = TinyAD::Double<6>;
+        const Eigen::Vector2d ar(p[6], p[7]), br(p[8], p[9]), cr(p[10], p[11]);
+        const Eigen::Matrix2d Mr = TinyAD::col_mat(br - ar, cr - ar);
+        Eigen::Matrix<double, Eigen::Dynamic, 1> xv(6);
+        for (int i = 0; i < 6; ++i) xv[i] = p[i];
+        const Eigen::Matrix<A6, 6, 1> xa = A6::make_active(xv);
+        const Eigen::Vector2<A6> a(xa[0], xa[1]), b(xa[2], xa[3]), c(xa[4], xa[5]);
+        const Eigen::Matrix2<A6> M = TinyAD::col_mat(b - a, c - a);
+        const Eigen::Matrix2<A6> J = M * Mr.inverse();
+        A6 E = J.squaredNorm() + J.inverse().squaredNorm();
+        put(E, out);
+        return 1;
+    }
+    return -1;
+}
+
+}  // namespace
+
+extern "C" int ref_scalar_case(const char* name, const double* params, double* out)
+{
+    try { return scalar_case_impl(name, params, out); }
+    catch (const std::exception& e) { g_last_error = e.what(); return -2; }
+}
