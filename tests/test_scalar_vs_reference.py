@@ -77,3 +77,22 @@ def test_complex_and_triangle_cases_follow_the_reference(name):
         want = oracle.ref_scalar_case(name, p, k)
         agree(name, oracle.scalar_case(name, p, k), want)
         agree(name, tad.scalar_case(name, p, k, on_device=False), want, tol=1e-12)
+
+
+@pytest.mark.gpu
+def test_device_scalar_follows_the_reference_on_perturbed_parameters(torch_cuda):
+    """The same comparison for the product's Scalar running in a CUDA kernel (one thread per case): 1e-12 relative."""
+    for name in sorted(set(c["name"] for c in CASES)):
+        rng = np.random.default_rng(zlib.crc32(name.encode()) + 1)
+        for c in [c for c in CASES if c["name"] == name]:
+            for _ in range(3):
+                p = perturbed(c, rng)
+                want = oracle.ref_scalar_case(name, p, c["k"])
+                if not all(np.isfinite(v) and np.isfinite(g).all() and np.isfinite(h).all() for v, g, h in want):
+                    continue
+                agree(name, tad.scalar_case(name, p, c["k"], on_device=True), want, tol=1e-12)
+    rng = np.random.default_rng(5)
+    for name in COMPLEX:
+        for _ in range(4):
+            p = list(rng.uniform(-2.0, 2.0, 4) + np.array([0.0, 0.0, 3.0, 0.0]))
+            agree(name, tad.scalar_case(name, p, 2, on_device=True), oracle.ref_scalar_case(name, p, 2), tol=1e-12)
