@@ -197,7 +197,12 @@ def build_ref(force=False):
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "include", "TinyAD")):
         srcs = [os.path.join(_HERE, f) for f in ("ref_driver.cc", "eigen_shim/Eigen/src/Shim.h", "Makefile")]
         if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            subprocess.run(["make", "-C", _HERE, "_ref/libtinyad_ref.so"], check=True, capture_output=True)
+            try:
+                subprocess.run(["make", "-C", _HERE, "_ref/libtinyad_ref.so"], check=True, capture_output=True)
+            except (subprocess.CalledProcessError, OSError) as e:      # the checker's checker is optional: tests that need it skip
+                import warnings
+                warnings.warn(f"oracle/_ref could not be built: {getattr(e, 'stderr', b'')[-400:]!r}")
+                return None
     return so if os.path.exists(so) else None
 
 
@@ -222,7 +227,12 @@ def build_ref_tests(force=False):
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "tests")):
         srcs = [os.path.join(_HERE, f) for f in ("ref_tests_main.cc", "eigen_shim/Eigen/src/Shim.h", "gtest_shim/gtest/gtest.h", "Makefile")]
         if force or not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
-            subprocess.run(["make", "-j8", "-C", _HERE, "_ref/reference_tests"], check=True, capture_output=True)
+            try:
+                subprocess.run(["make", "-j8", "-C", _HERE, "_ref/reference_tests"], check=True, capture_output=True)
+            except (subprocess.CalledProcessError, OSError) as e:
+                import warnings
+                warnings.warn(f"oracle/_ref/reference_tests could not be built: {getattr(e, 'stderr', b'')[-400:]!r}")
+                return None
             import shutil
             shutil.rmtree(os.path.join(_HERE, "_ref", "obj"), ignore_errors=True)   # 14 MB of objects: keep the snapshot small
     return exe if os.path.exists(exe) else None
