@@ -46,3 +46,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".hh", ".cuh", ".cu", ".h")):
                 src = open(os.path.join(base, f), errors="ignore").read()
                 assert "import oracle" not in src and "oracle/" not in src.replace("tests/oracle", ""), os.path.join(base, f)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/tinyad_b200.h must compile as C99 (-pedantic) and as C++17, with no other include path."""
+    import subprocess
+    import tempfile
+    inc = os.path.join(ROOT, "include")
+    with tempfile.TemporaryDirectory() as d:
+        for name, compiler, std in (("abi.c", "/usr/bin/gcc", "-std=c99"), ("abi.cc", "/usr/bin/g++", "-std=c++17")):
+            path = os.path.join(d, name)
+            with open(path, "w") as fh:
+                fh.write('#include "tinyad_b200.h"\nint main(void) { tad_function* f = 0; (void)f; return (int)TAD_OK; }\n')
+            p = subprocess.run([compiler, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", path], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
