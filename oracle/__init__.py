@@ -349,6 +349,96 @@ def ref_scalar_case(name, params, k, n_out_max=3):
     return res
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref/libtinyad_plugin.so: the reference's ScalarFunction with include/reference_binding/B200ObjectiveTerm.hh plugged
+# into its objective_terms (oracle/ref_plugin_driver.cc) -- the drop-in exercised from the reference's side.
+# ---------------------------------------------------------------------------------------------------------------------
+_PLUGIN = None
+
+
+class _PluginTerm(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("n_elements", ctypes.c_int64), ("conn", ctypes.c_void_p), ("data", ctypes.c_void_p),
+                ("n_data", ctypes.c_int), ("valence", ctypes.c_int)]
+
+
+def plugin_path():
+    return os.path.join(_HERE, "_ref", "libtinyad_plugin.so")
+
+
+def build_plugin(force=False):
+    """Needs /root/reference and the built product libraries (python -m tinyad_b200.build); elsewhere the prebuilt file is used."""
+    so = plugin_path()
+    product = os.path.join(os.path.dirname(_HERE), "tinyad_b200", "libtinyad_b200.so")
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "include", "TinyAD")) and os.path.exists(product):
+        srcs = [os.path.join(_HERE, f) for f in ("ref_plugin_driver.cc", "eigen_shim/Eigen/src/Shim.h", "Makefile",
+                                                 "../include/reference_binding/B200ObjectiveTerm.hh", "../include/tinyad_b200.h")]
+        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            try:
+                subprocess.run(["make", "-C", _HERE, "_ref/libtinyad_plugin.so"], check=True, capture_output=True)
+            except (subprocess.CalledProcessError, OSError) as e:
+                import warnings
+                warnings.warn(f"oracle/_ref/libtinyad_plugin.so could not be built: {getattr(e, 'stderr', b'')[-400:]!r}")
+                return None
+    return so if os.path.exists(so) else None
+
+
+def plugin_lib():
+    global _PLUGIN
+    if _PLUGIN is None:
+        so = build_plugin()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libtinyad_plugin.so is not built (make -C oracle _ref/libtinyad_plugin.so)")
+        L = ctypes.CDLL(so)
+        L.plugin_scalar_eval.restype = ctypes.c_void_p
+        L.plugin_scalar_eval.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_double]
+        L.plugin_last_error.restype = ctypes.c_char_p
+        L.plugin_result_f.restype = ctypes.c_double
+        L.plugin_result_f.argtypes = [ctypes.c_void_p]
+        for n in ("nnz", "cols", "g_size"):
+            f = getattr(L, "plugin_result_" + n)
+            f.restype = ctypes.c_int64
+            f.argtypes = [ctypes.c_void_p]
+        L.plugin_result_copy.argtypes = [ctypes.c_void_p] * 5
+        L.plugin_result_free.argtypes = [ctypes.c_void_p]
+        _PLUGIN = L
+    return _PLUGIN
+
+
+def plugin_scalar_eval(d, n_vertices, terms, mode, x, eps=1e-9, assembly=0):
+    """TinyAD::ScalarFunction::eval* of the REFERENCE with a B200ScalarObjectiveTerm in its objective_terms: the element functors
+    run on cuda:0 through the product's C ABI, everything above the term interface is the reference's own code."""
+    L = plugin_lib()
+    keep = []
+    arr = (_PluginTerm * len(terms))()
+    for i, t in enumerate(terms):
+        conn = np.ascontiguousarray(t.conn, dtype=np.int32).reshape(len(t.conn), -1)
+        data = np.ascontiguousarray(t.data, dtype=np.float64).reshape(len(t.conn), -1)
+        keep += [conn, data]
+        arr[i] = _PluginTerm(t.kind, conn.shape[0], conn.ctypes.data, data.ctypes.data, data.shape[1], conn.shape[1])
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    assert x.size == d * n_vertices
+    h = L.plugin_scalar_eval(d, n_vertices, len(terms), ctypes.addressof(arr), assembly, mode, x.ctypes.data, eps)
+    if not h:
+        raise RuntimeError(L.plugin_last_error().decode())
+    try:
+        res = Result(f=L.plugin_result_f(h))
+        res.g = np.empty(L.plugin_result_g_size(h))
+        res.r = np.empty(0)
+        cols, nnz = L.plugin_result_cols(h), L.plugin_result_nnz(h)
+        res.shape = (cols, cols)
+        want = mode >= 2
+        if want:
+            res.outer = np.empty(cols + 1, dtype=np.int32)
+            res.inner = np.empty(nnz, dtype=np.int32)
+            res.values = np.empty(nnz)
+        L.plugin_result_copy(h, res.g.ctypes.data, res.outer.ctypes.data if want else None, res.inner.ctypes.data if want else None,
+                             res.values.ctypes.data if want else None)
+        return res
+    finally:
+        L.plugin_result_free(h)
+
+
 def ref_project(H, eps=1e-9):
     """TinyAD::project_positive_definite of the reference on one dense symmetric matrix."""
     A = np.array(H, dtype=np.float64, order="C")
