@@ -244,7 +244,13 @@ def run_ref_tests(name_filter=None, skip=REF_TESTS_SKIPPED, timeout=600):
     if exe is None:
         raise RuntimeError("oracle/_ref/reference_tests is not built (make -C oracle _ref/reference_tests, needs /root/reference)")
     cmd = [exe] + (["--skip=" + ",".join(skip)] if skip else []) + ([name_filter] if name_filter else [])
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    env = dict(os.environ)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    env["OMP_NUM_THREADS"] = str(max(2, cores))      # tests/OpenMPTest.cc:24 asserts omp_get_max_threads() >= 2, whatever the caller exported
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     return p.returncode, p.stdout + p.stderr
 
 
