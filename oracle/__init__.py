@@ -84,8 +84,10 @@ def _terms_array(terms):
     keep = []
     arr = (_Term * len(terms))()
     for i, t in enumerate(terms):
-        conn = np.ascontiguousarray(t.conn, dtype=np.int32).reshape(len(t.conn), -1)
-        data = np.ascontiguousarray(t.data, dtype=np.float64).reshape(len(t.conn), -1)
+        conn = np.ascontiguousarray(t.conn, dtype=np.int32)
+        data = np.ascontiguousarray(t.data, dtype=np.float64)
+        conn = conn if conn.ndim == 2 else conn.reshape(len(conn), -1)     # (0, valence) stays what it is: an empty element range
+        data = data if data.ndim == 2 else data.reshape(len(conn), -1)
         keep += [conn, data]
         arr[i] = _Term(t.kind, conn.shape[0], conn.ctypes.data, data.ctypes.data, data.shape[1])
     return arr, keep

@@ -215,3 +215,31 @@ def test_project_positive_definite(k):
             if clearly_kept or (np.diag(H) >= np.abs(H).sum(axis=1) - np.abs(np.diag(H)) + eps).all():
                 assert np.array_equal(b, H)                    # untouched (HessianProjection.hh:62-63 and :92-93)
             assert np.abs(b - (Q * w2) @ Q.T).max() <= 1e-12 * scale
+
+
+def test_edge_cases_and_error_behaviour():
+    """Empty element range, a function without terms, and the two run-time errors of the path: an out-of-range variable handle
+    (Detail/Element.hh:160-170) and non-finite derivatives (Detail/ScalarObjectiveTerm.hh:250-253) throw in both."""
+    V, F = meshes.grid_2d(3)
+    x = V.reshape(-1).copy()
+    nv = len(V)
+    empty = [oracle.Term(oracle.SYMDIRICHLET2D, np.zeros((0, 3), dtype=np.int32), np.zeros((0, 5)))]
+    for terms in (empty, []):
+        for mode in range(4):
+            a = oracle.scalar_eval(2, nv, terms, mode, x)
+            b = oracle.ref_scalar_eval(2, nv, terms, mode, x)
+            assert a.f == b.f == 0.0
+            if mode >= 1:
+                assert np.array_equal(a.g, b.g) and not a.g.any() and len(a.g) == 2 * nv
+            if mode >= 2:
+                assert a.shape == b.shape == (2 * nv, 2 * nv) and len(a.inner) == len(b.inner) == 0 and np.array_equal(a.outer, b.outer)
+    bad = [oracle.Term(oracle.PENALTY2D, np.array([[nv]], dtype=np.int32), np.zeros((1, 2)))]
+    xn = x.copy()
+    xn[3] = np.nan
+    good = [oracle.Term(oracle.SYMDIRICHLET2D, F, meshes.tri_rest_data(V, F))]
+    for fn in (oracle.scalar_eval, oracle.ref_scalar_eval):
+        with pytest.raises(RuntimeError):
+            fn(2, nv, bad, oracle.HESSIAN_PROJ, x)
+        with pytest.raises(RuntimeError):
+            fn(2, nv, good, oracle.HESSIAN_PROJ, xn)
+        assert np.isnan(fn(2, nv, good, oracle.EVAL, xn).f)           # the passive pass does not check (ScalarObjectiveTerm.hh:162-187)
